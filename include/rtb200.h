@@ -1,0 +1,194 @@
+/* rtb200.h — C ABI of librtb200.so, the B200-native (sm_100a) replacement for the per-pixel
+ * radiance loop of SuneelFreimuth/raytracer-server.
+ *
+ * The reference has no FFI; its seam is three Rust signatures (citations relative to the
+ * reference tree).  Each entry point below names the one it stands in for:
+ *
+ *   Scene::from_toml<R: Read>(&mut R) -> Result<Scene, LoadTomlError>      src/scene.rs:143-150
+ *   sample_pixel(x, y, width, height, samples_per_pixel, &Scene) -> Vec3    src/server.rs:320-364
+ *   RenderJob::run(&self, &Scene, width, height, spp) -> bool               src/server.rs:157-199
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All functions return RTB_OK (0) or a
+ * negative error code and set a thread-local message readable with rtb_last_error().
+ * A scene handle is immutable after creation and may be shared by host threads; every render
+ * call / job owns its own CUDA stream and scratch buffers.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with RTB_ECUDA.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_ABI_VERSION 1
+
+/* error codes — LoadTomlError::{Io,Parse,MeshLoad} (src/scene.rs:350-355) plus the reference's
+ * panics turned into codes: no emitter = unreachable!() (src/scene.rs:136); plane light =
+ * unimplemented!() (src/geometry.rs:593). */
+enum {
+    RTB_OK = 0,
+    RTB_EIO = -1,
+    RTB_EPARSE = -2,
+    RTB_EMESH = -3,
+    RTB_ENOLIGHT = -4,
+    RTB_EUNSUPPORTED = -5,
+    RTB_ECUDA = -6,
+    RTB_EINVAL = -7,
+    RTB_ECANCELLED = 1 /* RenderJob::run returns true when stopped early (src/server.rs:198) */
+};
+
+typedef struct rtb_scene rtb_scene;
+typedef struct rtb_job rtb_job;
+
+/* estimator selection (src/scene.rs:187-229) */
+#define RTB_EST_NEE 0      /* live branch: next-event estimation, src/scene.rs:217-229 */
+#define RTB_EST_MIS_DEAD 1 /* the `if false` "MIS" branch verbatim, src/scene.rs:189-216 */
+
+/* Render request.  spp has the reference's meaning: spp/4 samples in each of 2x2 sub-pixels
+ * (src/server.rs:332), so spp < 4 renders black.  (rank, world) select an interleaved tile
+ * shard: this call renders the 32x32 tiles t with t % world == rank (world = 1: whole frame). */
+typedef struct rtb_params {
+    int32_t width;
+    int32_t height;
+    int32_t spp;
+    int32_t estimator; /* RTB_EST_* ("use_mis" of the orphaned config.toml:5) */
+    uint64_t seed;     /* Philox key; the reference is unseeded (rand::random) */
+    int32_t rank;
+    int32_t world;
+    int32_t pool_paths; /* in-flight path slots; 0 = default */
+    int32_t reserved[5];
+} rtb_params;
+
+typedef struct rtb_scene_info {
+    int32_t n_objects;
+    int32_t n_planes;
+    int32_t n_spheres;
+    int32_t n_meshes;
+    int32_t n_triangles;
+    int32_t light_object; /* Scene::light_source, src/scene.rs:129-137 */
+    int32_t bvh_nodes;
+    int32_t bvh_leaves;
+    int32_t device;
+    int32_t reserved[3];
+    float bvh_min[3];
+    float bvh_max[3];
+    float camera_pos[3];
+    float camera_dir[3];
+    double build_ms; /* device LBVH build */
+} rtb_scene_info;
+
+/* one object as the loader built it (f64, after transforms) — Object / Geometry, src/scene.rs:10-15 */
+typedef struct rtb_object_info {
+    int32_t brdf;          /* 0 diffuse, 1 specular, 2 phong */
+    int32_t geometry;      /* 0 sphere, 1 plane, 2 mesh (cube / prism / OBJ) */
+    int32_t n_triangles;
+    int32_t first_triangle; /* global triangle index of the mesh's first triangle, or -1 */
+    double emitted[3];
+    double k[3];           /* kd | ks | phong {kd, ks, power} */
+    double color_d[3];
+    double color_s[3];
+    double pos[3];
+    double n[3];
+    double r;
+    double bb_min[3];      /* Mesh::bounding_box incl. the scale() quirk (src/geometry.rs:503-506) */
+    double bb_max[3];
+    double surface_area;   /* Mesh::surface_area: computed before the transforms, never refreshed */
+} rtb_object_info;
+
+/* counters of the last finished render / job — counted on the device, never inferred */
+typedef struct rtb_stats {
+    uint64_t samples;        /* received_radiance calls */
+    uint64_t rays_primary;   /* trace_ray calls, by kind */
+    uint64_t rays_extension;
+    uint64_t rays_shadow;
+    uint64_t iterations;     /* wavefront iterations */
+    uint64_t kernel_launches;
+    uint64_t bvh_node_visits; /* only filled by counting builds (rtb_trace_* with count_work) */
+    uint64_t bvh_tri_tests;
+    double render_ms;        /* CUDA-event time of the whole device-side render */
+    double extend_ms;        /* CUDA-event time of the traversal+shade kernel, summed */
+    double shadow_ms;
+    double generate_ms;
+    double resolve_ms;
+} rtb_stats;
+
+/* ---- scene: Scene::from_toml + SceneSpec::to_scene (src/scene.rs:143-150, 357-441) ---------
+ * Same TOML grammar and semantics: transform order, bbox-centre pivots and the scale() bbox
+ * quirk (src/geometry.rs:445-510), first-emitter light rule, OBJ subset (v / f a/b/c, triangles
+ * only, src/geometry.rs:777-833).  Mesh paths resolve against assets_dir (the reference uses
+ * <argv[1]>/assets, src/scene.rs:405).  `device` is the CUDA ordinal that will own the scene;
+ * device = -1 creates a host-only handle (loader checks on machines without a GPU): info / object /
+ * triangle queries work, every compute entry point fails with RTB_ECUDA. */
+int rtb_scene_load_toml(const char* toml_path, const char* assets_dir, int device, rtb_scene** out);
+int rtb_scene_load_toml_string(const char* toml_text, const char* assets_dir, int device, rtb_scene** out);
+void rtb_scene_destroy(rtb_scene* scene);
+int rtb_scene_get_info(const rtb_scene* scene, rtb_scene_info* info);
+int rtb_scene_object(const rtb_scene* scene, int32_t index, rtb_object_info* out);
+/* re-copy the flattened host scene (pinned) to the device; returns bytes copied via *bytes */
+int rtb_scene_upload(rtb_scene* scene, uint64_t* bytes);
+/* host-side view of the loader result, for cross-checks: triangles as 9 floats each (a,b,c) in
+ * global triangle order; returns the count (call with cap = 0 to query) */
+int64_t rtb_scene_triangles(const rtb_scene* scene, float* out9, int64_t cap);
+
+const char* rtb_last_error(void);
+
+/* ---- whole frame: what RenderJob::run has sent once all messages are out -------------------
+ * rgb8_out: height*width*3 bytes, row 0 = top of the screen (message row y), exactly the bytes
+ * of src/server.rs:187-189.  With world > 1 only this rank's tiles are written (others left
+ * untouched).  `cancel` (may be NULL) is polled between wavefront iterations; returns
+ * RTB_ECANCELLED if it became non-zero (src/server.rs:170, 198). */
+int rtb_render(rtb_scene* scene, const rtb_params* params, uint8_t* rgb8_out, volatile int* cancel);
+
+/* device-resident variants (bench `value`, multi-GPU gather): the result stays in device memory
+ * owned by the caller.  d_rgb8_tiles receives this rank's pixels in tile order
+ * (rtb_local_pixels() * 3 bytes); d_subpixel_sums (optional) receives the fp32 sums of the four
+ * sub-pixels as float4 {r,g,b,0} per (pixel, sub-pixel), same order.  Synchronous on return. */
+int64_t rtb_local_pixels(const rtb_params* params);
+int rtb_render_device(rtb_scene* scene, const rtb_params* params, void* d_rgb8_tiles, void* d_subpixel_sums,
+                      volatile int* cancel);
+/* scatter `world` tile-ordered shards (concatenated, each rtb_local_pixels(rank r)*3 bytes padded
+ * to shard_stride bytes) into a scan-line frame; all pointers are device pointers */
+int rtb_untile_device(const rtb_params* params, const void* d_shards, int64_t shard_stride, void* d_rgb8_frame,
+                      int device);
+
+/* counters of the last render on this scene handle by the calling thread's most recent call */
+int rtb_get_stats(const rtb_scene* scene, rtb_stats* stats);
+
+/* ---- streaming job: the message loop of RenderJob::run (src/server.rs:166-194) -------------
+ * rtb_job_next yields records in the reference's wire shape: screen column x, screen row y
+ * (top-down), n <= 60 pixels, n*3 bytes of rgb.  Returns 1 while records remain, 0 when the
+ * frame is complete, RTB_ECANCELLED after rtb_job_cancel.  Progressive mode (passes > 1, not in
+ * the reference) re-sends every record once per pass with the running estimate. */
+int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rtb_job** out);
+int rtb_job_next(rtb_job* job, uint16_t* x, uint16_t* y, uint8_t* n, uint8_t* rgb /* >= 180 bytes */);
+/* bulk form: up to max_records records packed exactly like the reference's binary messages,
+ * [0]=0 type, [1]=n, [2..4]=x u16le, [4..6]=y u16le, then n*(r,g,b) (src/server.rs:173-190);
+ * each record occupies 6+3n bytes back to back.  Returns the number of records written. */
+int rtb_job_next_messages(rtb_job* job, uint8_t* buf, int64_t buf_bytes, int32_t max_records, int64_t* bytes_written);
+int rtb_job_cancel(rtb_job* job);
+int rtb_job_end(rtb_job* job);
+
+/* ---- parity hooks (no RNG) ------------------------------------------------------------------
+ * Scene::trace_ray (src/scene.rs:272-289) on explicit rays.  obj = object index or -1, tri =
+ * triangle index inside that object's mesh or -1, t = hit distance.  rtb_trace_primary builds the
+ * camera rays of src/server.rs:353-357 for every pixel (row 0 = top) at a fixed sub-pixel
+ * (sx, sy) and jitter (dx, dy).  work2 (optional) receives {bvh node visits, triangle tests}. */
+int rtb_trace_primary(rtb_scene* scene, int32_t width, int32_t height, int32_t sx, int32_t sy, float dx, float dy,
+                      int32_t* obj, int32_t* tri, float* t);
+int rtb_trace_rays(rtb_scene* scene, int64_t n, const float* org3, const float* dir3, int32_t* obj, int32_t* tri,
+                   float* t, uint64_t* work2);
+/* radiance of explicit (pixel x, screen row y, sample index) camera paths, fp32 rgb — the
+ * path-level probe matching the oracle's or_sample_radiance under the shared RNG contract */
+int rtb_sample_radiance(rtb_scene* scene, const rtb_params* params, int64_t n, const int32_t* px, const int32_t* py,
+                        const int32_t* sample_idx, float* rgb3);
+
+/* FP32 FMA-chain microbenchmark on `device`: measured non-tensor FP32 peak (TFLOP/s) */
+int rtb_fp32_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

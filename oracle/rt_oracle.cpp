@@ -746,9 +746,10 @@ struct Scene {  // src/scene.rs:101-107
         Vec3 rad;
         if (estimator == 1) {  // dead branch :189-216, verbatim (fresh-sample pdfs included)
             Vec3 rad_direct = V(0, 0, 0);
-            double b2[4], b3[4];
-            s.block((uint32_t)depth, 2, b2);
-            s.block((uint32_t)depth, 3, b3);
+            double b2[4], b3[4], b4[4];
+            s.block((uint32_t)depth, 2, b2);  // fresh BRDF sample used only for its pdf (:195)
+            s.block((uint32_t)depth, 3, b3);  // second light point (:206)
+            s.block((uint32_t)depth, 4, b4);  // this branch's own BRDF sample (:203), independent of the continuation's
             Vec3 y, ny;
             double pdf_light;
             light_sample(b0, y, ny, pdf_light);
@@ -763,7 +764,7 @@ struct Scene {  // src/scene.rs:101-107
             }
             Vec3 i2;
             double pdf_brdf2;
-            brdf_sample(obj.brdf, n, o, b1, i2, pdf_brdf2);
+            brdf_sample(obj.brdf, n, o, b4, i2, pdf_brdf2);
             Hit h2{};
             if (trace_ray(Ray{x, i2}, h2, cnt)) {
                 if (h2.id == light_source) {

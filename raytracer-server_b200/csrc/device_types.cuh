@@ -1,0 +1,89 @@
+// device_types.cuh — device-side scene layout (structure of arrays, fp32) and small math helpers.
+//
+// Replaces the reference's AoS f64 scene graph (Object / Geometry / Mesh / Octree,
+// src/scene.rs:10-28,101-107, src/geometry.rs:371-424,1133-1143):
+//   * analytic primitives (planes, spheres) and per-object materials: small tables that every
+//     CTA stages into shared memory once (broadcast reads in the inner loops);
+//   * all mesh triangles of all objects: one LBVH (lbvh.cu), 64-byte nodes holding both child
+//     boxes, triangles in leaf order as three float4 (v0|1/|N|, e1|global tri id, e2|object id).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtb {
+
+// ---------------------------------------------------------------- primitive codes
+// pcode: bit31 = hit normal flipped w.r.t. the geometric normal, bit30 = previous vertex was
+// specular (emission + ks/p still to be applied), bit29 = `o` is stale (reference quirk,
+// src/scene.rs:178), bits 0..28 = id: analytic primitive index (< TRI_BASE) or TRI_BASE + leaf slot.
+constexpr uint32_t PC_FLIPPED = 0x80000000u;
+constexpr uint32_t PC_SPEC_PENDING = 0x40000000u;
+constexpr uint32_t PC_STALE_O = 0x20000000u;
+constexpr uint32_t PC_ID_MASK = 0x1fffffffu;
+constexpr uint32_t PC_NONE = 0x1fffffffu;
+constexpr uint32_t TRI_BASE = 256u;  // == MAX_OBJECTS
+
+struct DevPrim {      // 48 B, mirrors FlatPrim
+    float4 a;         // plane: n.xyz, dot(pos,n)   sphere: c.xyz, r
+    float4 b;         // plane: pos.xyz             sphere: r*r
+    int32_t type, obj, group, pad;
+};
+
+struct DevMaterial {  // 80 B, mirrors FlatMaterial
+    float4 emitted;
+    float4 k;
+    float4 color_d;
+    float4 color_s;
+    int32_t brdf, geom, first_tri, n_tri;
+};
+
+struct DevSceneHeader {  // lives in global memory; one per scene
+    float cam_pos[3];
+    float cam_dir[3];
+    int32_t n_prims;
+    int32_t n_objects;
+    int32_t light_obj;
+    int32_t light_geom;    // GEOM_*
+    int32_t light_prim;    // analytic index of the light when it is a sphere
+    int32_t light_first_tri, light_n_tri;
+    float light_area;      // Mesh::surface_area of the UNTRANSFORMED mesh (reference quirk)
+    int32_t n_tris;
+    int32_t root;          // encoded BVH root reference (inner >= 0, leaf < 0), valid if n_tris > 0
+    float bvh_min[3];
+    float bvh_max[3];
+};
+
+struct DevScene {          // passed to kernels by value
+    const DevSceneHeader* hdr;
+    const DevPrim* prims;
+    const DevMaterial* mats;
+    const float4* nodes;   // 4 x float4 per node
+    const float4* tris;    // 3 x float4 per triangle, leaf order
+    const float* light_cdf;
+    const float4* tri_orig; // 3 x float4 per triangle in GLOBAL order: a, b, c (mesh-light sampling)
+    int32_t n_prims, n_objects, n_tris, root;
+    float3 bvh_min, bvh_max;
+};
+
+// ---------------------------------------------------------------- float3 helpers
+__host__ __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__host__ __device__ __forceinline__ float3 f3(const float4& v) { return make_float3(v.x, v.y, v.z); }
+__host__ __device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__host__ __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__host__ __device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ __forceinline__ float3 cross(float3 a, float3 b) {
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize(float3 a) {
+    float inv = rsqrtf(dot(a, a));
+    return a * inv;
+}
+// Vec3::flip_across (src/geometry.rs:99-101)
+__device__ __forceinline__ float3 flip_across(float3 s, float3 axis) { return (2.0f * dot(s, axis)) * axis - s; }
+
+}  // namespace rtb

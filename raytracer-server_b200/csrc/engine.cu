@@ -1,0 +1,1035 @@
+// engine.cu — host runtime of librtb200.so: scene upload, render contexts, the wavefront launch
+// loop, streaming jobs and the C ABI declared in include/rtb200.h.
+//
+// Stands in for the reference's callers of the hot path: Scene::from_toml (src/scene.rs:143-150),
+// RenderJob::run (src/server.rs:157-199) and sample_pixel (src/server.rs:320-364).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/rtb200.h"
+#include "lbvh.hpp"
+#include "scene_host.hpp"
+#include "wavefront.cuh"
+
+using namespace rtb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CU_TRY(x)                                                                                           \
+    do {                                                                                                    \
+        cudaError_t e_ = (x);                                                                               \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(RTB_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+static_assert(sizeof(FlatPrim) == sizeof(DevPrim), "FlatPrim/DevPrim layout");
+static_assert(sizeof(FlatMaterial) == sizeof(DevMaterial), "FlatMaterial/DevMaterial layout");
+static_assert(sizeof(DevPrim) == 48 && sizeof(DevMaterial) == 80, "16-byte multiples expected by stage_scene");
+static_assert(MAX_OBJECTS == (int)TRI_BASE, "primitive code space");
+
+struct RenderContext {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    uint32_t P = 0, SP = 0;
+    float4* qbuf = nullptr;      // 2 queues x 4 arrays x P
+    float4* sbuf = nullptr;      // 3 arrays x SP
+    float4* accum = nullptr;
+    size_t accum_cap = 0;
+    DevCtrl* ctrl = nullptr;
+    uint32_t* h_active = nullptr;  // pinned ring of read-backs
+    static constexpr int RING = 16;
+    cudaEvent_t ring_ev[RING] = {};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ext_ev;  // start/stop pairs around every k_extend_shade launch
+    unsigned char* d_rgb = nullptr;
+    size_t rgb_cap = 0;
+    unsigned char* h_rgb = nullptr;   // pinned
+    size_t h_rgb_cap = 0;
+    int32_t* d_probe = nullptr;
+    size_t probe_cap = 0;
+    int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0;
+
+    ~RenderContext() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        cudaFree(qbuf); cudaFree(sbuf); cudaFree(accum); cudaFree(ctrl); cudaFree(d_rgb); cudaFree(d_probe);
+        if (h_active) cudaFreeHost(h_active);
+        if (h_rgb) cudaFreeHost(h_rgb);
+        for (auto& e : ring_ev) if (e) cudaEventDestroy(e);
+        for (auto& e : ext_ev) cudaEventDestroy(e);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+};
+
+}  // namespace
+
+struct rtb_scene {
+    HostScene hs;
+    FlatScene fs;
+    int device = 0;
+    DevSceneHeader h_hdr{};
+    // one pinned staging block: header | prims | materials | triangle vertices | tri_obj | light cdf
+    unsigned char* h_stage = nullptr;
+    unsigned char* d_stage = nullptr;
+    size_t stage_bytes = 0;
+    size_t off_prims = 0, off_mats = 0, off_verts = 0, off_triobj = 0, off_cdf = 0;
+    float4* d_tri_orig = nullptr;
+    LbvhResult bvh;
+    DevScene view{};
+    rtb_scene_info info{};
+    std::mutex mu;
+    std::vector<RenderContext*> pool;
+    rtb_stats last_stats{};
+    cudaStream_t stream = nullptr;
+
+    ~rtb_scene() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        for (auto* c : pool) delete c;
+        free_lbvh(bvh);
+        cudaFree(d_stage);
+        cudaFree(d_tri_orig);
+        if (h_stage) cudaFreeHost(h_stage);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__global__ void k_tri_orig(const float* __restrict__ verts, int n, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* v = verts + (size_t)i * 9;
+    out[3 * i] = make_float4(v[0], v[1], v[2], 0.f);
+    out[3 * i + 1] = make_float4(v[3], v[4], v[5], 0.f);
+    out[3 * i + 2] = make_float4(v[6], v[7], v[8], 0.f);
+}
+
+int upload_scene(rtb_scene* sc, uint64_t* bytes) {
+    CU_TRY(cudaSetDevice(sc->device));
+    CU_TRY(cudaMemcpyAsync(sc->d_stage, sc->h_stage, sc->stage_bytes, cudaMemcpyHostToDevice, sc->stream));
+    CU_TRY(cudaStreamSynchronize(sc->stream));
+    if (bytes) *bytes = sc->stage_bytes;
+    return RTB_OK;
+}
+
+int build_device_scene(rtb_scene* sc) {
+    const FlatScene& fs = sc->fs;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(RTB_ECUDA, std::string("no CUDA device (librtb200 has no CPU fallback): ") + cudaGetErrorString(e));
+    if (sc->device < 0 || sc->device >= ndev) return fail(RTB_EINVAL, "device ordinal out of range");
+    CU_TRY(cudaSetDevice(sc->device));
+    CU_TRY(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+
+    const int n_tris = (int)fs.tri_obj.size();
+    sc->off_prims = align_up(sizeof(DevSceneHeader), 256);
+    sc->off_mats = align_up(sc->off_prims + fs.prims.size() * sizeof(DevPrim), 256);
+    sc->off_verts = align_up(sc->off_mats + fs.materials.size() * sizeof(DevMaterial), 256);
+    sc->off_triobj = align_up(sc->off_verts + fs.tri_verts.size() * sizeof(float), 256);
+    sc->off_cdf = align_up(sc->off_triobj + fs.tri_obj.size() * sizeof(int32_t), 256);
+    sc->stage_bytes = align_up(sc->off_cdf + fs.light_cdf.size() * sizeof(float), 256);
+    CU_TRY(cudaMallocHost((void**)&sc->h_stage, sc->stage_bytes));
+    CU_TRY(cudaMalloc((void**)&sc->d_stage, sc->stage_bytes));
+    std::memset(sc->h_stage, 0, sc->stage_bytes);
+    if (!fs.prims.empty()) std::memcpy(sc->h_stage + sc->off_prims, fs.prims.data(), fs.prims.size() * sizeof(DevPrim));
+    std::memcpy(sc->h_stage + sc->off_mats, fs.materials.data(), fs.materials.size() * sizeof(DevMaterial));
+    if (n_tris) {
+        std::memcpy(sc->h_stage + sc->off_verts, fs.tri_verts.data(), fs.tri_verts.size() * sizeof(float));
+        std::memcpy(sc->h_stage + sc->off_triobj, fs.tri_obj.data(), fs.tri_obj.size() * sizeof(int32_t));
+    }
+    if (!fs.light_cdf.empty()) std::memcpy(sc->h_stage + sc->off_cdf, fs.light_cdf.data(), fs.light_cdf.size() * sizeof(float));
+
+    // geometry first (the header needs the BVH root and box)
+    CU_TRY(cudaMemcpyAsync(sc->d_stage, sc->h_stage, sc->stage_bytes, cudaMemcpyHostToDevice, sc->stream));
+    const float* d_verts = reinterpret_cast<const float*>(sc->d_stage + sc->off_verts);
+    const int32_t* d_triobj = reinterpret_cast<const int32_t*>(sc->d_stage + sc->off_triobj);
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    CU_TRY(cudaEventRecord(e0, sc->stream));
+    std::string err;
+    if (!build_lbvh(d_verts, d_triobj, n_tris, sc->stream, sc->bvh, err)) return fail(RTB_ECUDA, err);
+    if (n_tris) {
+        CU_TRY(cudaMalloc((void**)&sc->d_tri_orig, (size_t)n_tris * 3 * sizeof(float4)));
+        k_tri_orig<<<(n_tris + 255) / 256, 256, 0, sc->stream>>>(d_verts, n_tris, sc->d_tri_orig);
+    }
+    CU_TRY(cudaEventRecord(e1, sc->stream));
+    CU_TRY(cudaStreamSynchronize(sc->stream));
+    float build_ms = 0;
+    CU_TRY(cudaEventElapsedTime(&build_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+
+    DevSceneHeader& H = sc->h_hdr;
+    std::memset(&H, 0, sizeof(H));
+    for (int k = 0; k < 3; ++k) {
+        H.cam_pos[k] = fs.cam_pos[k];
+        H.cam_dir[k] = fs.cam_dir[k];
+        H.bvh_min[k] = sc->bvh.bmin[k];
+        H.bvh_max[k] = sc->bvh.bmax[k];
+    }
+    H.n_prims = (int)fs.prims.size();
+    H.n_objects = fs.n_objects;
+    H.light_obj = fs.light_obj;
+    H.light_geom = fs.light_geom;
+    H.light_prim = -1;
+    for (size_t k = 0; k < fs.prims.size(); ++k)
+        if (fs.prims[k].obj == fs.light_obj) H.light_prim = (int)k;
+    H.light_first_tri = fs.materials[fs.light_obj].first_tri;
+    H.light_n_tri = fs.materials[fs.light_obj].n_tri;
+    H.light_area = fs.light_area;
+    H.n_tris = n_tris;
+    H.root = sc->bvh.root;
+    std::memcpy(sc->h_stage, &H, sizeof(H));
+    CU_TRY(cudaMemcpyAsync(sc->d_stage, sc->h_stage, sizeof(H), cudaMemcpyHostToDevice, sc->stream));
+    CU_TRY(cudaStreamSynchronize(sc->stream));
+
+    DevScene& V = sc->view;
+    V.hdr = reinterpret_cast<const DevSceneHeader*>(sc->d_stage);
+    V.prims = reinterpret_cast<const DevPrim*>(sc->d_stage + sc->off_prims);
+    V.mats = reinterpret_cast<const DevMaterial*>(sc->d_stage + sc->off_mats);
+    V.nodes = sc->bvh.d_nodes;
+    V.tris = sc->bvh.d_tris;
+    V.light_cdf = reinterpret_cast<const float*>(sc->d_stage + sc->off_cdf);
+    V.tri_orig = sc->d_tri_orig;
+    V.n_prims = H.n_prims;
+    V.n_objects = H.n_objects;
+    V.n_tris = n_tris;
+    V.root = H.root;
+    V.bvh_min = make_float3(H.bvh_min[0], H.bvh_min[1], H.bvh_min[2]);
+    V.bvh_max = make_float3(H.bvh_max[0], H.bvh_max[1], H.bvh_max[2]);
+
+    rtb_scene_info& I = sc->info;
+    std::memset(&I, 0, sizeof(I));
+    I.n_objects = fs.n_objects;
+    I.n_planes = fs.n_planes;
+    I.n_spheres = fs.n_spheres;
+    I.n_meshes = fs.n_meshes;
+    I.n_triangles = n_tris;
+    I.light_object = fs.light_obj;
+    I.bvh_nodes = sc->bvh.n_nodes;
+    I.bvh_leaves = sc->bvh.n_leaves;
+    I.device = sc->device;
+    for (int k = 0; k < 3; ++k) {
+        I.bvh_min[k] = H.bvh_min[k];
+        I.bvh_max[k] = H.bvh_max[k];
+        I.camera_pos[k] = fs.cam_pos[k];
+        I.camera_dir[k] = fs.cam_dir[k];
+    }
+    I.build_ms = build_ms;
+    return RTB_OK;
+}
+
+int finish_scene(rtb_scene* sc, int rc, const std::string& err, rtb_scene** out) {
+    if (rc != RTB_OK) {
+        delete sc;
+        return fail(rc, err);
+    }
+    std::string e2;
+    rc = flatten_scene(sc->hs, sc->fs, e2);
+    if (rc != RTB_OK) {
+        delete sc;
+        return fail(rc, e2);
+    }
+    if (sc->device < 0) {  // host-only handle (loader checks without a GPU): no device state at all
+        rtb_scene_info& I = sc->info;
+        std::memset(&I, 0, sizeof(I));
+        I.n_objects = sc->fs.n_objects;
+        I.n_planes = sc->fs.n_planes;
+        I.n_spheres = sc->fs.n_spheres;
+        I.n_meshes = sc->fs.n_meshes;
+        I.n_triangles = (int)sc->fs.tri_obj.size();
+        I.light_object = sc->fs.light_obj;
+        I.device = -1;
+        for (int k = 0; k < 3; ++k) { I.camera_pos[k] = sc->fs.cam_pos[k]; I.camera_dir[k] = sc->fs.cam_dir[k]; }
+        *out = sc;
+        return RTB_OK;
+    }
+    rc = build_device_scene(sc);
+    if (rc != RTB_OK) {
+        std::string keep = g_last_error;
+        delete sc;
+        g_last_error = keep;
+        return rc;
+    }
+    *out = sc;
+    return RTB_OK;
+}
+
+// ---------------------------------------------------------------- render contexts
+RenderContext* acquire_context(rtb_scene* sc) {
+    std::lock_guard<std::mutex> lk(sc->mu);
+    if (!sc->pool.empty()) {
+        RenderContext* c = sc->pool.back();
+        sc->pool.pop_back();
+        return c;
+    }
+    RenderContext* c = new RenderContext();
+    c->device = sc->device;
+    return c;
+}
+void release_context(rtb_scene* sc, RenderContext* c) {
+    std::lock_guard<std::mutex> lk(sc->mu);
+    sc->pool.push_back(c);
+}
+
+int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, size_t accum_elems) {
+    CU_TRY(cudaSetDevice(sc->device));
+    if (!c->stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU_TRY(cudaMalloc((void**)&c->ctrl, sizeof(DevCtrl)));
+        CU_TRY(cudaMallocHost((void**)&c->h_active, sizeof(uint32_t) * RenderContext::RING));
+        for (auto& e : c->ring_ev) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreate(&c->ev_begin));
+        CU_TRY(cudaEventCreate(&c->ev_end));
+        const size_t smem = shared_scene_bytes(sc->view.n_prims, sc->view.n_objects, WF_THREADS);
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, sc->device));
+        CU_TRY(cudaFuncSetAttribute(k_extend_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaFuncSetAttribute(k_extend_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int b = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_extend_shade<false>, WF_THREADS, smem));
+        c->grid_ext = std::max(1, b) * prop.multiProcessorCount;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_extend_shade<true>, WF_THREADS, smem));
+        c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false>, WF_THREADS, smem));
+        c->grid_sh = std::max(1, b) * prop.multiProcessorCount;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<true>, WF_THREADS, smem));
+        c->grid_sh_count = std::max(1, b) * prop.multiProcessorCount;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate, WF_THREADS, 0));
+        c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
+    }
+    if (c->P != P) {
+        cudaFree(c->qbuf);
+        c->qbuf = nullptr;
+        CU_TRY(cudaMalloc((void**)&c->qbuf, (size_t)P * 8 * sizeof(float4)));
+        c->P = P;
+    }
+    if (c->SP != SP) {
+        cudaFree(c->sbuf);
+        c->sbuf = nullptr;
+        CU_TRY(cudaMalloc((void**)&c->sbuf, (size_t)SP * 3 * sizeof(float4)));
+        c->SP = SP;
+    }
+    if (c->accum_cap < accum_elems) {
+        cudaFree(c->accum);
+        c->accum = nullptr;
+        CU_TRY(cudaMalloc((void**)&c->accum, accum_elems * sizeof(float4)));
+        c->accum_cap = accum_elems;
+    }
+    return RTB_OK;
+}
+
+int need_device(const rtb_scene* sc) {
+    if (!sc) return fail(RTB_EINVAL, "NULL scene");
+    if (sc->device < 0) return fail(RTB_ECUDA, "host-only scene handle (device = -1): no CUDA device owns it, and there is no CPU fallback");
+    return RTB_OK;
+}
+
+int check_params(const rtb_params* p) {
+    if (!p) return fail(RTB_EINVAL, "params is NULL");
+    if (p->width <= 0 || p->height <= 0 || p->width > 65535 || p->height > 65535)
+        return fail(RTB_EINVAL, "width/height must be in 1..65535 (the wire format carries u16 coordinates)");
+    if (p->spp < 0) return fail(RTB_EINVAL, "spp must be >= 0");
+    if ((long long)p->spp / 4 * 4 >= (1 << 20)) return fail(RTB_EINVAL, "spp too large (sample index field is 20 bits)");
+    if (p->world < 1 || p->rank < 0 || p->rank >= p->world) return fail(RTB_EINVAL, "need 0 <= rank < world");
+    if (p->estimator != RTB_EST_NEE && p->estimator != RTB_EST_MIS_DEAD) return fail(RTB_EINVAL, "unknown estimator");
+    if ((long long)p->width * p->height * 4 >= (1ll << 31)) return fail(RTB_EINVAL, "frame too large for 31-bit accumulator indices");
+    return RTB_OK;
+}
+
+int local_tiles(const rtb_params* p) {
+    int tx = (p->width + TILE - 1) / TILE, ty = (p->height + TILE - 1) / TILE;
+    int T = tx * ty;
+    return T > p->rank ? (T - p->rank + p->world - 1) / p->world : 0;
+}
+
+void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, RenderArgs& a) {
+    std::memset(&a, 0, sizeof(a));
+    a.S = sc->view;
+    a.cam = make_camera(sc->fs.cam_pos, sc->fs.cam_dir, p->width, p->height);
+    a.width = p->width;
+    a.height = p->height;
+    a.spp = p->spp;
+    a.num_samples = p->spp / 4;
+    a.ks_done = (uint32_t)(p->spp / 4) * 4u;
+    a.k0 = (uint32_t)p->seed;
+    a.k1 = (uint32_t)(p->seed >> 32);
+    a.estimator = p->estimator;
+    a.rank = p->rank;
+    a.world = p->world;
+    a.tiles_x = (p->width + TILE - 1) / TILE;
+    a.tiles_y = (p->height + TILE - 1) / TILE;
+    a.n_local_tiles = local_tiles(p);
+    a.P = c->P;
+    a.SP = c->SP;
+    for (int k = 0; k < 2; ++k) {
+        float4* b = c->qbuf + (size_t)k * 4 * c->P;
+        a.q[k].o = b;
+        a.q[k].d = b + c->P;
+        a.q[k].beta = b + 2 * (size_t)c->P;
+        a.q[k].ov = b + 3 * (size_t)c->P;
+    }
+    a.sq.o = c->sbuf;
+    a.sq.d = c->sbuf + c->SP;
+    a.sq.c = c->sbuf + 2 * (size_t)c->SP;
+    a.accum = c->accum;
+    a.ctrl = c->ctrl;
+}
+
+// The wavefront loop: runs samples [ks_begin, ks_end) (ks = k*4 + sub-pixel) of every local pixel,
+// or the n_probe explicit items.  Accumulators are NOT cleared here.
+int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_begin, uint32_t ks_end, bool count_work,
+                  volatile int* cancel, rtb_stats& st, bool& cancelled) {
+    cancelled = false;
+    DevCtrl h{};
+    h.ext_head[0] = h.ext_head[1] = 0;
+    h.ext_tail[0] = h.ext_tail[1] = a.P;
+    h.sh_head = 0;
+    h.sh_tail = a.SP;
+    unsigned long long npl = (unsigned long long)a.n_local_tiles * 1024ull;
+    h.work_next = a.probe_px ? 0ull : (unsigned long long)ks_begin * npl;
+    h.work_total = a.probe_px ? (unsigned long long)a.n_probe : (unsigned long long)ks_end * npl;
+    CU_TRY(cudaMemcpyAsync(c->ctrl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaEventRecord(c->ev_begin, c->stream));
+    const size_t smem = shared_scene_bytes(a.S.n_prims, a.S.n_objects, WF_THREADS);
+    uint64_t launches = 0;
+    size_t ext_pairs = 0;
+    int cur = 0;
+    uint64_t it = 0;
+    bool done = h.work_total == h.work_next;
+    int outstanding = 0;
+    uint64_t oldest = 0;
+    while (!done) {
+        if (cancel && *cancel) { cancelled = true; break; }
+        k_prepare<<<1, 1, 0, c->stream>>>(a, cur);
+        k_generate<<<c->grid_gen, WF_THREADS, 0, c->stream>>>(a, cur);
+        if (c->ext_ev.size() < 2 * (ext_pairs + 1)) {
+            cudaEvent_t e0, e1;
+            CU_TRY(cudaEventCreate(&e0));
+            CU_TRY(cudaEventCreate(&e1));
+            c->ext_ev.push_back(e0);
+            c->ext_ev.push_back(e1);
+        }
+        CU_TRY(cudaEventRecord(c->ext_ev[2 * ext_pairs], c->stream));
+        if (count_work) k_extend_shade<true><<<c->grid_ext_count, WF_THREADS, smem, c->stream>>>(a, cur);
+        else k_extend_shade<false><<<c->grid_ext, WF_THREADS, smem, c->stream>>>(a, cur);
+        CU_TRY(cudaEventRecord(c->ext_ev[2 * ext_pairs + 1], c->stream));
+        ++ext_pairs;
+        if (count_work) k_shadow<true><<<c->grid_sh_count, WF_THREADS, smem, c->stream>>>(a);
+        else k_shadow<false><<<c->grid_sh, WF_THREADS, smem, c->stream>>>(a);
+        launches += 4;
+        // lagged, non-blocking termination test: read back `active` (state after this iteration's
+        // k_prepare) into a pinned ring; the host keeps launching until a completed read-back says 0.
+        int slot = (int)(it % RenderContext::RING);
+        CU_TRY(cudaMemcpyAsync(&c->h_active[slot], &c->ctrl->active, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaEventRecord(c->ring_ev[slot], c->stream));
+        ++outstanding;
+        ++it;
+        cur ^= 1;
+        while (outstanding > 0) {
+            int s = (int)(oldest % RenderContext::RING);
+            cudaError_t q = outstanding >= RenderContext::RING ? cudaEventSynchronize(c->ring_ev[s]) : cudaEventQuery(c->ring_ev[s]);
+            if (q == cudaErrorNotReady) break;
+            if (q != cudaSuccess) return fail(RTB_ECUDA, std::string("wavefront loop: ") + cudaGetErrorString(q));
+            if (c->h_active[s] == 0) done = true;
+            ++oldest;
+            --outstanding;
+        }
+    }
+    CU_TRY(cudaEventRecord(c->ev_end, c->stream));
+    CU_TRY(cudaMemcpyAsync(&h, c->ctrl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
+    double ext_ms = 0;
+    for (size_t k = 0; k < ext_pairs; ++k) {
+        float m = 0;
+        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[2 * k], c->ext_ev[2 * k + 1]));
+        ext_ms += m;
+    }
+    st.samples += h.samples;
+    st.rays_primary += h.rays_primary;
+    st.rays_extension += h.rays_extension - h.rays_primary;
+    st.rays_shadow += h.rays_shadow;
+    st.iterations += h.iterations;
+    st.kernel_launches += launches;
+    st.bvh_node_visits += h.node_visits;
+    st.bvh_tri_tests += h.tri_tests;
+    st.render_ms += ms;
+    st.extend_ms += ext_ms;
+    return RTB_OK;
+}
+
+// full render of this rank's tiles into the context's accumulators, then resolve
+int render_into_context(rtb_scene* sc, const rtb_params* p, RenderContext* c, RenderArgs& a, volatile int* cancel, rtb_stats& st,
+                        bool& cancelled) {
+    uint32_t P = p->pool_paths > 0 ? (uint32_t)p->pool_paths : (1u << 22);
+    P = std::max<uint32_t>(P, 1024u);
+    P = (P + 31u) & ~31u;
+    uint32_t SP = p->estimator == RTB_EST_NEE ? P : 2 * P;
+    size_t accum_elems = (size_t)p->width * p->height * 4;
+    int rc = ensure_context(sc, c, P, SP, accum_elems);
+    if (rc != RTB_OK) return rc;
+    fill_args(sc, p, c, a);
+    CU_TRY(cudaMemsetAsync(c->accum, 0, accum_elems * sizeof(float4), c->stream));
+    st = rtb_stats{};
+    cancelled = false;
+    if (a.num_samples > 0 && a.n_local_tiles > 0) {
+        bool count_work = p->reserved[0] == 1;
+        rc = run_wavefront(sc, c, a, 0u, (uint32_t)a.num_samples * 4u, count_work, cancel, st, cancelled);
+        if (rc != RTB_OK) return rc;
+    }
+    return RTB_OK;
+}
+
+int resolve_to(RenderContext* c, const RenderArgs& a, unsigned char* d_out, float4* d_sub, int scanline, rtb_stats& st) {
+    int n = a.n_local_tiles * 1024;
+    if (n == 0) return RTB_OK;
+    cudaEvent_t e0 = c->ev_begin, e1 = c->ev_end;
+    CU_TRY(cudaEventRecord(e0, c->stream));
+    k_resolve<<<(n + 255) / 256, 256, 0, c->stream>>>(a, d_out, d_sub, scanline);
+    CU_TRY(cudaEventRecord(e1, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    st.resolve_ms += ms;
+    st.kernel_launches += 1;
+    return RTB_OK;
+}
+
+int ensure_rgb(RenderContext* c, size_t bytes, bool host) {
+    if (c->rgb_cap < bytes) {
+        cudaFree(c->d_rgb);
+        c->d_rgb = nullptr;
+        CU_TRY(cudaMalloc((void**)&c->d_rgb, bytes));
+        c->rgb_cap = bytes;
+    }
+    if (host && c->h_rgb_cap < bytes) {
+        if (c->h_rgb) cudaFreeHost(c->h_rgb);
+        c->h_rgb = nullptr;
+        CU_TRY(cudaMallocHost((void**)&c->h_rgb, bytes));
+        c->h_rgb_cap = bytes;
+    }
+    return RTB_OK;
+}
+
+}  // namespace
+
+// ======================================================================================= C ABI
+extern "C" {
+
+const char* rtb_last_error(void) { return g_last_error.c_str(); }
+
+int rtb_scene_load_toml(const char* toml_path, const char* assets_dir, int device, rtb_scene** out) {
+    if (!toml_path || !out) return fail(RTB_EINVAL, "NULL argument");
+    *out = nullptr;
+    rtb_scene* sc = new rtb_scene();
+    sc->device = device;
+    std::string err;
+    int rc = load_scene_file(toml_path, assets_dir ? assets_dir : "", sc->hs, err);
+    return finish_scene(sc, rc, err, out);
+}
+
+int rtb_scene_load_toml_string(const char* toml_text, const char* assets_dir, int device, rtb_scene** out) {
+    if (!toml_text || !out) return fail(RTB_EINVAL, "NULL argument");
+    *out = nullptr;
+    rtb_scene* sc = new rtb_scene();
+    sc->device = device;
+    std::string err;
+    int rc = load_scene_text(toml_text, assets_dir ? assets_dir : "", sc->hs, err);
+    return finish_scene(sc, rc, err, out);
+}
+
+void rtb_scene_destroy(rtb_scene* scene) { delete scene; }
+
+int rtb_scene_get_info(const rtb_scene* scene, rtb_scene_info* info) {
+    if (!scene || !info) return fail(RTB_EINVAL, "NULL argument");
+    *info = scene->info;
+    return RTB_OK;
+}
+
+int rtb_scene_upload(rtb_scene* scene, uint64_t* bytes) {
+    if (int rc = need_device(scene)) return rc;
+    return upload_scene(scene, bytes);
+}
+
+int64_t rtb_scene_triangles(const rtb_scene* scene, float* out9, int64_t cap) {
+    if (!scene) return fail(RTB_EINVAL, "NULL scene");
+    int64_t n = (int64_t)scene->fs.tri_obj.size();
+    if (out9 && cap > 0) std::memcpy(out9, scene->fs.tri_verts.data(), (size_t)std::min(n, cap) * 9 * sizeof(float));
+    return n;
+}
+
+int rtb_scene_object(const rtb_scene* scene, int32_t index, rtb_object_info* out) {
+    if (!scene || !out) return fail(RTB_EINVAL, "NULL argument");
+    if (index < 0 || index >= scene->fs.n_objects) return fail(RTB_EINVAL, "object index out of range");
+    const HostObject& o = scene->hs.objects[index];
+    std::memset(out, 0, sizeof(*out));
+    out->brdf = o.brdf;
+    out->geometry = o.geom;
+    out->emitted[0] = o.emitted.x; out->emitted[1] = o.emitted.y; out->emitted[2] = o.emitted.z;
+    if (o.brdf == BRDF_PHONG) {
+        out->k[0] = o.phong_kd; out->k[1] = o.phong_ks; out->k[2] = o.phong_power;
+        out->color_d[0] = o.color_d.x; out->color_d[1] = o.color_d.y; out->color_d[2] = o.color_d.z;
+        out->color_s[0] = o.color_s.x; out->color_s[1] = o.color_s.y; out->color_s[2] = o.color_s.z;
+    } else {
+        out->k[0] = o.k.x; out->k[1] = o.k.y; out->k[2] = o.k.z;
+    }
+    out->pos[0] = o.pos.x; out->pos[1] = o.pos.y; out->pos[2] = o.pos.z;
+    out->n[0] = o.n.x; out->n[1] = o.n.y; out->n[2] = o.n.z;
+    out->r = o.r;
+    out->n_triangles = (int32_t)(o.indices.size() / 3);
+    out->first_triangle = scene->fs.materials[index].first_tri;
+    out->bb_min[0] = o.bb_min.x; out->bb_min[1] = o.bb_min.y; out->bb_min[2] = o.bb_min.z;
+    out->bb_max[0] = o.bb_max.x; out->bb_max[1] = o.bb_max.y; out->bb_max[2] = o.bb_max.z;
+    out->surface_area = o.surface_area;
+    return RTB_OK;
+}
+
+int64_t rtb_local_pixels(const rtb_params* params) {
+    if (check_params(params) != RTB_OK) return RTB_EINVAL;
+    return (int64_t)local_tiles(params) * 1024;
+}
+
+int rtb_get_stats(const rtb_scene* scene, rtb_stats* stats) {
+    if (!scene || !stats) return fail(RTB_EINVAL, "NULL argument");
+    rtb_scene* s = const_cast<rtb_scene*>(scene);
+    std::lock_guard<std::mutex> lk(s->mu);
+    *stats = s->last_stats;
+    return RTB_OK;
+}
+
+int rtb_render_device(rtb_scene* scene, const rtb_params* params, void* d_rgb8_tiles, void* d_subpixel_sums, volatile int* cancel) {
+    if (int rc0 = need_device(scene)) return rc0;
+    int rc = check_params(params);
+    if (rc != RTB_OK) return rc;
+    RenderContext* c = acquire_context(scene);
+    RenderArgs a;
+    rtb_stats st{};
+    bool cancelled = false;
+    rc = render_into_context(scene, params, c, a, cancel, st, cancelled);
+    if (rc == RTB_OK && !cancelled && d_rgb8_tiles)
+        rc = resolve_to(c, a, (unsigned char*)d_rgb8_tiles, (float4*)d_subpixel_sums, 0, st);
+    {
+        std::lock_guard<std::mutex> lk(scene->mu);
+        scene->last_stats = st;
+    }
+    release_context(scene, c);
+    if (rc != RTB_OK) return rc;
+    return cancelled ? RTB_ECANCELLED : RTB_OK;
+}
+
+int rtb_render(rtb_scene* scene, const rtb_params* params, uint8_t* rgb8_out, volatile int* cancel) {
+    if (!scene || !rgb8_out) return fail(RTB_EINVAL, "NULL argument");
+    if (int rc0 = need_device(scene)) return rc0;
+    int rc = check_params(params);
+    if (rc != RTB_OK) return rc;
+    RenderContext* c = acquire_context(scene);
+    RenderArgs a;
+    rtb_stats st{};
+    bool cancelled = false;
+    rc = render_into_context(scene, params, c, a, cancel, st, cancelled);
+    if (rc == RTB_OK && !cancelled) {
+        const size_t frame = (size_t)params->width * params->height * 3;
+        const bool whole = params->world == 1;
+        const size_t bytes = whole ? frame : (size_t)a.n_local_tiles * 1024 * 3;
+        rc = ensure_rgb(c, std::max<size_t>(bytes, 1), true);
+        if (rc == RTB_OK) rc = resolve_to(c, a, c->d_rgb, nullptr, whole ? 1 : 0, st);
+        if (rc == RTB_OK && bytes) {
+            cudaError_t e = cudaMemcpyAsync(c->h_rgb, c->d_rgb, bytes, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) rc = fail(RTB_ECUDA, std::string("frame read-back: ") + cudaGetErrorString(e));
+        }
+        if (rc == RTB_OK) {
+            if (whole) std::memcpy(rgb8_out, c->h_rgb, frame);
+            else {
+                for (int lp = 0; lp < a.n_local_tiles * 1024; ++lp) {
+                    int x, y;
+                    if (!local_to_xy(lp, a.rank, a.world, a.tiles_x, a.width, a.height, x, y)) continue;
+                    std::memcpy(rgb8_out + ((size_t)y * a.width + x) * 3, c->h_rgb + (size_t)lp * 3, 3);
+                }
+            }
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(scene->mu);
+        scene->last_stats = st;
+    }
+    release_context(scene, c);
+    if (rc != RTB_OK) return rc;
+    return cancelled ? RTB_ECANCELLED : RTB_OK;
+}
+
+int rtb_untile_device(const rtb_params* params, const void* d_shards, int64_t shard_stride, void* d_rgb8_frame, int device) {
+    int rc = check_params(params);
+    if (rc != RTB_OK) return rc;
+    if (!d_shards || !d_rgb8_frame) return fail(RTB_EINVAL, "NULL argument");
+    CU_TRY(cudaSetDevice(device));
+    int tx = (params->width + TILE - 1) / TILE, ty = (params->height + TILE - 1) / TILE;
+    long long total = (long long)tx * ty * 1024;
+    k_untile<<<(unsigned)((total + 255) / 256), 256>>>((const unsigned char*)d_shards, shard_stride, params->world, tx, ty,
+                                                       params->width, params->height, (unsigned char*)d_rgb8_frame);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaGetLastError());
+    return RTB_OK;
+}
+
+// ---------------------------------------------------------------- parity hooks
+static int trace_common(rtb_scene* scene, int64_t n, const float* org3, const float* dir3, int width, int height, int sx, int sy,
+                        float dx, float dy, int32_t* obj, int32_t* tri, float* t, uint64_t* work2) {
+    if (!scene || !obj || !tri || !t) return fail(RTB_EINVAL, "NULL argument");
+    if (int rc0 = need_device(scene)) return rc0;
+    if (n <= 0) return RTB_OK;
+    CU_TRY(cudaSetDevice(scene->device));
+    float *d_org = nullptr, *d_dir = nullptr, *d_t = nullptr;
+    int32_t *d_obj = nullptr, *d_tri = nullptr;
+    unsigned long long* d_work = nullptr;
+    auto cleanup = [&]() { cudaFree(d_org); cudaFree(d_dir); cudaFree(d_t); cudaFree(d_obj); cudaFree(d_tri); cudaFree(d_work); };
+    cudaError_t e = cudaSuccess;
+    auto T = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    if (org3) {
+        T(cudaMalloc((void**)&d_org, (size_t)n * 3 * sizeof(float)));
+        T(cudaMalloc((void**)&d_dir, (size_t)n * 3 * sizeof(float)));
+        if (e == cudaSuccess) T(cudaMemcpy(d_org, org3, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+        if (e == cudaSuccess) T(cudaMemcpy(d_dir, dir3, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    T(cudaMalloc((void**)&d_t, (size_t)n * sizeof(float)));
+    T(cudaMalloc((void**)&d_obj, (size_t)n * sizeof(int32_t)));
+    T(cudaMalloc((void**)&d_tri, (size_t)n * sizeof(int32_t)));
+    T(cudaMalloc((void**)&d_work, 2 * sizeof(unsigned long long)));
+    if (e == cudaSuccess) T(cudaMemset(d_work, 0, 2 * sizeof(unsigned long long)));
+    if (e == cudaSuccess) {
+        const size_t smem = shared_scene_bytes(scene->view.n_prims, scene->view.n_objects, WF_THREADS);
+        Camera cam = make_camera(scene->fs.cam_pos, scene->fs.cam_dir, std::max(width, 1), std::max(height, 1));
+        int grid = (int)std::min<int64_t>((n + WF_THREADS - 1) / WF_THREADS, 148 * 8);
+        if (work2) {
+            T(cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_trace_rays<true><<<grid, WF_THREADS, smem>>>(scene->view, n, d_org, d_dir, cam, width, height, sx, sy, dx, dy, d_obj, d_tri, d_t, d_work);
+        } else {
+            T(cudaFuncSetAttribute(k_trace_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_trace_rays<false><<<grid, WF_THREADS, smem>>>(scene->view, n, d_org, d_dir, cam, width, height, sx, sy, dx, dy, d_obj, d_tri, d_t, d_work);
+        }
+        T(cudaDeviceSynchronize());
+        T(cudaGetLastError());
+    }
+    if (e == cudaSuccess) T(cudaMemcpy(obj, d_obj, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (e == cudaSuccess) T(cudaMemcpy(tri, d_tri, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (e == cudaSuccess) T(cudaMemcpy(t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (e == cudaSuccess && work2) T(cudaMemcpy(work2, d_work, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cleanup();
+    if (e != cudaSuccess) return fail(RTB_ECUDA, std::string("rtb_trace: ") + cudaGetErrorString(e));
+    return RTB_OK;
+}
+
+int rtb_trace_primary(rtb_scene* scene, int32_t width, int32_t height, int32_t sx, int32_t sy, float dx, float dy, int32_t* obj,
+                      int32_t* tri, float* t) {
+    if (width <= 0 || height <= 0) return fail(RTB_EINVAL, "bad frame size");
+    return trace_common(scene, (int64_t)width * height, nullptr, nullptr, width, height, sx, sy, dx, dy, obj, tri, t, nullptr);
+}
+
+int rtb_trace_rays(rtb_scene* scene, int64_t n, const float* org3, const float* dir3, int32_t* obj, int32_t* tri, float* t,
+                   uint64_t* work2) {
+    if (!org3 || !dir3) return fail(RTB_EINVAL, "NULL rays");
+    return trace_common(scene, n, org3, dir3, 1, 1, 0, 0, 0.f, 0.f, obj, tri, t, work2);
+}
+
+int rtb_sample_radiance(rtb_scene* scene, const rtb_params* params, int64_t n, const int32_t* px, const int32_t* py,
+                        const int32_t* sample_idx, float* rgb3) {
+    if (!scene || !px || !py || !sample_idx || !rgb3) return fail(RTB_EINVAL, "NULL argument");
+    if (int rc0 = need_device(scene)) return rc0;
+    int rc = check_params(params);
+    if (rc != RTB_OK) return rc;
+    if (n <= 0) return RTB_OK;
+    if (params->spp < 4) return fail(RTB_EINVAL, "spp < 4 has no samples");
+    for (int64_t i = 0; i < n; ++i)
+        if (px[i] < 0 || px[i] >= params->width || py[i] < 0 || py[i] >= params->height || sample_idx[i] < 0 ||
+            sample_idx[i] >= params->spp / 4 * 4)
+            return fail(RTB_EINVAL, "probe item out of range");
+    RenderContext* c = acquire_context(scene);
+    uint32_t P = (uint32_t)std::min<int64_t>(std::max<int64_t>((n + 31) / 32 * 32, 1024), 1 << 22);
+    uint32_t SP = params->estimator == RTB_EST_NEE ? P : 2 * P;
+    rc = ensure_context(scene, c, P, SP, (size_t)n);
+    RenderArgs a;
+    rtb_stats st{};
+    if (rc == RTB_OK) {
+        if (c->probe_cap < (size_t)n * 3) {
+            cudaFree(c->d_probe);
+            c->d_probe = nullptr;
+            if (cudaMalloc((void**)&c->d_probe, (size_t)n * 3 * sizeof(int32_t)) != cudaSuccess) rc = fail(RTB_ECUDA, "probe alloc");
+            else c->probe_cap = (size_t)n * 3;
+        }
+    }
+    if (rc == RTB_OK) {
+        fill_args(scene, params, c, a);
+        a.probe_px = c->d_probe;
+        a.probe_py = c->d_probe + n;
+        a.probe_sample = c->d_probe + 2 * n;
+        a.n_probe = (int)n;
+        cudaError_t e = cudaMemcpyAsync(c->d_probe, px, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_probe + n, py, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_probe + 2 * n, sample_idx, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->accum, 0, (size_t)n * sizeof(float4), c->stream);
+        if (e != cudaSuccess) rc = fail(RTB_ECUDA, cudaGetErrorString(e));
+    }
+    bool cancelled = false;
+    if (rc == RTB_OK) rc = run_wavefront(scene, c, a, 0, 0, params->reserved[0] == 1, nullptr, st, cancelled);
+    if (rc == RTB_OK) {
+        std::vector<float4> host((size_t)n);
+        cudaError_t e = cudaMemcpy(host.data(), c->accum, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(RTB_ECUDA, cudaGetErrorString(e));
+        else
+            for (int64_t i = 0; i < n; ++i) {
+                rgb3[3 * i] = host[i].x; rgb3[3 * i + 1] = host[i].y; rgb3[3 * i + 2] = host[i].z;
+            }
+    }
+    {
+        std::lock_guard<std::mutex> lk(scene->mu);
+        scene->last_stats = st;
+    }
+    release_context(scene, c);
+    return rc;
+}
+
+int rtb_fp32_peak(int device, double* tflops) {
+    if (!tflops) return fail(RTB_EINVAL, "NULL argument");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+    float* d = nullptr;
+    CU_TRY(cudaMalloc((void**)&d, (size_t)threads * blocks * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(cudaEventRecord(e0));
+        k_fma_peak<<<blocks, threads>>>(d, iters);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * iters * (double)threads * blocks;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return RTB_OK;
+}
+
+}  // extern "C"
+
+// ======================================================================================= jobs
+// RenderJob::run's message loop (src/server.rs:166-194).  A worker thread renders pass after pass
+// on the job's own context; after each pass the frame is resolved and copied to pinned host memory
+// on the context's stream; the consumer walks rows top-down in 60-pixel windows like the reference.
+struct rtb_job {
+    rtb_scene* scene = nullptr;
+    rtb_params params{};
+    int passes = 1;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint8_t> frame;   // latest completed pass, scan-line RGB8
+    int passes_done = 0;          // produced
+    int pass_consumed = 0;        // fully sent
+    int cursor_y = 0, cursor_x = 0;
+    bool frame_fresh = false;
+    volatile int cancel = 0;
+    int error = RTB_OK;
+    std::string error_msg;
+    bool finished = false;
+};
+
+namespace {
+
+constexpr int PIXELS_PER_MSG = 60;  // RenderJob::PIXELS_PER_MSG, src/server.rs:145
+
+void job_worker(rtb_job* j) {
+    rtb_scene* sc = j->scene;
+    const rtb_params& p = j->params;
+    RenderContext* c = acquire_context(sc);
+    RenderArgs a;
+    rtb_stats st{};
+    auto finish = [&](int rc) {
+        {
+            std::lock_guard<std::mutex> lk(sc->mu);
+            sc->last_stats = st;
+        }
+        release_context(sc, c);
+        std::lock_guard<std::mutex> lk(j->mu);
+        if (rc != RTB_OK && rc != RTB_ECANCELLED) { j->error = rc; j->error_msg = g_last_error; }
+        j->finished = true;
+        j->cv.notify_all();
+    };
+    uint32_t P = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 22);
+    P = (std::max<uint32_t>(P, 1024u) + 31u) & ~31u;
+    uint32_t SP = p.estimator == RTB_EST_NEE ? P : 2 * P;
+    const size_t accum_elems = (size_t)p.width * p.height * 4;
+    const size_t frame = (size_t)p.width * p.height * 3;
+    int rc = ensure_context(sc, c, P, SP, accum_elems);
+    if (rc == RTB_OK) rc = ensure_rgb(c, frame, true);
+    if (rc != RTB_OK) return finish(rc);
+    fill_args(sc, &p, c, a);
+    if (cudaMemsetAsync(c->accum, 0, accum_elems * sizeof(float4), c->stream) != cudaSuccess) return finish(fail(RTB_ECUDA, "memset"));
+    const uint32_t ks_total = (uint32_t)a.num_samples * 4u;
+    const int passes = std::max(1, j->passes);
+    for (int pass = 0; pass < passes; ++pass) {
+        uint32_t k0 = (uint32_t)((uint64_t)ks_total * pass / passes), k1 = (uint32_t)((uint64_t)ks_total * (pass + 1) / passes);
+        bool cancelled = false;
+        if (k1 > k0) {
+            rc = run_wavefront(sc, c, a, k0, k1, false, &j->cancel, st, cancelled);
+            if (rc != RTB_OK) return finish(rc);
+        }
+        if (cancelled || j->cancel) return finish(RTB_ECANCELLED);
+        // resolve with the per-sub-pixel sample counts reached so far
+        RenderArgs r = a;
+        r.ks_done = k1;
+        rc = resolve_to(c, r, c->d_rgb, nullptr, 1, st);
+        if (rc != RTB_OK) return finish(rc);
+        cudaError_t e = cudaMemcpyAsync(c->h_rgb, c->d_rgb, frame, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return finish(fail(RTB_ECUDA, cudaGetErrorString(e)));
+        std::unique_lock<std::mutex> lk(j->mu);
+        // wait until the consumer has drained the previous pass (keeps passes in order, bounded memory)
+        j->cv.wait(lk, [&] { return !j->frame_fresh || j->cancel; });
+        if (j->cancel) { lk.unlock(); return finish(RTB_ECANCELLED); }
+        j->frame.assign(c->h_rgb, c->h_rgb + frame);
+        j->frame_fresh = true;
+        j->passes_done = pass + 1;
+        j->cursor_x = j->cursor_y = 0;
+        j->cv.notify_all();
+    }
+    finish(RTB_OK);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rtb_job** out) {
+    if (!scene || !out) return fail(RTB_EINVAL, "NULL argument");
+    if (int rc0 = need_device(scene)) return rc0;
+    int rc = check_params(params);
+    if (rc != RTB_OK) return rc;
+    if (params->world != 1) return fail(RTB_EINVAL, "streaming jobs render whole frames (world must be 1)");
+    rtb_job* j = new rtb_job();
+    j->scene = scene;
+    j->params = *params;
+    j->passes = std::max(1, passes);
+    j->worker = std::thread(job_worker, j);
+    *out = j;
+    return RTB_OK;
+}
+
+// returns 1 = record produced, 0 = frame(s) complete, RTB_ECANCELLED, or a negative error
+int rtb_job_next(rtb_job* job, uint16_t* x, uint16_t* y, uint8_t* n, uint8_t* rgb) {
+    if (!job || !x || !y || !n || !rgb) return fail(RTB_EINVAL, "NULL argument");
+    std::unique_lock<std::mutex> lk(job->mu);
+    job->cv.wait(lk, [&] { return job->frame_fresh || job->finished || job->cancel; });
+    if (job->cancel) return RTB_ECANCELLED;
+    if (!job->frame_fresh) {
+        if (job->error != RTB_OK) return fail(job->error, job->error_msg);
+        return 0;
+    }
+    const int w = job->params.width, h = job->params.height;
+    int cx = job->cursor_x, cy = job->cursor_y;
+    int cnt = std::min(PIXELS_PER_MSG, w - cx);  // windows(), src/server.rs:254-280
+    *x = (uint16_t)cx;
+    *y = (uint16_t)cy;
+    *n = (uint8_t)cnt;
+    std::memcpy(rgb, job->frame.data() + ((size_t)cy * w + cx) * 3, (size_t)cnt * 3);
+    cx += cnt;
+    if (cx >= w) { cx = 0; ++cy; }
+    job->cursor_x = cx;
+    job->cursor_y = cy;
+    if (cy >= h) {  // pass fully sent
+        job->frame_fresh = false;
+        job->pass_consumed++;
+        job->cv.notify_all();
+    }
+    return 1;
+}
+
+int rtb_job_next_messages(rtb_job* job, uint8_t* buf, int64_t buf_bytes, int32_t max_records, int64_t* bytes_written) {
+    if (!job || !buf || !bytes_written) return fail(RTB_EINVAL, "NULL argument");
+    int64_t off = 0;
+    int produced = 0;
+    while (produced < max_records && off + 6 + 3 * PIXELS_PER_MSG <= buf_bytes) {
+        {   // never block once something has been produced
+            std::unique_lock<std::mutex> lk(job->mu);
+            if (produced > 0 && !job->frame_fresh) break;
+        }
+        uint16_t x, y;
+        uint8_t n;
+        int rc = rtb_job_next(job, &x, &y, &n, buf + off + 6);
+        if (rc != 1) {
+            *bytes_written = off;
+            return produced > 0 ? produced : rc;
+        }
+        uint8_t* m = buf + off;  // header, src/server.rs:173-177
+        m[0] = 0;
+        m[1] = n;
+        m[2] = (uint8_t)(x & 0xff); m[3] = (uint8_t)(x >> 8);
+        m[4] = (uint8_t)(y & 0xff); m[5] = (uint8_t)(y >> 8);
+        off += 6 + 3 * (int64_t)n;
+        ++produced;
+    }
+    *bytes_written = off;
+    return produced;
+}
+
+int rtb_job_cancel(rtb_job* job) {
+    if (!job) return fail(RTB_EINVAL, "NULL job");
+    std::lock_guard<std::mutex> lk(job->mu);
+    job->cancel = 1;
+    job->cv.notify_all();
+    return RTB_OK;
+}
+
+int rtb_job_end(rtb_job* job) {
+    if (!job) return fail(RTB_EINVAL, "NULL job");
+    {
+        std::lock_guard<std::mutex> lk(job->mu);
+        if (!job->finished) job->cancel = 1;
+        job->cv.notify_all();
+    }
+    if (job->worker.joinable()) job->worker.join();
+    int was_cancelled = job->cancel && job->error == RTB_OK && job->passes_done < job->passes;
+    delete job;
+    return was_cancelled ? RTB_ECANCELLED : RTB_OK;
+}
+
+}  // extern "C"

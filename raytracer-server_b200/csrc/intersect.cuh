@@ -1,0 +1,281 @@
+// intersect.cuh — Scene::trace_ray on the device: analytic primitives + LBVH traversal.
+//
+// What it must reproduce (reference, f64):
+//   Scene::trace_ray            src/scene.rs:272-289   nearest hit, strict '<' (lowest index wins ties)
+//   Geometry::intersect Sphere  src/geometry.rs:514-550  t > 1e-4, near root then far root, no offset
+//   Geometry::intersect Plane   src/geometry.rs:551-568  |d.n| < 1e-4 miss, t >= 0, pos += 1e-5 n_facing
+//   Triangle::intersect         src/geometry.rs:637-670  |n^.d| < 1e-4 miss, u,v range, t > 1e-4, +1e-5 n_facing
+//   Mesh::intersect             src/geometry.rs:887-903  (brute-force branch = true nearest hit; the LBVH is
+//                                                        an exact accelerator for that branch)
+//   mutually_visible            src/scene.rs:258-270     visible iff nearest t + 1e-3 >= |y - x|
+//
+// fp32 robustness: the reference leaves a surface through a 1e-5 offset that f64 resolves and
+// fp32 (ulp 7.6e-6 at x = 100) does not.  A ray therefore carries the primitive it starts on
+// (`origin`), and for exactly that primitive the intersection is evaluated as the reference's
+// f64 arithmetic would see it: origin 1e-5 above the facing side of a plane/triangle
+// (t = -1e-5 / (d . n_facing)), or exactly on a sphere (roots 0 and 2b).  Coincident planes
+// (every reference scene duplicates one wall, scenes/*.toml objects 1 and 5) share a class.
+#pragma once
+
+#include "device_types.cuh"
+
+namespace rtb {
+
+constexpr int STACK_SMEM = 16;   // stack levels kept in shared memory (per thread)
+constexpr int STACK_LOCAL = 48;  // overflow levels in local memory
+constexpr int NODE_SENTINEL = 0x7fffffff;
+constexpr float T_EPS = 1e-4f;          // sphere / triangle t threshold
+constexpr float DN_EPS = 1e-4f;         // plane / triangle parallel threshold
+constexpr float SURF_OFFSET = 1e-5f;    // hit-position offset along the facing normal
+constexpr float SHADOW_MARGIN = 1e-3f;  // ERR_MARGIN, src/scene.rs:259
+
+struct SharedScene {     // staged per CTA
+    const DevPrim* prims;
+    const DevMaterial* mats;
+    int* stack;          // [STACK_SMEM][blockDim.x]
+};
+
+// dynamic shared memory needed by a CTA of `threads` threads
+__host__ __device__ inline size_t shared_scene_bytes(int n_prims, int n_objects, int threads) {
+    return (size_t)n_prims * sizeof(DevPrim) + (size_t)n_objects * sizeof(DevMaterial) +
+           (size_t)STACK_SMEM * threads * sizeof(int);
+}
+
+__device__ __forceinline__ SharedScene stage_scene(const DevScene& S, unsigned char* smem) {
+    SharedScene sh;
+    DevPrim* p = reinterpret_cast<DevPrim*>(smem);
+    DevMaterial* m = reinterpret_cast<DevMaterial*>(smem + (size_t)S.n_prims * sizeof(DevPrim));
+    int* st = reinterpret_cast<int*>(smem + (size_t)S.n_prims * sizeof(DevPrim) + (size_t)S.n_objects * sizeof(DevMaterial));
+    {   // 16-byte copies; both structs are multiples of 16 B
+        const float4* src = reinterpret_cast<const float4*>(S.prims);
+        float4* dst = reinterpret_cast<float4*>(p);
+        for (int i = threadIdx.x; i < S.n_prims * 3; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const float4*>(S.mats);
+        dst = reinterpret_cast<float4*>(m);
+        for (int i = threadIdx.x; i < S.n_objects * 5; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    sh.prims = p;
+    sh.mats = m;
+    sh.stack = st;
+    return sh;
+}
+
+// does the ray touch the box of all mesh triangles?  (queue class: BVH rays vs analytic-only rays)
+__device__ __forceinline__ bool ray_hits_bvh_box(const DevScene& S, float3 o, float3 d) {
+    if (S.n_tris == 0) return false;
+    float ix = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    float iy = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    float iz = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    float x0 = (S.bvh_min.x - o.x) * ix, x1 = (S.bvh_max.x - o.x) * ix;
+    float y0 = (S.bvh_min.y - o.y) * iy, y1 = (S.bvh_max.y - o.y) * iy;
+    float z0 = (S.bvh_min.z - o.z) * iz, z1 = (S.bvh_max.z - o.z) * iz;
+    float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return tmin <= tmax * 1.0000005f;
+}
+
+// ---- analytic primitives -------------------------------------------------------------------
+// Returns true and the distance if primitive k is hit.  `origin` = pcode of the primitive the ray
+// starts on (PC_NONE id for camera / free rays).
+__device__ __forceinline__ bool prim_intersect(const DevPrim& P, int k, float3 o, float3 d, uint32_t origin,
+                                               int origin_group, float& t_out) {
+    if (P.type == 0) {  // plane
+        float3 n = f3(P.a);
+        float dn = dot(d, n);
+        if (fabsf(dn) < DN_EPS) return false;
+        float t;
+        if (P.group == origin_group) {
+            float dnf = (origin & PC_FLIPPED) ? -dn : dn;  // d . n_facing
+            t = -SURF_OFFSET / dnf;
+        } else {
+            t = (P.a.w - dot(o, n)) / dn;
+        }
+        if (t >= 0.0f) { t_out = t; return true; }
+        return false;
+    }
+    // sphere
+    float3 op = f3(P.a) - o;
+    float b = dot(op, d);
+    if ((uint32_t)k == (origin & PC_ID_MASK)) {  // origin exactly on the sphere: roots 0 and 2b
+        float t = 2.0f * b;
+        if (t > T_EPS) { t_out = t; return true; }
+        return false;
+    }
+    // det = b^2 - op.op + r^2 evaluated as r^2 - |op - b d|^2 (same value, well conditioned in fp32;
+    // exact for unit d, and every ray direction on this path is normalised)
+    float3 l = op - b * d;
+    float det = P.b.x - dot(l, l);
+    if (det < 0.0f) return false;
+    det = sqrtf(det);
+    float t = b - det;
+    if (t > T_EPS) { t_out = t; return true; }
+    t = b + det;
+    if (t > T_EPS) { t_out = t; return true; }
+    return false;
+}
+
+__device__ __forceinline__ int origin_group_of(const SharedScene& sh, uint32_t origin) {
+    uint32_t id = origin & PC_ID_MASK;
+    return id < TRI_BASE ? sh.prims[id].group : -1;
+}
+
+// ---- LBVH traversal ------------------------------------------------------------------------
+struct StackRef {
+    int* smem;         // base + threadIdx.x, stride blockDim.x
+    int stride;
+};
+
+template <bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ bool bvh_traverse(const DevScene& S, const SharedScene& sh, float3 o, float3 d, uint32_t origin,
+                                             float& best_t, uint32_t& best_id, float dist, uint32_t* work) {
+    // ANY_HIT: returns true as soon as some triangle has t + SHADOW_MARGIN < dist.
+    // else   : updates (best_t, best_id) with the nearest triangle hit below best_t.
+    const float idx = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    const float idy = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    const float idz = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    const float oox = o.x * idx, ooy = o.y * idy, ooz = o.z * idz;
+    const uint32_t origin_id = origin & PC_ID_MASK;
+    int* sstack = sh.stack + threadIdx.x;
+    const int stride = blockDim.x;
+    int lstack[STACK_LOCAL];
+    int sp = 0;
+    float tlimit = ANY_HIT ? dist - SHADOW_MARGIN : best_t;
+    int node = S.root;
+
+    while (node != NODE_SENTINEL) {
+        if (node >= 0) {
+            const float4* np = S.nodes + (size_t)node * 4;
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            if (COUNT) work[0]++;
+            // n0 = c0 (lo.x hi.x lo.y hi.y)  n1 = c1 (lo.x hi.x lo.y hi.y)  n2 = (c0.lo.z c0.hi.z c1.lo.z c1.hi.z)
+            float a0 = n0.x * idx - oox, a1 = n0.y * idx - oox, a2 = n0.z * idy - ooy, a3 = n0.w * idy - ooy;
+            float a4 = n2.x * idz - ooz, a5 = n2.y * idz - ooz;
+            float b0 = n1.x * idx - oox, b1 = n1.y * idx - oox, b2 = n1.z * idy - ooy, b3 = n1.w * idy - ooy;
+            float b4 = n2.z * idz - ooz, b5 = n2.w * idz - ooz;
+            float tmin0 = fmaxf(fmaxf(fminf(a0, a1), fminf(a2, a3)), fmaxf(fminf(a4, a5), 0.0f));
+            float tmax0 = fminf(fminf(fmaxf(a0, a1), fmaxf(a2, a3)), fminf(fmaxf(a4, a5), tlimit));
+            float tmin1 = fmaxf(fmaxf(fminf(b0, b1), fminf(b2, b3)), fmaxf(fminf(b4, b5), 0.0f));
+            float tmax1 = fminf(fminf(fmaxf(b0, b1), fmaxf(b2, b3)), fminf(fmaxf(b4, b5), tlimit));
+            bool h0 = tmin0 <= tmax0, h1 = tmin1 <= tmax1;
+            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            if (h0 && h1) {
+                bool swap = tmin1 < tmin0;
+                int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+                if (sp < STACK_SMEM) sstack[sp * stride] = farc;
+                else lstack[sp - STACK_SMEM] = farc;
+                ++sp;
+                node = nearc;
+            } else if (h0 || h1) {
+                node = h0 ? c0 : c1;
+            } else {
+                if (sp == 0) node = NODE_SENTINEL;
+                else { --sp; node = sp < STACK_SMEM ? sstack[sp * stride] : lstack[sp - STACK_SMEM]; }
+            }
+        } else {
+            uint32_t v = ~(uint32_t)node;
+            uint32_t first = v >> 3, cnt = (v & 7u) + 1u;
+            for (uint32_t s = first; s < first + cnt; ++s) {
+                const float4* tp = S.tris + (size_t)s * 3;
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                if (COUNT) work[1]++;
+                float3 e1 = f3(t1), e2 = f3(t2);
+                float3 pvec = cross(d, e2);
+                float det = dot(e1, pvec);      // = d . ((c-a) x (b-a)) = |N| (n^ . d)
+                float nd = det * t0.w;          // n^ . d
+                if (fabsf(nd) < DN_EPS) continue;
+                float inv = 1.0f / det;
+                float3 tvec = o - f3(t0);
+                float u = dot(tvec, pvec) * inv;
+                float3 qvec = cross(tvec, e1);
+                float vv = dot(d, qvec) * inv;
+                float t = dot(e2, qvec) * inv;
+                if (TRI_BASE + s == origin_id) {  // the triangle this ray starts on (see header)
+                    float dnf = (origin & PC_FLIPPED) ? -nd : nd;
+                    t = -SURF_OFFSET / dnf;
+                }
+                if (u < 0.0f || vv < 0.0f || u + vv > 1.0f || !(t > T_EPS)) continue;
+                if (ANY_HIT) {
+                    if (t < tlimit) return true;
+                } else if (t < best_t) {
+                    best_t = t;
+                    best_id = TRI_BASE + s;
+                    tlimit = t;
+                }
+            }
+            if (sp == 0) node = NODE_SENTINEL;
+            else { --sp; node = sp < STACK_SMEM ? sstack[sp * stride] : lstack[sp - STACK_SMEM]; }
+        }
+    }
+    return false;
+}
+
+// ---- Scene::trace_ray ------------------------------------------------------------------------
+// use_bvh: the ray's queue class (ray_hits_bvh_box at push time)
+template <bool COUNT>
+__device__ __forceinline__ void closest_hit(const DevScene& S, const SharedScene& sh, float3 o, float3 d, uint32_t origin,
+                                            bool use_bvh, float& best_t, uint32_t& best_id, uint32_t* work) {
+    best_t = INFINITY;
+    best_id = PC_NONE;
+    const int og = origin_group_of(sh, origin);
+    for (int k = 0; k < S.n_prims; ++k) {
+        float t;
+        if (prim_intersect(sh.prims[k], k, o, d, origin, og, t) && t < best_t) {
+            best_t = t;
+            best_id = (uint32_t)k;
+        }
+    }
+    if (use_bvh) bvh_traverse<false, COUNT>(S, sh, o, d, origin, best_t, best_id, 0.0f, work);
+}
+
+// mutually_visible: true if something lies strictly in front of the target (t + margin < dist)
+template <bool COUNT>
+__device__ __forceinline__ bool occluded(const DevScene& S, const SharedScene& sh, float3 o, float3 d, uint32_t origin,
+                                         bool use_bvh, float dist, uint32_t* work) {
+    const int og = origin_group_of(sh, origin);
+    for (int k = 0; k < S.n_prims; ++k) {
+        float t;
+        if (prim_intersect(sh.prims[k], k, o, d, origin, og, t) && t + SHADOW_MARGIN < dist) return true;
+    }
+    if (use_bvh) {
+        float bt = INFINITY;
+        uint32_t bi = PC_NONE;
+        return bvh_traverse<true, COUNT>(S, sh, o, d, origin, bt, bi, dist, work);
+    }
+    return false;
+}
+
+// ---- hit geometry ----------------------------------------------------------------------------
+struct HitGeom {
+    float3 pos;      // Hit.pos (offset rules of the reference applied)
+    float3 n;        // Hit.n, facing the ray
+    int obj;         // Hit.id
+    uint32_t pcode;  // id | PC_FLIPPED
+};
+
+__device__ __forceinline__ HitGeom hit_geometry(const DevScene& S, const SharedScene& sh, float3 o, float3 d, float t,
+                                                uint32_t id) {
+    HitGeom h;
+    float3 p = o + t * d;
+    float3 n;
+    bool offset = true;
+    if (id < TRI_BASE) {
+        const DevPrim& P = sh.prims[id];
+        h.obj = P.obj;
+        if (P.type == 0) n = f3(P.a);
+        else { n = normalize(p - f3(P.a)); offset = false; }
+    } else {
+        const float4* tp = S.tris + (size_t)(id - TRI_BASE) * 3;
+        const float4 t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+        n = normalize(cross(f3(t2), f3(t1)));  // Triangle::normal: norm((c-a) x (b-a))
+        h.obj = __float_as_int(t2.w);
+    }
+    bool flipped = !(dot(n, -d) >= 0.0f);
+    if (flipped) n = -n;
+    h.n = n;
+    h.pos = offset ? p + SURF_OFFSET * n : p;
+    h.pcode = id | (flipped ? PC_FLIPPED : 0u);
+    return h;
+}
+
+}  // namespace rtb

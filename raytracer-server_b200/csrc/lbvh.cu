@@ -1,0 +1,315 @@
+// lbvh.cu — device-built linear BVH over all mesh triangles of a scene.
+//
+// Replaces the reference's per-mesh octree (Octree::build / _build, src/geometry.rs:1149-1216,
+// set-up time only) with a structure that answers the question the reference's own brute-force
+// branch answers (Mesh::intersect, src/geometry.rs:887-903): the true nearest triangle.
+//
+// Pipeline (all on the GPU, one stream):
+//   1. triangle bounds + centroid bounds (atomic min/max on order-preserving int keys)
+//   2. 63-bit Morton codes of the centroids (21 bits per axis)
+//   3. radix sort of (code, triangle) pairs                         [cub::DeviceRadixSort]
+//   4. Karras 2012 hierarchy: one thread per internal node finds its range and split
+//   5. bottom-up refit with one atomic arrival counter per internal node
+//   6. collapse subtrees of <= LEAF_MAX triangles into leaves (LBVH subtrees are contiguous in
+//      sorted order), compact the surviving nodes                    [cub::DeviceScan]
+//   7. emit 64-byte nodes {child0 box, child1 box, child refs} and triangles in leaf order
+#include "lbvh.hpp"
+
+#include <cub/cub.cuh>
+
+#include <cfloat>
+#include <cstdio>
+
+namespace rtb {
+namespace {
+
+#define LBVH_CHECK(x)                                                                  \
+    do {                                                                               \
+        cudaError_t e_ = (x);                                                          \
+        if (e_ != cudaSuccess) {                                                       \
+            err = std::string("CUDA error in LBVH build: ") + cudaGetErrorString(e_); \
+            return false;                                                              \
+        }                                                                              \
+    } while (0)
+
+constexpr int LEAF_MAX = 4;
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct Bounds6 {
+    int lo[3], hi[3];    // triangle-vertex bounds (ordered ints)
+    int clo[3], chi[3];  // centroid bounds
+};
+
+__global__ void k_init_bounds(Bounds6* b) {
+    for (int k = 0; k < 3; ++k) {
+        b->lo[k] = b->clo[k] = float_to_ordered(FLT_MAX);
+        b->hi[k] = b->chi[k] = float_to_ordered(-FLT_MAX);
+    }
+}
+
+__global__ void k_tri_bounds(const float* __restrict__ verts, int n, float4* __restrict__ lo4, float4* __restrict__ hi4, Bounds6* gb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* v = verts + (size_t)i * 9;
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) {
+        float a = v[k], b = v[3 + k], c = v[6 + k];
+        lo[k] = fminf(a, fminf(b, c));
+        hi[k] = fmaxf(a, fmaxf(b, c));
+    }
+    for (int k = 0; k < 3; ++k) {  // conservative pad: a few fp32 ulps
+        float pad = fmaxf(fabsf(lo[k]), fabsf(hi[k])) * 2.4e-7f + 1e-30f;
+        lo[k] -= pad;
+        hi[k] += pad;
+    }
+    lo4[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    hi4[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    for (int k = 0; k < 3; ++k) {
+        float c = 0.5f * (lo[k] + hi[k]);
+        atomicMin(&gb->lo[k], float_to_ordered(lo[k]));
+        atomicMax(&gb->hi[k], float_to_ordered(hi[k]));
+        atomicMin(&gb->clo[k], float_to_ordered(c));
+        atomicMax(&gb->chi[k], float_to_ordered(c));
+    }
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v) {  // 21 bits -> every third bit
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void k_morton(const float4* __restrict__ lo4, const float4* __restrict__ hi4, int n, const Bounds6* gb,
+                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 lo = lo4[i], hi = hi4[i];
+    float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    unsigned long long q[3];
+    for (int k = 0; k < 3; ++k) {
+        float a = ordered_to_float(gb->clo[k]), b = ordered_to_float(gb->chi[k]);
+        float ext = b - a;
+        float u = ext > 0.f ? (c[k] - a) / ext : 0.f;
+        u = fminf(fmaxf(u, 0.f), 1.f);
+        q[k] = (unsigned long long)fminf(u * 2097152.0f, 2097151.0f);
+    }
+    keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    vals[i] = (uint32_t)i;
+}
+
+// common-prefix length of sorted keys i and j; ties are broken by the index (Karras 2012, sec. 4)
+__device__ __forceinline__ int delta(const unsigned long long* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll(a ^ b);
+}
+
+// child reference during the build: >= 0 internal node, < 0 leaf slot ~ref
+__global__ void k_hierarchy(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
+                            int* __restrict__ parent_int, int* __restrict__ parent_leaf, int* __restrict__ rfirst,
+                            int* __restrict__ rlast) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    int lc = (first == gamma) ? ~gamma : gamma;
+    int rc = (last == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    left[i] = lc;
+    right[i] = rc;
+    rfirst[i] = first;
+    rlast[i] = last;
+    if (lc >= 0) parent_int[lc] = i; else parent_leaf[~lc] = i;
+    if (rc >= 0) parent_int[rc] = i; else parent_leaf[~rc] = i;
+    if (i == 0) parent_int[0] = -1;
+}
+
+__global__ void k_refit(int n, const uint32_t* __restrict__ sorted, const float4* __restrict__ tlo, const float4* __restrict__ thi,
+                        const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent_int,
+                        const int* __restrict__ parent_leaf, int* __restrict__ arrive, float4* __restrict__ nlo,
+                        float4* __restrict__ nhi) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int node = parent_leaf[s];
+    while (node >= 0) {
+        if (atomicAdd(&arrive[node], 1) == 0) return;  // first child to arrive leaves; the second one merges
+        __threadfence();
+        int lc = left[node], rc = right[node];
+        float4 alo = lc >= 0 ? __ldcg(&nlo[lc]) : tlo[sorted[~lc]], ahi = lc >= 0 ? __ldcg(&nhi[lc]) : thi[sorted[~lc]];
+        float4 blo = rc >= 0 ? __ldcg(&nlo[rc]) : tlo[sorted[~rc]], bhi = rc >= 0 ? __ldcg(&nhi[rc]) : thi[sorted[~rc]];
+        nlo[node] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+        nhi[node] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+        __threadfence();
+        node = parent_int[node];
+    }
+}
+
+__global__ void k_mark_used(int n_internal, const int* __restrict__ rfirst, const int* __restrict__ rlast, int* __restrict__ used) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    used[i] = (rlast[i] - rfirst[i] + 1) > LEAF_MAX ? 1 : 0;
+}
+
+__device__ __forceinline__ int encode_leaf(int first, int count) { return ~((first << 3) | (count - 1)); }
+
+__global__ void k_emit(int n_internal, const uint32_t* __restrict__ sorted, const float4* __restrict__ tlo,
+                       const float4* __restrict__ thi, const int* __restrict__ left, const int* __restrict__ right,
+                       const int* __restrict__ rfirst, const int* __restrict__ rlast, const int* __restrict__ used,
+                       const int* __restrict__ newidx, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
+                       float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal || !used[i]) return;
+    int c[2] = {left[i], right[i]};
+    float4 lo[2], hi[2];
+    int ref[2];
+    for (int k = 0; k < 2; ++k) {
+        if (c[k] < 0) {
+            int s = ~c[k];
+            lo[k] = tlo[sorted[s]];
+            hi[k] = thi[sorted[s]];
+            ref[k] = encode_leaf(s, 1);
+        } else {
+            lo[k] = nlo[c[k]];
+            hi[k] = nhi[c[k]];
+            ref[k] = used[c[k]] ? newidx[c[k]] : encode_leaf(rfirst[c[k]], rlast[c[k]] - rfirst[c[k]] + 1);
+        }
+    }
+    float4* o = out + (size_t)newidx[i] * 4;
+    o[0] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
+    o[1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
+    o[2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
+    o[3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.f, 0.f);
+}
+
+__global__ void k_pack_tris(int n, const uint32_t* __restrict__ sorted, const float* __restrict__ verts,
+                            const int32_t* __restrict__ tri_obj, float4* __restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t g = sorted[s];
+    const float* v = verts + (size_t)g * 9;
+    float3 a = make_float3(v[0], v[1], v[2]);
+    float3 e1 = make_float3(v[3] - a.x, v[4] - a.y, v[5] - a.z);  // b - a
+    float3 e2 = make_float3(v[6] - a.x, v[7] - a.y, v[8] - a.z);  // c - a
+    // N = (c-a) x (b-a)  (Triangle::normal, src/geometry.rs:606-608)
+    float nx = e2.y * e1.z - e2.z * e1.y, ny = e2.z * e1.x - e2.x * e1.z, nz = e2.x * e1.y - e2.y * e1.x;
+    float len = sqrtf(nx * nx + ny * ny + nz * nz);
+    float4* o = out + (size_t)s * 3;
+    o[0] = make_float4(a.x, a.y, a.z, len > 0.f ? 1.0f / len : 0.f);
+    o[1] = make_float4(e1.x, e1.y, e1.z, __int_as_float((int)g));
+    o[2] = make_float4(e2.x, e2.y, e2.z, __int_as_float(tri_obj[g]));
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
+};
+
+}  // namespace
+
+bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err) {
+    out = LbvhResult();
+    if (n <= 0) return true;
+    const int T = 256;
+    const int nb = (n + T - 1) / T;
+    const int ni = n - 1;
+
+    DevBuf<float4> tlo, thi, nlo, nhi;
+    DevBuf<Bounds6> gb;
+    DevBuf<unsigned long long> keys, keys2;
+    DevBuf<uint32_t> vals, vals2;
+    DevBuf<int> left, right, pint, pleaf, rfirst, rlast, arrive, used, newidx;
+    LBVH_CHECK(tlo.alloc(n)); LBVH_CHECK(thi.alloc(n)); LBVH_CHECK(nlo.alloc(n)); LBVH_CHECK(nhi.alloc(n));
+    LBVH_CHECK(gb.alloc(1));
+    LBVH_CHECK(keys.alloc(n)); LBVH_CHECK(keys2.alloc(n)); LBVH_CHECK(vals.alloc(n)); LBVH_CHECK(vals2.alloc(n));
+    LBVH_CHECK(left.alloc(n)); LBVH_CHECK(right.alloc(n)); LBVH_CHECK(pint.alloc(n)); LBVH_CHECK(pleaf.alloc(n));
+    LBVH_CHECK(rfirst.alloc(n)); LBVH_CHECK(rlast.alloc(n)); LBVH_CHECK(arrive.alloc(n)); LBVH_CHECK(used.alloc(n));
+    LBVH_CHECK(newidx.alloc(n + 1));
+
+    k_init_bounds<<<1, 1, 0, stream>>>(gb.p);
+    k_tri_bounds<<<nb, T, 0, stream>>>(d_verts, n, tlo.p, thi.p, gb.p);
+    k_morton<<<nb, T, 0, stream>>>(tlo.p, thi.p, n, gb.p, keys.p, vals.p);
+
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    LBVH_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, stream));
+    LBVH_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, used.p, newidx.p, n, stream));
+    DevBuf<unsigned char> tmp;
+    LBVH_CHECK(tmp.alloc(tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes));
+    LBVH_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, stream));
+
+    float4* d_tris = nullptr;
+    LBVH_CHECK(cudaMalloc((void**)&d_tris, (size_t)n * 3 * sizeof(float4)));
+    out.d_tris = d_tris;
+    k_pack_tris<<<nb, T, 0, stream>>>(n, vals2.p, d_verts, d_tri_obj, d_tris);
+
+    Bounds6 hb;
+    if (n <= LEAF_MAX) {  // the whole mesh is one leaf
+        out.root = ~((0 << 3) | (n - 1));
+        out.n_nodes = 0;
+        out.n_leaves = 1;
+        LBVH_CHECK(cudaMalloc((void**)&out.d_nodes, 4 * sizeof(float4)));
+    } else {
+        LBVH_CHECK(cudaMemsetAsync(arrive.p, 0, (size_t)n * sizeof(int), stream));
+        const int nbi = (ni + T - 1) / T;
+        k_hierarchy<<<nbi, T, 0, stream>>>(keys2.p, n, left.p, right.p, pint.p, pleaf.p, rfirst.p, rlast.p);
+        k_refit<<<nb, T, 0, stream>>>(n, vals2.p, tlo.p, thi.p, left.p, right.p, pint.p, pleaf.p, arrive.p, nlo.p, nhi.p);
+        k_mark_used<<<nbi, T, 0, stream>>>(ni, rfirst.p, rlast.p, used.p);
+        LBVH_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, used.p, newidx.p, ni, stream));
+        int last_used = 0, last_idx = 0;
+        LBVH_CHECK(cudaMemcpyAsync(&last_used, used.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        LBVH_CHECK(cudaMemcpyAsync(&last_idx, newidx.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        LBVH_CHECK(cudaStreamSynchronize(stream));
+        out.n_nodes = last_idx + last_used;
+        LBVH_CHECK(cudaMalloc((void**)&out.d_nodes, (size_t)(out.n_nodes ? out.n_nodes : 1) * 4 * sizeof(float4)));
+        k_emit<<<nbi, T, 0, stream>>>(ni, vals2.p, tlo.p, thi.p, left.p, right.p, rfirst.p, rlast.p, used.p, newidx.p, nlo.p,
+                                      nhi.p, out.d_nodes);
+        out.root = 0;  // Karras: internal node 0 is the root; it is always used here (n > LEAF_MAX) and keeps index 0
+        out.n_leaves = out.n_nodes + 1;
+    }
+    LBVH_CHECK(cudaMemcpyAsync(&hb, gb.p, sizeof(hb), cudaMemcpyDeviceToHost, stream));
+    LBVH_CHECK(cudaStreamSynchronize(stream));
+    LBVH_CHECK(cudaGetLastError());
+    for (int k = 0; k < 3; ++k) {
+        int lo = hb.lo[k], hi = hb.hi[k];
+        float flo, fhi;
+        int t = lo >= 0 ? lo : lo ^ 0x7fffffff;
+        memcpy(&flo, &t, 4);
+        t = hi >= 0 ? hi : hi ^ 0x7fffffff;
+        memcpy(&fhi, &t, 4);
+        out.bmin[k] = flo;
+        out.bmax[k] = fhi;
+    }
+    return true;
+}
+
+void free_lbvh(LbvhResult& r) {
+    if (r.d_nodes) cudaFree(r.d_nodes);
+    if (r.d_tris) cudaFree(r.d_tris);
+    r = LbvhResult();
+}
+
+}  // namespace rtb

@@ -1,0 +1,24 @@
+// lbvh.hpp — device-built linear BVH (see lbvh.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace rtb {
+
+struct LbvhResult {
+    float4* d_nodes = nullptr;  // 4 x float4 per node: c0 (lo.x hi.x lo.y hi.y), c1 (same), (c0.lo.z c0.hi.z c1.lo.z c1.hi.z), refs
+    float4* d_tris = nullptr;   // 3 x float4 per triangle in leaf order: (a | 1/|N|), (b-a | global tri id), (c-a | object id)
+    int root = 0;               // encoded reference: >= 0 node index, < 0 leaf ~((first << 3) | (count - 1))
+    int n_nodes = 0;
+    int n_leaves = 0;
+    float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+};
+
+// d_verts: 9 floats per triangle (a, b, c) in global triangle order; d_tri_obj: owning object.
+bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err);
+void free_lbvh(LbvhResult& r);
+
+}  // namespace rtb
