@@ -147,6 +147,9 @@ int rtb_render(rtb_scene* scene, const rtb_params* params, uint8_t* rgb8_out, vo
  * (rtb_local_pixels() * 3 bytes); d_subpixel_sums (optional) receives the fp32 sums of the four
  * sub-pixels as float4 {r,g,b,0} per (pixel, sub-pixel), same order.  Synchronous on return. */
 int64_t rtb_local_pixels(const rtb_params* params);
+/* host-side tile order: (x, y) of every local pixel slot of shard (rank, world), -1/-1 for slots of
+ * partial tiles that fall outside the frame; returns the slot count.  Pure CPU (no device needed). */
+int64_t rtb_tile_map(const rtb_params* params, int32_t* xy, int64_t cap);
 int rtb_render_device(rtb_scene* scene, const rtb_params* params, void* d_rgb8_tiles, void* d_subpixel_sums,
                       volatile int* cancel);
 /* scatter `world` tile-ordered shards (concatenated, each rtb_local_pixels(rank r)*3 bytes padded

@@ -63,7 +63,7 @@ def lib():
         L.or_trace_rays.argtypes = [C.c_void_p, C.c_long, dp, dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), dp,
                                     dp, dp, C.POINTER(C.c_long)]
         L.or_primary_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]
-        L.or_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
+        L.or_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(C.c_uint8), dp, C.POINTER(C.c_long)]
         L.or_sample_radiance.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_long,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), dp]
@@ -226,14 +226,16 @@ class OracleScene:
         return org, dirs
 
     def render(self, width: int, height: int, spp: int, seed: int = 0, y0: int = 0, y1: int | None = None,
-               nthreads: int = 1, want_sub: bool = False):
-        """Returns dict(rgb8 [h,w,3] uint8, sub [h,w,4,3] f64 or None, rays, samples)."""
+               nthreads: int = 1, want_sub: bool = False, row_stride: int = 1):
+        """Returns dict(rgb8 [h,w,3] uint8, sub [h,w,4,3] f64 or None, rays, samples).
+        nthreads > 0: static row bands like src/server.rs:166-168; < 0: |n| threads, dynamic rows.
+        Only rows y0, y0+row_stride, ... < y1 are rendered."""
         if y1 is None:
             y1 = height
         rgb = np.zeros((height, width, 3), dtype=np.uint8)
         sub = np.zeros((height, width, 4, 3)) if want_sub else None
         cnt = (C.c_long * 2)(0, 0)
-        lib().or_render(self._h, width, height, spp, seed, y0, y1, nthreads,
+        lib().or_render(self._h, width, height, spp, seed, y0, y1, row_stride, nthreads,
                         rgb.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(sub) if want_sub else None, cnt)
         return {"rgb8": rgb, "sub": sub, "rays": cnt[0], "samples": cnt[1]}
 

@@ -1049,17 +1049,18 @@ void or_primary_rays(void* sp, int width, int height, int sx, int sy, double dx,
 // bytes RenderJob::run would send (src/server.rs:187-189); sub (h*w*12 doubles, optional) the
 // un-clamped sub-pixel means.  Threads split the row range into bands like src/server.rs:166-168.
 // counters2 = {rays, samples}.
-void or_render(void* sp, int width, int height, int spp, uint64_t seed, int y0, int y1, int nthreads, uint8_t* rgb8,
-               double* sub, long* counters2) {
+void or_render(void* sp, int width, int height, int spp, uint64_t seed, int y0, int y1, int row_stride, int nthreads,
+               uint8_t* rgb8, double* sub, long* counters2) {
     Scene* s = (Scene*)sp;
     // nthreads > 0: static row bands exactly like src/server.rs:166-168;
     // nthreads < 0: |nthreads| threads pulling rows from a shared counter (test convenience only).
     bool dynamic = nthreads < 0;
     if (dynamic) nthreads = -nthreads;
     if (nthreads < 1) nthreads = 1;
-    int rows = y1 - y0;
+    if (row_stride < 1) row_stride = 1;
+    int rows = (y1 - y0 + row_stride - 1) / row_stride;  // rows y0, y0+stride, ... < y1
     std::vector<Counters> cnts((size_t)nthreads);
-    std::atomic<int> next_row{y0};
+    std::atomic<int> next_row{0};
     auto do_row = [&](int y, Counters* cnt) {
         for (int x = 0; x < width; ++x) {
             long i = (long)y * width + x;
@@ -1069,9 +1070,9 @@ void or_render(void* sp, int width, int height, int spp, uint64_t seed, int y0, 
     };
     auto band = [&](int t) {
         if (dynamic) {
-            for (int y = next_row.fetch_add(1); y < y1; y = next_row.fetch_add(1)) do_row(y, &cnts[t]);
+            for (int j = next_row.fetch_add(1); j < rows; j = next_row.fetch_add(1)) do_row(y0 + j * row_stride, &cnts[t]);
         } else {
-            for (int y = y0 + t * rows / nthreads; y < y0 + (t + 1) * rows / nthreads; ++y) do_row(y, &cnts[t]);
+            for (int j = t * rows / nthreads; j < (t + 1) * rows / nthreads; ++j) do_row(y0 + j * row_stride, &cnts[t]);
         }
     };
     if (nthreads == 1) band(0);

@@ -59,7 +59,7 @@ class ObjectInfo(C.Structure):
 
 EXPORTS = [
     "rtb_last_error", "rtb_scene_load_toml", "rtb_scene_load_toml_string", "rtb_scene_destroy", "rtb_scene_get_info", "rtb_scene_object",
-    "rtb_scene_upload", "rtb_scene_triangles", "rtb_render", "rtb_local_pixels", "rtb_render_device",
+    "rtb_scene_upload", "rtb_scene_triangles", "rtb_render", "rtb_local_pixels", "rtb_tile_map", "rtb_render_device",
     "rtb_untile_device", "rtb_get_stats", "rtb_job_begin", "rtb_job_next", "rtb_job_next_messages", "rtb_job_cancel",
     "rtb_job_end", "rtb_trace_primary", "rtb_trace_rays", "rtb_sample_radiance", "rtb_fp32_peak",
 ]
@@ -89,6 +89,8 @@ def lib():
     L.rtb_render.argtypes = [vp, C.POINTER(Params), C.POINTER(C.c_uint8), ip]
     L.rtb_local_pixels.argtypes = [C.POINTER(Params)]
     L.rtb_local_pixels.restype = C.c_int64
+    L.rtb_tile_map.argtypes = [C.POINTER(Params), ip, C.c_int64]
+    L.rtb_tile_map.restype = C.c_int64
     L.rtb_render_device.argtypes = [vp, C.POINTER(Params), vp, vp, ip]
     L.rtb_untile_device.argtypes = [C.POINTER(Params), vp, C.c_int64, vp, C.c_int]
     L.rtb_get_stats.argtypes = [vp, C.POINTER(Stats)]

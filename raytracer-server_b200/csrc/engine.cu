@@ -621,6 +621,19 @@ int64_t rtb_local_pixels(const rtb_params* params) {
     return (int64_t)local_tiles(params) * 1024;
 }
 
+int64_t rtb_tile_map(const rtb_params* params, int32_t* xy, int64_t cap) {
+    if (check_params(params) != RTB_OK) return RTB_EINVAL;
+    int64_t n = (int64_t)local_tiles(params) * 1024;
+    int tiles_x = (params->width + TILE - 1) / TILE;
+    for (int64_t lp = 0; lp < n && lp < cap && xy; ++lp) {
+        int x, y;
+        bool in = local_to_xy((int)lp, params->rank, params->world, tiles_x, params->width, params->height, x, y);
+        xy[2 * lp] = in ? x : -1;
+        xy[2 * lp + 1] = in ? y : -1;
+    }
+    return n;
+}
+
 int rtb_get_stats(const rtb_scene* scene, rtb_stats* stats) {
     if (!scene || !stats) return fail(RTB_EINVAL, "NULL argument");
     rtb_scene* s = const_cast<rtb_scene*>(scene);

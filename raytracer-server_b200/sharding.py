@@ -1,0 +1,82 @@
+"""Multi-GPU frame assembly: one process per GPU, image tiles interleaved over ranks.
+
+The path shards with no data-path collective (pixels are independent): every rank
+renders the 32x32 tiles t with t % world == rank into a tile-ordered RGB8 shard; ONE collective
+per frame (all_gather over NCCL / NVLink, gloo in the CPU tests) collects the shards and a scatter
+kernel (``rtb_untile_device``) — or numpy on the CPU — puts them into scan-line order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .host import Scene, _check, make_params
+
+
+def local_pixels(width: int, height: int, rank: int, world: int) -> int:
+    p = make_params(width, height, 4, rank=rank, world=world)
+    return _check(_abi.lib().rtb_local_pixels(C.byref(p)))
+
+
+def shard_stride(width: int, height: int, world: int) -> int:
+    """Bytes of the largest shard (all_gather needs equal sizes; smaller shards are zero padded)."""
+    return max(local_pixels(width, height, r, world) for r in range(world)) * 3
+
+
+def tile_map(width: int, height: int, rank: int, world: int) -> np.ndarray:
+    """[n_local, 2] int32 (x, y) per local pixel slot; -1 for slots outside the frame."""
+    p = make_params(width, height, 4, rank=rank, world=world)
+    n = local_pixels(width, height, rank, world)
+    xy = np.full((max(n, 1), 2), -1, dtype=np.int32)
+    _check(_abi.lib().rtb_tile_map(C.byref(p), xy.ctypes.data_as(C.POINTER(C.c_int32)), n))
+    return xy[:n]
+
+
+def untile_numpy(shards: np.ndarray, width: int, height: int, world: int) -> np.ndarray:
+    """CPU twin of rtb_untile_device: shards [world, stride] uint8 -> frame [h, w, 3]."""
+    frame = np.zeros((height, width, 3), dtype=np.uint8)
+    for r in range(world):
+        xy = tile_map(width, height, r, world)
+        px = shards[r, : xy.shape[0] * 3].reshape(-1, 3)
+        ok = xy[:, 0] >= 0
+        frame[xy[ok, 1], xy[ok, 0]] = px[ok]
+    return frame
+
+
+def gather_frame_cpu(local_shard: np.ndarray, width: int, height: int, group=None) -> np.ndarray:
+    """all_gather of tile-ordered shards on CPU tensors (gloo) + numpy untile; every rank gets the frame."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    stride = shard_stride(width, height, world)
+    mine = torch.zeros(stride, dtype=torch.uint8)
+    mine[: local_shard.size] = torch.from_numpy(np.ascontiguousarray(local_shard).reshape(-1))
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return untile_numpy(torch.stack(parts).numpy(), width, height, world)
+
+
+def render_sharded(scene: Scene, width: int, height: int, spp: int, *, seed: int = 0, use_mis: bool = False,
+                   pool_paths: int = 0, group=None):
+    """Renders this rank's tiles on its GPU, all_gathers the RGB8 shards (NCCL) and returns the full
+    scan-line frame as a CUDA uint8 tensor [h, w, 3] on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", scene.info.device)
+    stride = shard_stride(width, height, world)
+    mine = torch.zeros(stride, dtype=torch.uint8, device=dev)
+    p = make_params(width, height, spp, use_mis=use_mis, seed=seed, rank=rank, world=world, pool_paths=pool_paths)
+    torch.cuda.synchronize(dev)
+    scene.render_device(p, mine.data_ptr())
+    gathered = torch.empty(world * stride, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    frame = torch.empty((height, width, 3), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize(dev)
+    _check(_abi.lib().rtb_untile_device(C.byref(p), C.c_void_p(gathered.data_ptr()), stride, C.c_void_p(frame.data_ptr()),
+                                        scene.info.device))
+    return frame

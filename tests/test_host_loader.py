@@ -1,0 +1,184 @@
+"""Host logic of the boundary, no GPU: the C++ TOML-subset + OBJ loader (device = -1 handles) against
+Python's tomllib and the oracle's own set-up code, and the reference's error behaviour."""
+import os
+import tomllib
+
+import numpy as np
+import pytest
+
+from conftest import SCENE_NAMES, SCENES, scene_path
+
+ASSETS = os.path.join(SCENES, "assets")
+
+
+def load(rtb, text, assets=ASSETS):
+    return rtb.Scene.from_toml_string(text, assets_dir=assets, device=-1)
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+def test_loader_matches_tomllib_and_oracle(rtb, oracle_scene, name):
+    with open(scene_path(name), "rb") as f:
+        spec = tomllib.load(f)
+    sc = rtb.Scene.from_toml(scene_path(name), device=-1)
+    osc = oracle_scene(name)
+    assert sc.info.n_objects == len(spec["objects"]) == osc.num_objects
+    assert sc.light_source == osc.light_source == 8
+    assert list(sc.info.camera_pos) == pytest.approx(spec["camera"]["pos"])
+    assert list(sc.info.camera_dir) == pytest.approx(spec["camera"]["dir"], rel=1e-6)
+    tri_total = 0
+    for i, ob in enumerate(spec["objects"]):
+        info = sc.object(i)
+        assert info["emitted"] == ob.get("emitted", [0.0, 0.0, 0.0])
+        assert info["brdf"] == {"diffuse": 0, "specular": 1, "phong": 2}[ob["brdf"]["type"]]
+        gt = ob["geometry"]["type"]
+        assert info["geometry"] == {"sphere": 0, "plane": 1, "cube": 2, "prism": 2, "mesh": 2}[gt]
+        if gt == "sphere":
+            assert info["pos"] == ob["geometry"]["pos"] and info["r"] == ob["geometry"]["r"]
+        if gt == "plane":
+            assert info["pos"] == ob["geometry"]["pos"] and info["n"] == ob["geometry"]["n"]
+        if info["geometry"] == 2:
+            st = osc.mesh_stats(i)
+            assert info["n_triangles"] == st["triangles"] and info["first_triangle"] == tri_total
+            assert np.allclose(info["bb_min"], st["bbox_min"], rtol=0, atol=1e-12)
+            assert np.allclose(info["bb_max"], st["bbox_max"], rtol=0, atol=1e-12)
+            want = osc.mesh_triangles(i).astype(np.float32)        # f64 set-up, rounded once to fp32
+            got = sc.triangles()[tri_total: tri_total + info["n_triangles"]]
+            assert np.array_equal(got, want)
+            tri_total += info["n_triangles"]
+    assert sc.info.n_triangles == tri_total
+
+
+def test_transform_semantics(rtb, oracle_mod):
+    # transforms apply in TOML order, about the bbox centre, with the scale() bbox quirk
+    # (src/geometry.rs:445-510): translate then scale != scale then translate for the pivot
+    def scene(tr):
+        return f"""
+[camera]
+pos = [0.0, 0.0, 10.0]
+dir = [0.0, 0.0, -1.0]
+[[objects]]
+brdf = {{ type = "diffuse", kd = [0.5, 0.5, 0.5] }}
+geometry = {{ type = "prism", pos = [1.0, 2.0, 3.0], size = [1.0, 2.0, 4.0] }}
+transforms = [ {tr} ]
+[[objects]]
+emitted = [1.0, 1.0, 1.0]
+brdf = {{ type = "diffuse", kd = [0.0, 0.0, 0.0] }}
+geometry = {{ type = "sphere", pos = [0.0, 9.0, 0.0], r = 1.0 }}
+transforms = [ {{ scale = 2.0 }}, {{ translate = [1.0, 0.0, 0.0] }}, {{ rotate_x = 1.0 }} ]
+"""
+    for tr in ("{ scale = 2.0 }, { translate = [1.0, 0.5, 0.0] }, { rotate_y = 0.3 }",
+               "{ rotate_z = -0.4 }, { scale = 0.5 }, { scale = 3.0 }, { rotate_x = 1.2 }",
+               "{ translate = [5.0, 0.0, 0.0] }, { scale = 2.0 }, { scale = 2.0 }"):
+        sc = load(rtb, scene(tr))
+        osc = oracle_mod.OracleScene.from_toml_string(scene(tr), ASSETS)
+        st = osc.mesh_stats(0)
+        info = sc.object(0)
+        assert np.allclose(info["bb_min"], st["bbox_min"], atol=1e-12) and np.allclose(info["bb_max"], st["bbox_max"], atol=1e-12)
+        assert np.array_equal(sc.triangles(), osc.mesh_triangles(0).astype(np.float32))
+        light = sc.object(1)
+        assert light["r"] == 2.0 and light["pos"] == [1.0, 9.0, 0.0]      # spheres: scale r, translate pos, rotations ignored
+    # the quirk itself: after one scale the stored box is min + (min - c) * s, wider than the vertices
+    sc = load(rtb, scene("{ scale = 2.0 }"))
+    info = sc.object(0)
+    assert info["bb_min"] == [1.0 + (1.0 - 1.5) * 2, 2.0 + (2.0 - 3.0) * 2, 3.0 + (3.0 - 5.0) * 2]
+    assert sc.triangles().reshape(-1, 3).min(0).tolist() == [0.5, 1.0, 1.0]
+
+
+def test_plane_rotation_and_cube(rtb):
+    sc = load(rtb, """
+[camera]
+pos = [0, 0, 10]     # integers are accepted where the reference's serde structs want f64
+dir = [0, 0, -1]
+[[objects]]
+brdf = { type = "diffuse", kd = [0.5, 0.5, 0.5] }
+geometry = { type = "plane", pos = [0.0, 0.0, 0.0], n = [0.0, 1.0, 0.0] }
+transforms = [ { rotate_x = 1.5707963267948966 }, { translate = [0.0, 1.0, 0.0] }, { scale = 7.0 } ]
+[[objects]]
+emitted = [3, 3, 3]
+brdf = { type = "specular", ks = [0.9, 0.9, 0.9] }
+geometry = { type = "cube", pos = [0.0, 0.0, 0.0], size = 2.0 }
+""")
+    p = sc.object(0)
+    assert p["n"] == pytest.approx([0.0, 0.0, 1.0], abs=1e-15) and p["pos"] == [0.0, 1.0, 0.0]
+    c = sc.object(1)
+    assert c["n_triangles"] == 12 and c["surface_area"] == pytest.approx(24.0) and c["brdf"] == 1
+    assert sc.light_source == 1
+
+
+def test_phong_and_toml_forms(rtb):
+    sc = load(rtb, """
+# dotted keys, literal strings, multi-line arrays, trailing commas, comments everywhere
+camera.pos = [ 1.0,
+               2.0,   # y
+               3.0, ]
+camera.dir = [0.0, 0.0, -1.0]
+
+[[objects]]
+emitted = [1e1, 1.0e+1, 1_0.0]
+geometry = { type = 'sphere', pos = [0.0, 5.0, 0.0], r = 1.5 }
+[objects.brdf]
+type = "phong"
+kd = 0.3
+ks = 0.6
+power = 20
+color_d = [1.0, 0.5, 0.25]
+color_s = [1.0, 1.0, 1.0]
+""")
+    o = sc.object(0)
+    assert o["brdf"] == 2 and o["k"] == [0.3, 0.6, 20.0] and o["color_d"] == [1.0, 0.5, 0.25]
+    assert o["emitted"] == [10.0, 10.0, 10.0] and list(sc.info.camera_pos) == [1.0, 2.0, 3.0]
+
+
+LIGHT = """
+[[objects]]
+emitted = [1.0, 1.0, 1.0]
+brdf = { type = "diffuse", kd = [0.0, 0.0, 0.0] }
+geometry = { type = "sphere", pos = [0.0, 9.0, 0.0], r = 1.0 }
+"""
+CAM = "[camera]\npos = [0.0, 0.0, 10.0]\ndir = [0.0, 0.0, -1.0]\n"
+
+
+@pytest.mark.parametrize("text,kind", [
+    ("[camera]\npos = [0.0, 0.0, 0.0]\n", "Parse"),                                    # missing field `dir`
+    (CAM, "Parse"),                                                                    # missing field `objects`
+    (CAM + "[[objects]]\nbrdf = { type = \"lambert\", kd = [1.0,1.0,1.0] }\ngeometry = { type = \"sphere\", pos = [0.0,0.0,0.0], r = 1.0 }\n", "Parse"),
+    (CAM + "[[objects]]\nbrdf = { type = \"diffuse\", kd = [1.0,1.0] }\ngeometry = { type = \"sphere\", pos = [0.0,0.0,0.0], r = 1.0 }\n", "Parse"),
+    (CAM + "[[objects]]\nbrdf = { type = \"diffuse\", kd = [1.0,1.0,1.0] }\ngeometry = { type = \"torus\" }\n", "Parse"),
+    (CAM + LIGHT + "transforms = [ { shear = 1.0 } ]\n", "Parse"),
+    (CAM + "[[objects]]\nbrdf = { type = \"phong\", kd = 0.5, ks = 0.5, color_d = [1.0,1.0,1.0], color_s = [1.0,1.0,1.0], power = -2 }\ngeometry = { type = \"sphere\", pos = [0.0,0.0,0.0], r = 1.0 }\n" + LIGHT, "Parse"),
+    (CAM + "[[objects]\n", "Parse"),
+    (CAM + "x = \n", "Parse"),
+    (CAM + "[[objects]]\nbrdf = { type = \"diffuse\", kd = [1.0,1.0,1.0] }\ngeometry = { type = \"mesh\", path = \"missing.obj\" }\n" + LIGHT, "MeshLoad"),
+    (CAM + "[[objects]]\nbrdf = { type = \"diffuse\", kd = [1.0,1.0,1.0] }\ngeometry = { type = \"sphere\", pos = [0.0,0.0,0.0], r = 1.0 }\n", "NoLight"),
+    (CAM + "[[objects]]\nemitted = [1.0,1.0,1.0]\nbrdf = { type = \"diffuse\", kd = [1.0,1.0,1.0] }\ngeometry = { type = \"plane\", pos = [0.0,0.0,0.0], n = [0.0,1.0,0.0] }\n", "Unsupported"),
+])
+def test_loader_errors(rtb, text, kind):
+    with pytest.raises(rtb.LoadTomlError) as e:
+        load(rtb, text)
+    assert e.value.kind == kind
+
+
+def test_loader_io_and_mesh_errors(rtb, tmp_path):
+    with pytest.raises(rtb.LoadTomlError) as e:
+        rtb.Scene.from_toml(str(tmp_path / "nope.toml"), device=-1)
+    assert e.value.kind == "Io"
+    (tmp_path / "bad.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 x\nf 1 2 3\n")
+    (tmp_path / "range.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n")
+    (tmp_path / "short.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2\n")
+    (tmp_path / "ok.obj").write_text("# c\nvn 0 0 1\nvt 0 0\ng grp\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nf 1/7/1 2/8/1 3/9/1\nf 1//2 3//2 4//2 2//2\n")
+    for bad in ("bad.obj", "range.obj", "short.obj"):
+        with pytest.raises(rtb.LoadTomlError) as e:
+            load(rtb, CAM + f"[[objects]]\nbrdf = {{ type = \"diffuse\", kd = [1.0,1.0,1.0] }}\ngeometry = {{ type = \"mesh\", path = \"{bad}\" }}\n" + LIGHT, assets=str(tmp_path))
+        assert e.value.kind == "MeshLoad"
+    sc = load(rtb, CAM + "[[objects]]\nbrdf = { type = \"diffuse\", kd = [1.0,1.0,1.0] }\ngeometry = { type = \"mesh\", path = \"ok.obj\" }\n" + LIGHT, assets=str(tmp_path))
+    # a/b/c tokens keep the first index; a 4th vertex on a face line is ignored (triangles only)
+    assert sc.triangles().tolist() == [[[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 0, 0], [0, 1, 0], [0, 0, 1]]]
+
+
+def test_host_only_handles_refuse_to_compute(rtb):
+    sc = rtb.Scene.from_toml(scene_path("cornell_box"), device=-1)
+    with pytest.raises(rtb.RtbError) as e:
+        sc.render(8, 8, 4)
+    assert e.value.code == rtb.RTB_ECUDA if hasattr(rtb, "RTB_ECUDA") else True
+    with pytest.raises(rtb.RtbError):
+        sc.trace_primary(4, 4)
