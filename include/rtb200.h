@@ -37,7 +37,8 @@ enum {
     RTB_EUNSUPPORTED = -5,
     RTB_ECUDA = -6,
     RTB_EINVAL = -7,
-    RTB_ECANCELLED = 1 /* RenderJob::run returns true when stopped early (src/server.rs:198) */
+    RTB_ESTOPPED = -8,  /* rtb_job_next* after rtb_job_cancel (the job yields nothing more) */
+    RTB_ECANCELLED = 1  /* rtb_render* / rtb_job_end: RenderJob::run returns true when stopped early (src/server.rs:198) */
 };
 
 typedef struct rtb_scene rtb_scene;
@@ -163,13 +164,14 @@ int rtb_get_stats(const rtb_scene* scene, rtb_stats* stats);
 /* ---- streaming job: the message loop of RenderJob::run (src/server.rs:166-194) -------------
  * rtb_job_next yields records in the reference's wire shape: screen column x, screen row y
  * (top-down), n <= 60 pixels, n*3 bytes of rgb.  Returns 1 while records remain, 0 when the
- * frame is complete, RTB_ECANCELLED after rtb_job_cancel.  Progressive mode (passes > 1, not in
+ * frame is complete, RTB_ESTOPPED after rtb_job_cancel.  Progressive mode (passes > 1, not in
  * the reference) re-sends every record once per pass with the running estimate. */
 int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rtb_job** out);
 int rtb_job_next(rtb_job* job, uint16_t* x, uint16_t* y, uint8_t* n, uint8_t* rgb /* >= 180 bytes */);
 /* bulk form: up to max_records records packed exactly like the reference's binary messages,
  * [0]=0 type, [1]=n, [2..4]=x u16le, [4..6]=y u16le, then n*(r,g,b) (src/server.rs:173-190);
- * each record occupies 6+3n bytes back to back.  Returns the number of records written. */
+ * each record occupies 6+3n bytes back to back.  Returns the number of records written (0 = complete,
+ * RTB_ESTOPPED = cancelled and nothing written). */
 int rtb_job_next_messages(rtb_job* job, uint8_t* buf, int64_t buf_bytes, int32_t max_records, int64_t* bytes_written);
 int rtb_job_cancel(rtb_job* job);
 int rtb_job_end(rtb_job* job);

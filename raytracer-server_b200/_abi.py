@@ -19,6 +19,7 @@ RTB_ENOLIGHT = -4
 RTB_EUNSUPPORTED = -5
 RTB_ECUDA = -6
 RTB_EINVAL = -7
+RTB_ESTOPPED = -8
 RTB_ECANCELLED = 1
 
 EST_NEE = 0

@@ -310,10 +310,13 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         const size_t smem = shared_scene_bytes(sc->view.n_prims, sc->view.n_objects, WF_THREADS);
         cudaDeviceProp prop;
         CU_TRY(cudaGetDeviceProperties(&prop, sc->device));
-        CU_TRY(cudaFuncSetAttribute(k_extend_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU_TRY(cudaFuncSetAttribute(k_extend_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU_TRY(cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU_TRY(cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // The attribute is per kernel, not per scene: always opt in to the largest table set
+        // (MAX_OBJECTS primitives + materials + the stack), never to this scene's own (smaller) size.
+        const int smem_max = (int)shared_scene_bytes(MAX_OBJECTS, MAX_OBJECTS, WF_THREADS);
+        CU_TRY(cudaFuncSetAttribute(k_extend_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_extend_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         int b = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_extend_shade<false>, WF_THREADS, smem));
         c->grid_ext = std::max(1, b) * prop.multiProcessorCount;
@@ -746,10 +749,10 @@ static int trace_common(rtb_scene* scene, int64_t n, const float* org3, const fl
         Camera cam = make_camera(scene->fs.cam_pos, scene->fs.cam_dir, std::max(width, 1), std::max(height, 1));
         int grid = (int)std::min<int64_t>((n + WF_THREADS - 1) / WF_THREADS, 148 * 8);
         if (work2) {
-            T(cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            T(cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_scene_bytes(MAX_OBJECTS, MAX_OBJECTS, WF_THREADS)));
             k_trace_rays<true><<<grid, WF_THREADS, smem>>>(scene->view, n, d_org, d_dir, cam, width, height, sx, sy, dx, dy, d_obj, d_tri, d_t, d_work);
         } else {
-            T(cudaFuncSetAttribute(k_trace_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            T(cudaFuncSetAttribute(k_trace_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_scene_bytes(MAX_OBJECTS, MAX_OBJECTS, WF_THREADS)));
             k_trace_rays<false><<<grid, WF_THREADS, smem>>>(scene->view, n, d_org, d_dir, cam, width, height, sx, sy, dx, dy, d_obj, d_tri, d_t, d_work);
         }
         T(cudaDeviceSynchronize());
@@ -967,12 +970,12 @@ int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rt
     return RTB_OK;
 }
 
-// returns 1 = record produced, 0 = frame(s) complete, RTB_ECANCELLED, or a negative error
+// returns 1 = record produced, 0 = frame(s) complete, RTB_ESTOPPED after a cancel, or another negative error
 int rtb_job_next(rtb_job* job, uint16_t* x, uint16_t* y, uint8_t* n, uint8_t* rgb) {
     if (!job || !x || !y || !n || !rgb) return fail(RTB_EINVAL, "NULL argument");
     std::unique_lock<std::mutex> lk(job->mu);
     job->cv.wait(lk, [&] { return job->frame_fresh || job->finished || job->cancel; });
-    if (job->cancel) return RTB_ECANCELLED;
+    if (job->cancel) return RTB_ESTOPPED;
     if (!job->frame_fresh) {
         if (job->error != RTB_OK) return fail(job->error, job->error_msg);
         return 0;

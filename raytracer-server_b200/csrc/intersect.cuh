@@ -22,7 +22,8 @@
 namespace rtb {
 
 constexpr int STACK_SMEM = 16;   // stack levels kept in shared memory (per thread)
-constexpr int STACK_LOCAL = 48;  // overflow levels in local memory
+constexpr int STACK_LOCAL = 80;  // overflow levels in local memory: 96 in total covers any Karras tree over
+                                 // 63-bit keys + 32-bit tie-break (prefix lengths grow strictly along a path)
 constexpr int NODE_SENTINEL = 0x7fffffff;
 constexpr float T_EPS = 1e-4f;          // sphere / triangle t threshold
 constexpr float DN_EPS = 1e-4f;         // plane / triangle parallel threshold

@@ -205,7 +205,7 @@ class RenderJob:
         nbytes = C.c_int64()
         while True:
             rc = L.rtb_job_next_messages(self._h, self._buf, len(self._buf), min(max_records, 256), C.byref(nbytes))
-            if rc == _abi.RTB_ECANCELLED and nbytes.value == 0:
+            if rc == _abi.RTB_ESTOPPED:
                 self.cancelled = True
                 return
             _check(rc)
