@@ -110,10 +110,13 @@ typedef struct rtb_stats {
     uint64_t bvh_node_visits; /* only filled by counting builds (rtb_trace_* with count_work) */
     uint64_t bvh_tri_tests;
     double render_ms;        /* CUDA-event time of the whole device-side render */
-    double extend_ms;        /* CUDA-event time of the traversal+shade kernel, summed */
-    double shadow_ms;
+    double extend_ms;        /* CUDA-event time of k_traverse (all LBVH queries: closest + any hit), summed over launches */
+    double shadow_ms;        /* reserved (shadow rays are traversed inside k_traverse) */
     double generate_ms;
     double resolve_ms;
+    double shade_ms;         /* k_shade */
+    uint64_t rays_bvh;       /* primary + extension rays that needed the LBVH (the rest end at an analytic primitive) */
+    uint64_t shadow_bvh;     /* shadow rays that needed the LBVH */
 } rtb_stats;
 
 /* ---- scene: Scene::from_toml + SceneSpec::to_scene (src/scene.rs:143-150, 357-441) ---------

@@ -535,12 +535,24 @@ struct Philox {
 // uniform in (0,1): 24 bits, centred — the same value the fp32 CUDA path uses
 inline double u01(uint32_t x) { return ((double)(x >> 8) + 0.5) * (1.0 / 16777216.0); }
 
-struct Sampler {  // RNG contract: counter = (pixel, sample, depth, block), key = seed
+inline double u24(uint32_t v) { return ((double)v + 0.5) * (1.0 / 16777216.0); }
+
+struct Sampler {  // RNG contract (DESIGN.md): counter = (pixel, sample, depth, block), key = seed
     uint32_t pixel, sample, k0, k1;
     void block(uint32_t depth, uint32_t blk, double u[4]) const {
         uint32_t o[4];
         Philox::gen(pixel, sample, depth, blk, k0, k1, o);
         for (int i = 0; i < 4; ++i) u[i] = u01(o[i]);
+    }
+    // live vertex: ONE Philox block -> {light u1, light u2, russian roulette, brdf u1, brdf u2}
+    void vertex(uint32_t depth, double u[5]) const {
+        uint32_t o[4];
+        Philox::gen(pixel, sample, depth, 0, k0, k1, o);
+        u[0] = u24(o[0] >> 8);
+        u[1] = u24(o[1] >> 8);
+        u[2] = u24(o[2] >> 8);
+        u[3] = u24(o[3] >> 8);
+        u[4] = u24(((o[0] & 0xffu) << 16) | ((o[1] & 0xffu) << 8) | (o[2] & 0xffu));
     }
 };
 
@@ -722,9 +734,11 @@ struct Scene {  // src/scene.rs:101-107
         const Vec3& n = hit.n;
         const Object& obj = objects[hit.id];
         double p = depth <= 5 ? 1.0 : 0.9;  // MAX_BOUNCES / SURVIVAL_PROBABILITY :109-110,164-168
-        double b0[4], b1[4];
-        s.block((uint32_t)depth, 0, b0);  // {light u1, light u2, RR, light select}
-        s.block((uint32_t)depth, 1, b1);  // {brdf u1, brdf u2, lobe, -}
+        double v5[5], sel[4];
+        s.vertex((uint32_t)depth, v5);     // {light u1, light u2, RR, brdf u1, brdf u2}
+        s.block((uint32_t)depth, 1, sel);  // {phong lobe select, light triangle select, -, -}
+        const double b0[4] = {v5[0], v5[1], v5[2], sel[1]};  // light sample + roulette
+        const double b1[4] = {v5[3], v5[4], sel[0], 0.0};    // continuation BRDF sample
 
         if (obj.brdf.kind == B_SPECULAR) {  // :170-185
             Vec3 rad = V(0, 0, 0);

@@ -48,8 +48,8 @@ struct RenderContext {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     uint32_t P = 0, SP = 0;
-    float4* qbuf = nullptr;      // 2 queues x 4 arrays x P
-    float4* sbuf = nullptr;      // 3 arrays x SP
+    float4* qbuf = nullptr;      // 2 queues x (4 float4 arrays + 1 float2 array) x P
+    float4* sbuf = nullptr;      // 2 shadow queues x 3 arrays x SP
     float4* accum = nullptr;
     size_t accum_cap = 0;
     DevCtrl* ctrl = nullptr;
@@ -57,14 +57,14 @@ struct RenderContext {
     static constexpr int RING = 16;
     cudaEvent_t ring_ev[RING] = {};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    std::vector<cudaEvent_t> ext_ev;  // start/stop pairs around every k_extend_shade launch
+    std::vector<cudaEvent_t> ext_ev;  // per iteration: 3 events bracketing k_traverse | k_shade
     unsigned char* d_rgb = nullptr;
     size_t rgb_cap = 0;
     unsigned char* h_rgb = nullptr;   // pinned
     size_t h_rgb_cap = 0;
     int32_t* d_probe = nullptr;
     size_t probe_cap = 0;
-    int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0;
+    int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0, grid_shade = 0;
 
     ~RenderContext() {
         cudaSetDevice(device);
@@ -307,38 +307,35 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         for (auto& e : c->ring_ev) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU_TRY(cudaEventCreate(&c->ev_begin));
         CU_TRY(cudaEventCreate(&c->ev_end));
-        const size_t smem = shared_scene_bytes(sc->view.n_prims, sc->view.n_objects, WF_THREADS);
+        const size_t smem_tab = shared_tables_bytes(sc->view.n_prims, sc->view.n_objects);
+        const size_t smem_stack = shared_stack_bytes(WF_THREADS);
         cudaDeviceProp prop;
         CU_TRY(cudaGetDeviceProperties(&prop, sc->device));
         // The attribute is per kernel, not per scene: always opt in to the largest table set
-        // (MAX_OBJECTS primitives + materials + the stack), never to this scene's own (smaller) size.
-        const int smem_max = (int)shared_scene_bytes(MAX_OBJECTS, MAX_OBJECTS, WF_THREADS);
-        CU_TRY(cudaFuncSetAttribute(k_extend_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        CU_TRY(cudaFuncSetAttribute(k_extend_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        CU_TRY(cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        CU_TRY(cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        // (MAX_OBJECTS primitives + materials), never to this scene's own (smaller) size.
+        const int smem_max = (int)shared_tables_bytes(MAX_OBJECTS, MAX_OBJECTS);
+        CU_TRY(cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         int b = 0;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_extend_shade<false>, WF_THREADS, smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false>, WF_THREADS, smem_stack));
         c->grid_ext = std::max(1, b) * prop.multiProcessorCount;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_extend_shade<true>, WF_THREADS, smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true>, WF_THREADS, smem_stack));
         c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<false>, WF_THREADS, smem));
-        c->grid_sh = std::max(1, b) * prop.multiProcessorCount;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shadow<true>, WF_THREADS, smem));
-        c->grid_sh_count = std::max(1, b) * prop.multiProcessorCount;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate, WF_THREADS, 0));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade, SHADE_THREADS, smem_tab));
+        c->grid_shade = std::max(1, b) * prop.multiProcessorCount;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate, WF_THREADS, smem_tab));
         c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
     }
     if (c->P != P) {
         cudaFree(c->qbuf);
         c->qbuf = nullptr;
-        CU_TRY(cudaMalloc((void**)&c->qbuf, (size_t)P * 8 * sizeof(float4)));
+        CU_TRY(cudaMalloc((void**)&c->qbuf, (size_t)P * 9 * sizeof(float4)));
         c->P = P;
     }
     if (c->SP != SP) {
         cudaFree(c->sbuf);
         c->sbuf = nullptr;
-        CU_TRY(cudaMalloc((void**)&c->sbuf, (size_t)SP * 3 * sizeof(float4)));
+        CU_TRY(cudaMalloc((void**)&c->sbuf, (size_t)SP * 6 * sizeof(float4)));
         c->SP = SP;
     }
     if (c->accum_cap < accum_elems) {
@@ -399,10 +396,14 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
         a.q[k].d = b + c->P;
         a.q[k].beta = b + 2 * (size_t)c->P;
         a.q[k].ov = b + 3 * (size_t)c->P;
+        a.q[k].hit = reinterpret_cast<float2*>(c->qbuf + (size_t)8 * c->P) + (size_t)k * c->P;
     }
-    a.sq.o = c->sbuf;
-    a.sq.d = c->sbuf + c->SP;
-    a.sq.c = c->sbuf + 2 * (size_t)c->SP;
+    for (int k = 0; k < 2; ++k) {
+        float4* b = c->sbuf + (size_t)k * 3 * c->SP;
+        a.sq[k].o = b;
+        a.sq[k].d = b + c->SP;
+        a.sq[k].c = b + 2 * (size_t)c->SP;
+    }
     a.accum = c->accum;
     a.ctrl = c->ctrl;
 }
@@ -415,16 +416,16 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     DevCtrl h{};
     h.ext_head[0] = h.ext_head[1] = 0;
     h.ext_tail[0] = h.ext_tail[1] = a.P;
-    h.sh_head = 0;
-    h.sh_tail = a.SP;
+    h.sh_head[0] = h.sh_head[1] = 0;
     unsigned long long npl = (unsigned long long)a.n_local_tiles * 1024ull;
     h.work_next = a.probe_px ? 0ull : (unsigned long long)ks_begin * npl;
     h.work_total = a.probe_px ? (unsigned long long)a.n_probe : (unsigned long long)ks_end * npl;
     CU_TRY(cudaMemcpyAsync(c->ctrl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaEventRecord(c->ev_begin, c->stream));
-    const size_t smem = shared_scene_bytes(a.S.n_prims, a.S.n_objects, WF_THREADS);
+    const size_t smem_tab = shared_tables_bytes(a.S.n_prims, a.S.n_objects);
+    const size_t smem_stack = shared_stack_bytes(WF_THREADS);
     uint64_t launches = 0;
-    size_t ext_pairs = 0;
+    size_t ext_iters = 0;
     int cur = 0;
     uint64_t it = 0;
     bool done = h.work_total == h.work_next;
@@ -433,21 +434,20 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     while (!done) {
         if (cancel && *cancel) { cancelled = true; break; }
         k_prepare<<<1, 1, 0, c->stream>>>(a, cur);
-        k_generate<<<c->grid_gen, WF_THREADS, 0, c->stream>>>(a, cur);
-        if (c->ext_ev.size() < 2 * (ext_pairs + 1)) {
-            cudaEvent_t e0, e1;
+        k_generate<<<c->grid_gen, WF_THREADS, smem_tab, c->stream>>>(a, cur);
+        while (c->ext_ev.size() < 3 * (ext_iters + 1)) {
+            cudaEvent_t e0;
             CU_TRY(cudaEventCreate(&e0));
-            CU_TRY(cudaEventCreate(&e1));
             c->ext_ev.push_back(e0);
-            c->ext_ev.push_back(e1);
         }
-        CU_TRY(cudaEventRecord(c->ext_ev[2 * ext_pairs], c->stream));
-        if (count_work) k_extend_shade<true><<<c->grid_ext_count, WF_THREADS, smem, c->stream>>>(a, cur);
-        else k_extend_shade<false><<<c->grid_ext, WF_THREADS, smem, c->stream>>>(a, cur);
-        CU_TRY(cudaEventRecord(c->ext_ev[2 * ext_pairs + 1], c->stream));
-        ++ext_pairs;
-        if (count_work) k_shadow<true><<<c->grid_sh_count, WF_THREADS, smem, c->stream>>>(a);
-        else k_shadow<false><<<c->grid_sh, WF_THREADS, smem, c->stream>>>(a);
+        cudaEvent_t* ev = &c->ext_ev[3 * ext_iters];
+        CU_TRY(cudaEventRecord(ev[0], c->stream));
+        if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+        else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+        CU_TRY(cudaEventRecord(ev[1], c->stream));
+        k_shade<<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
+        CU_TRY(cudaEventRecord(ev[2], c->stream));
+        ++ext_iters;
         launches += 4;
         // lagged, non-blocking termination test: read back `active` (state after this iteration's
         // k_prepare) into a pinned ring; the host keeps launching until a completed read-back says 0.
@@ -473,15 +473,17 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     CU_TRY(cudaGetLastError());
     float ms = 0;
     CU_TRY(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
-    double ext_ms = 0;
-    for (size_t k = 0; k < ext_pairs; ++k) {
+    double ext_ms = 0, shade_ms = 0, shadow_ms = 0;
+    for (size_t k = 0; k < ext_iters; ++k) {
         float m = 0;
-        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[2 * k], c->ext_ev[2 * k + 1]));
+        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[3 * k], c->ext_ev[3 * k + 1]));
         ext_ms += m;
+        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[3 * k + 1], c->ext_ev[3 * k + 2]));
+        shade_ms += m;
     }
     st.samples += h.samples;
     st.rays_primary += h.rays_primary;
-    st.rays_extension += h.rays_extension - h.rays_primary;
+    st.rays_extension += h.rays_extension;
     st.rays_shadow += h.rays_shadow;
     st.iterations += h.iterations;
     st.kernel_launches += launches;
@@ -489,6 +491,10 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     st.bvh_tri_tests += h.tri_tests;
     st.render_ms += ms;
     st.extend_ms += ext_ms;
+    st.shade_ms += shade_ms;
+    st.shadow_ms += shadow_ms;
+    st.rays_bvh += h.rays_bvh;
+    st.shadow_bvh += h.shadow_bvh;
     return RTB_OK;
 }
 

@@ -24,7 +24,7 @@ namespace rtb {
 constexpr int STACK_SMEM = 16;   // stack levels kept in shared memory (per thread)
 constexpr int STACK_LOCAL = 80;  // overflow levels in local memory: 96 in total covers any Karras tree over
                                  // 63-bit keys + 32-bit tie-break (prefix lengths grow strictly along a path)
-constexpr int NODE_SENTINEL = 0x7fffffff;
+constexpr int NODE_SENTINEL = (int)0x80000000;  // negative like a leaf, but no leaf encodes to it (first < 2^28)
 constexpr float T_EPS = 1e-4f;          // sphere / triangle t threshold
 constexpr float DN_EPS = 1e-4f;         // plane / triangle parallel threshold
 constexpr float SURF_OFFSET = 1e-5f;    // hit-position offset along the facing normal
@@ -37,16 +37,21 @@ struct SharedScene {     // staged per CTA
 };
 
 // dynamic shared memory needed by a CTA of `threads` threads
+__host__ __device__ inline size_t shared_tables_bytes(int n_prims, int n_objects) {
+    return (size_t)n_prims * sizeof(DevPrim) + (size_t)n_objects * sizeof(DevMaterial);
+}
+__host__ __device__ inline size_t shared_stack_bytes(int threads) { return (size_t)STACK_SMEM * threads * sizeof(int); }
 __host__ __device__ inline size_t shared_scene_bytes(int n_prims, int n_objects, int threads) {
-    return (size_t)n_prims * sizeof(DevPrim) + (size_t)n_objects * sizeof(DevMaterial) +
-           (size_t)STACK_SMEM * threads * sizeof(int);
+    return shared_tables_bytes(n_prims, n_objects) + shared_stack_bytes(threads);
 }
 
-__device__ __forceinline__ SharedScene stage_scene(const DevScene& S, unsigned char* smem) {
+// copies the primitive / material tables into shared memory (broadcast reads in the inner loops);
+// with_stack: also carve the traversal stack out of the same allocation
+__device__ __forceinline__ SharedScene stage_scene(const DevScene& S, unsigned char* smem, bool with_stack = true) {
     SharedScene sh;
     DevPrim* p = reinterpret_cast<DevPrim*>(smem);
     DevMaterial* m = reinterpret_cast<DevMaterial*>(smem + (size_t)S.n_prims * sizeof(DevPrim));
-    int* st = reinterpret_cast<int*>(smem + (size_t)S.n_prims * sizeof(DevPrim) + (size_t)S.n_objects * sizeof(DevMaterial));
+    int* st = reinterpret_cast<int*>(smem + shared_tables_bytes(S.n_prims, S.n_objects));
     {   // 16-byte copies; both structs are multiples of 16 B
         const float4* src = reinterpret_cast<const float4*>(S.prims);
         float4* dst = reinterpret_cast<float4*>(p);
@@ -58,22 +63,24 @@ __device__ __forceinline__ SharedScene stage_scene(const DevScene& S, unsigned c
     __syncthreads();
     sh.prims = p;
     sh.mats = m;
-    sh.stack = st;
+    sh.stack = with_stack ? st : nullptr;
     return sh;
 }
 
-// does the ray touch the box of all mesh triangles?  (queue class: BVH rays vs analytic-only rays)
-__device__ __forceinline__ bool ray_hits_bvh_box(const DevScene& S, float3 o, float3 d) {
+// does the ray touch the box of all mesh triangles before tmax?  (queue class: rays that need the
+// BVH vs rays whose analytic result is already final)
+__device__ __forceinline__ bool ray_hits_bvh_box(const DevScene& S, float3 o, float3 d, float tmax = INFINITY) {
     if (S.n_tris == 0) return false;
-    float ix = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
-    float iy = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
-    float iz = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    // MUFU.RCP reciprocals (2 ulp): this test only decides which queue a ray goes to, and it is widened below
+    float ix = __fdividef(1.0f, fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    float iy = __fdividef(1.0f, fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    float iz = __fdividef(1.0f, fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
     float x0 = (S.bvh_min.x - o.x) * ix, x1 = (S.bvh_max.x - o.x) * ix;
     float y0 = (S.bvh_min.y - o.y) * iy, y1 = (S.bvh_max.y - o.y) * iy;
     float z0 = (S.bvh_min.z - o.z) * iz, z1 = (S.bvh_max.z - o.z) * iz;
     float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-    float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-    return tmin <= tmax * 1.0000005f;
+    float tfar = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    return tmin <= tfar * 1.000002f + 1e-6f;
 }
 
 // ---- analytic primitives -------------------------------------------------------------------
@@ -122,93 +129,158 @@ __device__ __forceinline__ int origin_group_of(const SharedScene& sh, uint32_t o
 }
 
 // ---- LBVH traversal ------------------------------------------------------------------------
-struct StackRef {
-    int* smem;         // base + threadIdx.x, stride blockDim.x
-    int stride;
+// Per-lane traversal state.  The stack lives in shared memory (first STACK_SMEM levels, one column per
+// thread) and spills to a local array beyond that.
+struct Trav {
+    float3 o, d;
+    float idx, idy, idz, oox, ooy, ooz;
+    uint32_t origin;     // pcode of the primitive the ray starts on
+    float tlimit;        // only hits with t < tlimit count (closest: current best; any-hit: |y-x| - margin)
+    uint32_t best_id;    // closest mode: id of the nearest triangle found so far (PC_NONE = none)
+    int node;            // current node reference; NODE_SENTINEL = done
+    int sp;
 };
 
+__device__ __forceinline__ void trav_begin(Trav& T, float3 o, float3 d, uint32_t origin, float tlimit, int root) {
+    T.o = o;
+    T.d = d;
+    T.idx = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    T.idy = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    T.idz = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    T.oox = o.x * T.idx;
+    T.ooy = o.y * T.idy;
+    T.ooz = o.z * T.idz;
+    T.origin = origin;
+    T.tlimit = tlimit;
+    T.best_id = PC_NONE;
+    T.node = root;
+    T.sp = 0;
+}
+
+__device__ __forceinline__ void trav_pop(Trav& T, const int* sstack, int stride, const int* lstack) {
+    if (T.sp == 0) T.node = NODE_SENTINEL;
+    else {
+        --T.sp;
+        T.node = T.sp < STACK_SMEM ? sstack[T.sp * stride] : lstack[T.sp - STACK_SMEM];
+    }
+}
+
+// one inner node: test both child boxes, descend into the nearer hit child, push the other
+template <bool COUNT>
+__device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, int* sstack, int stride, int* lstack, uint32_t* work) {
+    const float4* np = S.nodes + (size_t)T.node * 4;
+    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+    if (COUNT) work[0]++;
+    // n0 = c0 (lo.x hi.x lo.y hi.y)  n1 = c1 (lo.x hi.x lo.y hi.y)  n2 = (c0.lo.z c0.hi.z c1.lo.z c1.hi.z)
+    float a0 = n0.x * T.idx - T.oox, a1 = n0.y * T.idx - T.oox, a2 = n0.z * T.idy - T.ooy, a3 = n0.w * T.idy - T.ooy;
+    float a4 = n2.x * T.idz - T.ooz, a5 = n2.y * T.idz - T.ooz;
+    float b0 = n1.x * T.idx - T.oox, b1 = n1.y * T.idx - T.oox, b2 = n1.z * T.idy - T.ooy, b3 = n1.w * T.idy - T.ooy;
+    float b4 = n2.z * T.idz - T.ooz, b5 = n2.w * T.idz - T.ooz;
+    float tmin0 = fmaxf(fmaxf(fminf(a0, a1), fminf(a2, a3)), fmaxf(fminf(a4, a5), 0.0f));
+    float tmax0 = fminf(fminf(fmaxf(a0, a1), fmaxf(a2, a3)), fminf(fmaxf(a4, a5), T.tlimit));
+    float tmin1 = fmaxf(fmaxf(fminf(b0, b1), fminf(b2, b3)), fmaxf(fminf(b4, b5), 0.0f));
+    float tmax1 = fminf(fminf(fmaxf(b0, b1), fmaxf(b2, b3)), fminf(fmaxf(b4, b5), T.tlimit));
+    bool h0 = tmin0 <= tmax0, h1 = tmin1 <= tmax1;
+    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    if (h0 && h1) {
+        bool swap = tmin1 < tmin0;
+        int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+        if (T.sp < STACK_SMEM) sstack[T.sp * stride] = farc;
+        else lstack[T.sp - STACK_SMEM] = farc;
+        ++T.sp;
+        T.node = nearc;
+    } else if (h0 || h1) {
+        T.node = h0 ? c0 : c1;
+    } else {
+        trav_pop(T, sstack, stride, lstack);
+    }
+}
+
+// one leaf (T.node < 0, not the sentinel): Triangle::intersect on its 1..8 triangles.
+// ANY_HIT: returns true at the first triangle with t < tlimit.  Closest: shrinks tlimit / records best_id.
+template <bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ bool trav_leaf(const DevScene& S, Trav& T, uint32_t* work) {
+    const uint32_t v = ~(uint32_t)T.node;
+    const uint32_t first = v >> 3, cnt = (v & 7u) + 1u;
+    const uint32_t origin_id = T.origin & PC_ID_MASK;
+    for (uint32_t s = first; s < first + cnt; ++s) {
+        const float4* tp = S.tris + (size_t)s * 3;
+        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+        if (COUNT) work[1]++;
+        float3 e1 = f3(t1), e2 = f3(t2);
+        float3 pvec = cross(T.d, e2);
+        float det = dot(e1, pvec);      // = d . ((c-a) x (b-a)) = |N| (n^ . d)
+        float nd = det * t0.w;          // n^ . d
+        if (fabsf(nd) < DN_EPS) continue;
+        float inv = 1.0f / det;
+        float3 tvec = T.o - f3(t0);
+        float u = dot(tvec, pvec) * inv;
+        float3 qvec = cross(tvec, e1);
+        float vv = dot(T.d, qvec) * inv;
+        float t = dot(e2, qvec) * inv;
+        if (TRI_BASE + s == origin_id) {  // the triangle this ray starts on (see header)
+            float dnf = (T.origin & PC_FLIPPED) ? -nd : nd;
+            t = -SURF_OFFSET / dnf;
+        }
+        if (u < 0.0f || vv < 0.0f || u + vv > 1.0f || !(t > T_EPS)) continue;
+        if (t < T.tlimit) {
+            if (ANY_HIT) return true;
+            T.tlimit = t;
+            T.best_id = TRI_BASE + s;
+        }
+    }
+    return false;
+}
+
+// whole traversal for one ray ("while-while": a lane leaves the inner-node loop when it holds a leaf,
+// so the triangle code runs with as many lanes as possible)
 template <bool ANY_HIT, bool COUNT>
 __device__ __forceinline__ bool bvh_traverse(const DevScene& S, const SharedScene& sh, float3 o, float3 d, uint32_t origin,
                                              float& best_t, uint32_t& best_id, float dist, uint32_t* work) {
     // ANY_HIT: returns true as soon as some triangle has t + SHADOW_MARGIN < dist.
     // else   : updates (best_t, best_id) with the nearest triangle hit below best_t.
-    const float idx = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
-    const float idy = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
-    const float idz = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
-    const float oox = o.x * idx, ooy = o.y * idy, ooz = o.z * idz;
-    const uint32_t origin_id = origin & PC_ID_MASK;
     int* sstack = sh.stack + threadIdx.x;
     const int stride = blockDim.x;
     int lstack[STACK_LOCAL];
-    int sp = 0;
-    float tlimit = ANY_HIT ? dist - SHADOW_MARGIN : best_t;
-    int node = S.root;
-
-    while (node != NODE_SENTINEL) {
-        if (node >= 0) {
-            const float4* np = S.nodes + (size_t)node * 4;
-            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-            if (COUNT) work[0]++;
-            // n0 = c0 (lo.x hi.x lo.y hi.y)  n1 = c1 (lo.x hi.x lo.y hi.y)  n2 = (c0.lo.z c0.hi.z c1.lo.z c1.hi.z)
-            float a0 = n0.x * idx - oox, a1 = n0.y * idx - oox, a2 = n0.z * idy - ooy, a3 = n0.w * idy - ooy;
-            float a4 = n2.x * idz - ooz, a5 = n2.y * idz - ooz;
-            float b0 = n1.x * idx - oox, b1 = n1.y * idx - oox, b2 = n1.z * idy - ooy, b3 = n1.w * idy - ooy;
-            float b4 = n2.z * idz - ooz, b5 = n2.w * idz - ooz;
-            float tmin0 = fmaxf(fmaxf(fminf(a0, a1), fminf(a2, a3)), fmaxf(fminf(a4, a5), 0.0f));
-            float tmax0 = fminf(fminf(fmaxf(a0, a1), fmaxf(a2, a3)), fminf(fmaxf(a4, a5), tlimit));
-            float tmin1 = fmaxf(fmaxf(fminf(b0, b1), fminf(b2, b3)), fmaxf(fminf(b4, b5), 0.0f));
-            float tmax1 = fminf(fminf(fmaxf(b0, b1), fmaxf(b2, b3)), fminf(fmaxf(b4, b5), tlimit));
-            bool h0 = tmin0 <= tmax0, h1 = tmin1 <= tmax1;
-            int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                bool swap = tmin1 < tmin0;
-                int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-                if (sp < STACK_SMEM) sstack[sp * stride] = farc;
-                else lstack[sp - STACK_SMEM] = farc;
-                ++sp;
-                node = nearc;
-            } else if (h0 || h1) {
-                node = h0 ? c0 : c1;
-            } else {
-                if (sp == 0) node = NODE_SENTINEL;
-                else { --sp; node = sp < STACK_SMEM ? sstack[sp * stride] : lstack[sp - STACK_SMEM]; }
-            }
-        } else {
-            uint32_t v = ~(uint32_t)node;
-            uint32_t first = v >> 3, cnt = (v & 7u) + 1u;
-            for (uint32_t s = first; s < first + cnt; ++s) {
-                const float4* tp = S.tris + (size_t)s * 3;
-                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                if (COUNT) work[1]++;
-                float3 e1 = f3(t1), e2 = f3(t2);
-                float3 pvec = cross(d, e2);
-                float det = dot(e1, pvec);      // = d . ((c-a) x (b-a)) = |N| (n^ . d)
-                float nd = det * t0.w;          // n^ . d
-                if (fabsf(nd) < DN_EPS) continue;
-                float inv = 1.0f / det;
-                float3 tvec = o - f3(t0);
-                float u = dot(tvec, pvec) * inv;
-                float3 qvec = cross(tvec, e1);
-                float vv = dot(d, qvec) * inv;
-                float t = dot(e2, qvec) * inv;
-                if (TRI_BASE + s == origin_id) {  // the triangle this ray starts on (see header)
-                    float dnf = (origin & PC_FLIPPED) ? -nd : nd;
-                    t = -SURF_OFFSET / dnf;
-                }
-                if (u < 0.0f || vv < 0.0f || u + vv > 1.0f || !(t > T_EPS)) continue;
-                if (ANY_HIT) {
-                    if (t < tlimit) return true;
-                } else if (t < best_t) {
-                    best_t = t;
-                    best_id = TRI_BASE + s;
-                    tlimit = t;
-                }
-            }
-            if (sp == 0) node = NODE_SENTINEL;
-            else { --sp; node = sp < STACK_SMEM ? sstack[sp * stride] : lstack[sp - STACK_SMEM]; }
+    Trav T;
+    trav_begin(T, o, d, origin, ANY_HIT ? dist - SHADOW_MARGIN : best_t, S.root);
+    while (T.node != NODE_SENTINEL) {
+        while (T.node >= 0) trav_inner<COUNT>(S, T, sstack, stride, lstack, work);
+        if (T.node != NODE_SENTINEL) {
+            if (trav_leaf<ANY_HIT, COUNT>(S, T, work)) return true;
+            trav_pop(T, sstack, stride, lstack);
         }
     }
+    if (!ANY_HIT && T.best_id != PC_NONE) {
+        best_t = T.tlimit;
+        best_id = T.best_id;
+    }
     return false;
+}
+
+// ---- analytic part of Scene::trace_ray / mutually_visible (coherent: every lane walks the same table)
+__device__ __forceinline__ void analytic_closest(const SharedScene& sh, int n_prims, float3 o, float3 d, uint32_t origin,
+                                                 float& best_t, uint32_t& best_id) {
+    best_t = INFINITY;
+    best_id = PC_NONE;
+    const int og = origin_group_of(sh, origin);
+    for (int k = 0; k < n_prims; ++k) {
+        float t;
+        if (prim_intersect(sh.prims[k], k, o, d, origin, og, t) && t < best_t) {
+            best_t = t;
+            best_id = (uint32_t)k;
+        }
+    }
+}
+__device__ __forceinline__ bool analytic_occluded(const SharedScene& sh, int n_prims, float3 o, float3 d, uint32_t origin,
+                                                  float tlimit) {
+    const int og = origin_group_of(sh, origin);
+    bool occ = false;
+    for (int k = 0; k < n_prims; ++k) {
+        float t;
+        occ |= prim_intersect(sh.prims[k], k, o, d, origin, og, t) && t < tlimit;
+    }
+    return occ;
 }
 
 // ---- Scene::trace_ray ------------------------------------------------------------------------

@@ -3,14 +3,16 @@
 //
 // RNG contract (shared with oracle/rt_oracle.cpp so both consume identical numbers):
 //   Philox4x32-10, key = (seed lo, seed hi), counter = (pixel, sample, depth, block),
-//   u = ((x >> 8) + 0.5) * 2^-24 in (0,1).
+//   u24(v) = (v + 0.5) * 2^-24 in (0,1) for a 24-bit integer v.
 //   pixel  = y_screen * width + x      sample = (sy*2+sx) * (spp/4) + k
-//   depth 0 block 0 : {tent r1, tent r2, -, -}                       src/server.rs:339-351
-//   depth d block 0 : {light u1, light u2, russian roulette, light triangle select}
-//           block 1 : {brdf u1, brdf u2, phong lobe select, -}       continuation sample
-//           block 2 : {brdf u1, u2, lobe}   dead-MIS "fresh" sample used only for its pdf (:195)
-//           block 3 : {light u1, light u2, -, select}                dead-MIS second light point (:206)
-//           block 4 : {brdf u1, u2, lobe}   dead-MIS own BRDF sample (:203)
+//   depth 0 block 0 : tent r1 = u24(x>>8), r2 = u24(y>>8)                          src/server.rs:339-351
+//   depth d block 0 : ONE block feeds the whole live vertex (128 bits -> five 24-bit uniforms):
+//                     light u1 = u24(x>>8), light u2 = u24(y>>8), russian roulette = u24(z>>8),
+//                     brdf u1 = u24(w>>8), brdf u2 = u24((x&255)<<16 | (y&255)<<8 | (z&255))
+//           block 1 : phong lobe select = u24(x>>8), light triangle select = u24(y>>8)  (only drawn when needed)
+//           block 2 : {brdf u1, u2, lobe} = u24(x>>8, y>>8, z>>8)   dead-MIS "fresh" sample used only for its pdf (:195)
+//           block 3 : {light u1, u2, -, select}                      dead-MIS second light point (:206)
+//           block 4 : {brdf u1, u2, lobe}                            dead-MIS own BRDF sample (:203)
 #pragma once
 
 #include "device_types.cuh"
@@ -33,9 +35,24 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float u24(uint32_t v) { return ((float)v + 0.5f) * (1.0f / 16777216.0f); }
 __device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t block, uint32_t k0, uint32_t k1) {
     uint4 r = philox4x32_10(pixel, sample, depth, block, k0, k1);
     return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}
+// the five uniforms of a live vertex from ONE Philox block (see the contract above)
+struct VertexRng {
+    float light_u1, light_u2, rr, brdf_u1, brdf_u2;
+};
+__device__ __forceinline__ VertexRng rng_vertex(uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t k0, uint32_t k1) {
+    uint4 r = philox4x32_10(pixel, sample, depth, 0u, k0, k1);
+    VertexRng v;
+    v.light_u1 = u24(r.x >> 8);
+    v.light_u2 = u24(r.y >> 8);
+    v.rr = u24(r.z >> 8);
+    v.brdf_u1 = u24(r.w >> 8);
+    v.brdf_u2 = u24(((r.x & 0xffu) << 16) | ((r.y & 0xffu) << 8) | (r.z & 0xffu));
+    return v;
 }
 
 // ---- camera (sample_pixel, src/server.rs:328-357) ---------------------------------------------

@@ -1,17 +1,22 @@
 // wavefront.cuh — the wavefront path-tracing kernels (sm_100a).
 //
-// One iteration of the pipeline (all launches on one stream, counters stay on the device):
-//   k_prepare       1 thread: snapshot the free slots of the current path queue, reserve that many
-//                   camera samples, reset the other queue / shadow queue / work cursors
-//   k_generate      primary-ray generation (sample_pixel's loop nest, src/server.rs:335-358)
-//   k_extend_shade  Scene::trace_ray + one level of Scene::reflected_radiance per path:
-//                   closest hit, emission, light sample, russian roulette, BRDF sample; surviving
-//                   paths are compacted into the next queue, NEE candidates into the shadow queue
-//   k_shadow        Scene::mutually_visible for every NEE candidate; visible ones are added to the
-//                   fp32 sub-pixel accumulators
-// Queues are structure-of-arrays (float4 lanes, coalesced) and two-ended: rays that touch the
-// box of the mesh BVH are appended from the front, analytic-only rays from the back, with
-// warp-aggregated atomics, so a warp of the next launch is (almost always) homogeneous.
+// One iteration of the pipeline (all launches on one stream, every counter stays on the device):
+//   k_prepare   1 thread: snapshot the free slots of the current path queue, reserve that many camera
+//               samples, reset the other queue / the shadow queue / the work cursors
+//   k_generate  primary-ray generation (sample_pixel's loop nest, src/server.rs:335-358)
+//   k_traverse  Mesh::intersect for every ray that can reach the mesh box — the extension rays of this
+//               iteration AND the shadow rays queued by the previous k_shade: persistent warps walk the LBVH
+//               "while-while" and refill finished lanes with new rays, so the SIMD lanes stay busy although
+//               incoherent rays need very different numbers of steps; unoccluded NEE candidates are added
+//               to the fp32 sub-pixel accumulators here
+//   k_shade     one level of Scene::reflected_radiance per path (src/scene.rs:161-244): emission, light
+//               sample, russian roulette, BRDF sample.  It also runs the ANALYTIC half of Scene::trace_ray
+//               (planes, spheres: the same short table for every lane, no divergence) for the two rays it
+//               creates, so that only rays which still need the mesh are queued for a traversal kernel
+//   k_resolve   sample_pixel's tail + gamma_correct + `as u8` (src/server.rs:360-368, 187-189)
+// Queues are structure-of-arrays (float4 lanes, coalesced).  The path queue is two-ended: rays that need
+// the BVH are appended from the front, rays whose analytic hit is already final from the back, with
+// warp-aggregated atomics; k_extend only visits the front part.
 #pragma once
 
 #include "intersect.cuh"
@@ -21,31 +26,34 @@ namespace rtb {
 
 constexpr int WF_THREADS = 256;
 constexpr int TILE = 32;  // multi-GPU shard unit: 32x32 pixels, interleaved over ranks
-constexpr uint32_t SHADOW_PROBE = 0x80000000u;  // shadow-queue entry is a dead-MIS "does the BRDF ray reach the light" probe
+constexpr uint32_t SHADOW_PROBE = 0x80000000u;  // shadow entry = dead-MIS probe resolved by a CLOSEST-hit query (mesh lights)
 constexpr uint32_t MAX_DEPTH_FIELD = 4095u;
+constexpr uint32_t FETCH_CHUNK = 32;     // ray indices a warp reserves per atomic
+constexpr int REFILL_BELOW = 22;         // refill a warp when fewer than this many lanes are still traversing
 
 struct PathQueue {   // capacity P each
     float4* o;       // origin.xyz | pcode of the primitive the ray starts on (+ flags)
     float4* d;       // direction.xyz | accumulator index (pixel*4 + sub-pixel)
     float4* beta;    // throughput.rgb | (sample << 12 | depth of the vertex this ray will hit)
     float4* ov;      // stale `o` (only read when PC_STALE_O is set)
+    float2* hit;     // nearest hit so far: t | id (analytic result at creation, refined by k_extend)
 };
 
 struct ShadowQueue {  // capacity SP
     float4* o;        // x.xyz | pcode
-    float4* d;        // direction.xyz | distance |y - x|
+    float4* d;        // direction.xyz | tlimit (|y - x| - ERR_MARGIN; probes: analytic hit distance)
     float4* c;        // contribution.rgb | accumulator index (| SHADOW_PROBE)
 };
 
 struct DevCtrl {
     uint32_t ext_head[2], ext_tail[2];
-    uint32_t sh_head, sh_tail;
-    uint32_t cursor_ext, cursor_sh, cursor_gen;
+    uint32_t sh_head[2];
+    uint32_t cursor_trav, cursor_pad;
     uint32_t gen_count;
     uint32_t active;        // paths alive in the current queue after k_prepare (+ reserved samples)
-    uint32_t pad0;
     unsigned long long gen_base, work_next, work_total;
     unsigned long long samples, rays_primary, rays_extension, rays_shadow, iterations;
+    unsigned long long rays_bvh, shadow_bvh;   // of those, how many needed a BVH traversal
     unsigned long long node_visits, tri_tests;
 };
 
@@ -59,7 +67,7 @@ struct RenderArgs {
     int rank, world, tiles_x, tiles_y, n_local_tiles;
     uint32_t P, SP;
     PathQueue q[2];
-    ShadowQueue sq;
+    ShadowQueue sq[2];   // sq[c] is read by k_traverse(c) and was written by k_shade(1-c)
     float4* accum;       // [pixel*4 + sub] -> (r, g, b, -) sums
     DevCtrl* ctrl;
     // probe mode (rtb_sample_radiance): explicit work items, accumulator index = item index
@@ -81,23 +89,78 @@ __host__ __device__ __forceinline__ bool local_to_xy(int lp, int rank, int world
     return x < width && y < height;
 }
 
-// ---------------------------------------------------------------- warp-aggregated two-ended push
-// Returns the queue slot for lanes with pred set.  Front pushes grow head upward from 0, back
-// pushes grow tail downward from the capacity.  Must be called by all 32 lanes.
-__device__ __forceinline__ uint32_t push_two_ended(uint32_t* head, uint32_t* tail, bool pred, bool front) {
+// ---------------------------------------------------------------- warp-aggregated queue pushes
+// All 32 lanes call these.  One lane issues the (independent) atomics back to back, so their latencies overlap.
+struct PushSlots {
+    uint32_t ext, sh, pr;
+};
+__device__ __forceinline__ PushSlots push_all(uint32_t* ext_head, uint32_t* ext_tail, uint32_t* sh_head, bool ext_push,
+                                              bool ext_front, bool sh_push, bool pr_push) {
     const unsigned lane = threadIdx.x & 31;
-    unsigned mf = __ballot_sync(0xffffffffu, pred && front);
-    unsigned mb = __ballot_sync(0xffffffffu, pred && !front);
-    uint32_t basef = 0, baseb = 0;
+    const unsigned mf = __ballot_sync(0xffffffffu, ext_push && ext_front);
+    const unsigned mb = __ballot_sync(0xffffffffu, ext_push && !ext_front);
+    const unsigned ms = __ballot_sync(0xffffffffu, sh_push);
+    const unsigned mp = __ballot_sync(0xffffffffu, pr_push);
+    uint32_t bf = 0, bb = 0, bs = 0;
     if (lane == 0) {
-        if (mf) basef = atomicAdd(head, (uint32_t)__popc(mf));
-        if (mb) baseb = atomicSub(tail, (uint32_t)__popc(mb));
+        if (mf) bf = atomicAdd(ext_head, (uint32_t)__popc(mf));
+        if (mb) bb = atomicSub(ext_tail, (uint32_t)__popc(mb));
+        if (ms | mp) bs = atomicAdd(sh_head, (uint32_t)(__popc(ms) + __popc(mp)));
     }
-    basef = __shfl_sync(0xffffffffu, basef, 0);
-    baseb = __shfl_sync(0xffffffffu, baseb, 0);
-    unsigned below = (1u << lane) - 1u;
-    if (front) return basef + __popc(mf & below);
-    return baseb - 1u - __popc(mb & below);
+    bf = __shfl_sync(0xffffffffu, bf, 0);
+    bb = __shfl_sync(0xffffffffu, bb, 0);
+    bs = __shfl_sync(0xffffffffu, bs, 0);
+    const unsigned below = (1u << lane) - 1u;
+    PushSlots r;
+    r.ext = ext_front ? bf + __popc(mf & below) : bb - 1u - __popc(mb & below);
+    r.sh = bs + __popc(ms & below);
+    r.pr = bs + __popc(ms) + __popc(mp & below);
+    return r;
+}
+
+// Block-aggregated variant for k_shade: the 8 warps of a CTA pool their counts in shared memory and
+// three threads issue ONE atomic per counter per CTA iteration (fewer same-address atomics at L2).
+// Every thread of the CTA must call it (two __syncthreads inside).
+constexpr int SHADE_THREADS = 128;   // CTA size of k_shade: 4 warps share one set of queue atomics
+struct BlockPushSmem {
+    uint32_t cnt[SHADE_THREADS / 32][4];
+    uint32_t base[SHADE_THREADS / 32][4];
+};
+__device__ __forceinline__ PushSlots push_all_block(BlockPushSmem& sm, uint32_t* ext_head, uint32_t* ext_tail, uint32_t* sh_head,
+                                                    bool ext_push, bool ext_front, bool sh_push, bool pr_push) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned mf = __ballot_sync(0xffffffffu, ext_push && ext_front);
+    const unsigned mb = __ballot_sync(0xffffffffu, ext_push && !ext_front);
+    const unsigned ms = __ballot_sync(0xffffffffu, sh_push);
+    const unsigned mp = __ballot_sync(0xffffffffu, pr_push);
+    if (lane == 0) {
+        sm.cnt[warp][0] = __popc(mf);
+        sm.cnt[warp][1] = __popc(mb);
+        sm.cnt[warp][2] = __popc(ms) + __popc(mp);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int cls = threadIdx.x;
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < SHADE_THREADS / 32; ++w) tot += sm.cnt[w][cls];
+        uint32_t b = 0;
+        if (tot) b = cls == 0 ? atomicAdd(ext_head, tot) : (cls == 1 ? atomicSub(ext_tail, tot) : atomicAdd(sh_head, tot));
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SHADE_THREADS / 32; ++w) {
+            sm.base[w][cls] = cls == 1 ? b - run : b + run;   // back class grows downward
+            run += sm.cnt[w][cls];
+        }
+    }
+    __syncthreads();
+    const uint32_t bf = sm.base[warp][0], bb = sm.base[warp][1], bs = sm.base[warp][2];
+    const unsigned below = (1u << lane) - 1u;
+    PushSlots r;
+    r.ext = ext_front ? bf + __popc(mf & below) : bb - 1u - __popc(mb & below);
+    r.sh = bs + __popc(ms & below);
+    r.pr = bs + __popc(ms) + __popc(mp & below);
+    return r;
 }
 
 __device__ __forceinline__ void accum_add(float4* accum, uint32_t idx, float3 v) {
@@ -122,15 +185,16 @@ __global__ void k_prepare(RenderArgs a, int c) {
     C->work_next += n_new;
     C->ext_head[1 - c] = 0;
     C->ext_tail[1 - c] = a.P;
-    C->sh_head = 0;
-    C->sh_tail = a.SP;
-    C->cursor_ext = C->cursor_sh = C->cursor_gen = 0;
-    C->active = count + n_new;
+    C->sh_head[1 - c] = 0;
+    C->cursor_trav = 0;
+    C->active = count + n_new + C->sh_head[c];   // pending shadow rays keep the loop alive
     C->iterations++;
 }
 
 // ---------------------------------------------------------------- k_generate
 __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SharedScene sh = stage_scene(a.S, smem_raw, false);
     DevCtrl* C = a.ctrl;
     const uint32_t n = C->gen_count;
     const unsigned long long base = C->gen_base;
@@ -138,11 +202,12 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
     const uint32_t nwarps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const float w = (float)a.width, h = (float)a.height;
-    uint32_t made = 0;
+    uint32_t made = 0, made_bvh = 0;
     for (uint32_t b = warp_id * 32; b < n; b += nwarps_total * 32) {
         uint32_t j = b + lane;
         bool valid = j < n;
         float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, b4 = o4;
+        float2 h2 = make_float2(0.f, 0.f);
         bool front = false;
         if (valid) {
             unsigned long long wi = base + j;
@@ -169,33 +234,166 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
                 int sub = sample / a.num_samples;
                 float4 r = rng_block(rng_pixel, (uint32_t)sample, 0u, 0u, a.k0, a.k1);
                 float3 dir = camera_dir(a.cam, x, a.height - y - 1, sub & 1, sub >> 1, tent(r.x), tent(r.y), w, h);
-                front = ray_hits_bvh_box(a.S, a.cam.pos, dir);
+                float ta;
+                uint32_t ida;
+                analytic_closest(sh, a.S.n_prims, a.cam.pos, dir, PC_NONE, ta, ida);
+                front = ray_hits_bvh_box(a.S, a.cam.pos, dir, ta);
                 o4 = make_float4(a.cam.pos.x, a.cam.pos.y, a.cam.pos.z, __uint_as_float(PC_NONE));
                 d4 = make_float4(dir.x, dir.y, dir.z, __uint_as_float(acc));
                 b4 = make_float4(1.f, 1.f, 1.f, __uint_as_float(((uint32_t)sample << 12) | 1u));
+                h2 = make_float2(ta, __uint_as_float(ida));
             }
         }
-        uint32_t slot = push_two_ended(&C->ext_head[c], &C->ext_tail[c], valid, front);
+        PushSlots ps = push_all(&C->ext_head[c], &C->ext_tail[c], &C->sh_head[c], valid, front, false, false);
         if (valid) {
-            a.q[c].o[slot] = o4;
-            a.q[c].d[slot] = d4;
-            a.q[c].beta[slot] = b4;
+            a.q[c].o[ps.ext] = o4;
+            a.q[c].d[ps.ext] = d4;
+            a.q[c].beta[ps.ext] = b4;
+            a.q[c].hit[ps.ext] = h2;
             ++made;
+            made_bvh += front ? 1u : 0u;
         }
     }
-    // counters: one atomic per warp
-    for (int off = 16; off; off >>= 1) made += __shfl_down_sync(0xffffffffu, made, off);
+    for (int off = 16; off; off >>= 1) {
+        made += __shfl_down_sync(0xffffffffu, made, off);
+        made_bvh += __shfl_down_sync(0xffffffffu, made_bvh, off);
+    }
     if (lane == 0 && made) {
         atomicAdd(&C->samples, (unsigned long long)made);
         atomicAdd(&C->rays_primary, (unsigned long long)made);
+        if (made_bvh) atomicAdd(&C->rays_bvh, (unsigned long long)made_bvh);
     }
 }
 
-// ---------------------------------------------------------------- k_extend_shade
+// ---------------------------------------------------------------- persistent traversal kernels
+// Warp-level work fetch: a warp owns [wnext, wend) of the queue and takes a new FETCH_CHUNK with one
+// atomic when it runs dry.  Returns false once the queue is exhausted.  Warp-uniform.
+__device__ __forceinline__ bool warp_reserve(uint32_t* cursor, uint32_t count, uint32_t& wnext, uint32_t& wend) {
+    if (wnext < wend) return true;
+    uint32_t b = 0;
+    if ((threadIdx.x & 31) == 0) b = atomicAdd(cursor, FETCH_CHUNK);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= count) return false;
+    wnext = b;
+    wend = min(b + FETCH_CHUNK, count);
+    return true;
+}
+
+// k_traverse: every LBVH query of one iteration in ONE persistent launch —
+//   * closest hit for the front (BVH) class of path queue c            (Mesh::intersect; updates q.hit in place)
+//   * any hit for the NEE candidates in shadow queue c                  (mutually_visible; accumulates if unoccluded)
+//   * closest hit for dead-MIS probes against a mesh light              (hit.id == light_source test)
+// Lanes refill individually from one work cursor, so the two ray kinds share warps and the tail is paid once.
 template <bool COUNT>
-__global__ void __launch_bounds__(WF_THREADS, 2) k_extend_shade(RenderArgs a, int c) {
+__global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SharedScene sh = stage_scene(a.S, smem_raw);
+    int* sstack = reinterpret_cast<int*>(smem_raw) + threadIdx.x;
+    const int stride = blockDim.x;
+    int lstack[STACK_LOCAL];
+    DevCtrl* C = a.ctrl;
+    const uint32_t n_ext = C->ext_head[c];   // only the BVH class of the path queue needs a traversal
+    const uint32_t count = n_ext + C->sh_head[c];
+    const unsigned lane = threadIdx.x & 31;
+    const PathQueue Q = a.q[c];
+    const ShadowQueue SQ = a.sq[c];
+    const int light_obj = a.S.hdr->light_obj;
+    uint32_t work[2] = {0, 0};
+    uint32_t wnext = 0, wend = 0;
+    bool exhausted = false;
+    Trav T;
+    T.node = NODE_SENTINEL;
+    T.sp = 0;
+    T.best_id = PC_NONE;
+    T.tlimit = 0.f;
+    uint32_t slot = 0;
+    int kind = -1;            // -1 none, 0 extension (closest), 1 shadow (any hit), 2 probe (closest, mesh light)
+    bool occluded = false;
+
+    for (;;) {
+        // ---- retire finished rays
+        const bool idle = T.node == NODE_SENTINEL;
+        if (idle && kind >= 0) {
+            if (kind == 0) {
+                if (T.best_id != PC_NONE) Q.hit[slot] = make_float2(T.tlimit, __uint_as_float(T.best_id));
+            } else {
+                bool add;
+                if (kind == 2) add = T.best_id != PC_NONE && __float_as_int(__ldg(a.S.tris + (size_t)(T.best_id - TRI_BASE) * 3 + 2).w) == light_obj;
+                else add = !occluded;
+                if (add) {
+                    const float4 c4 = SQ.c[slot];
+                    accum_add(a.accum, __float_as_uint(c4.w) & ~SHADOW_PROBE, f3(c4));
+                }
+            }
+            kind = -1;
+        }
+        // ---- refill idle lanes
+        const unsigned idle_mask = __ballot_sync(0xffffffffu, idle);
+        if (idle_mask && !exhausted) {
+            if (!warp_reserve(&C->cursor_trav, count, wnext, wend)) exhausted = true;
+            else {
+                const uint32_t my = wnext + __popc(idle_mask & ((1u << lane) - 1u));
+                if (idle && my < wend) {
+                    if (my < n_ext) {
+                        slot = my;
+                        kind = 0;
+                        const float4 o4 = Q.o[my], d4 = Q.d[my];
+                        const float2 h2 = Q.hit[my];
+                        trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), h2.x, a.S.root);
+                    } else {
+                        slot = my - n_ext;
+                        const float4 o4 = SQ.o[slot], d4 = SQ.d[slot];
+                        kind = (__float_as_uint(SQ.c[slot].w) & SHADOW_PROBE) ? 2 : 1;
+                        occluded = false;
+                        trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), d4.w, a.S.root);
+                    }
+                }
+                wnext = min(wnext + (uint32_t)__popc(idle_mask), wend);
+            }
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, T.node != NODE_SENTINEL);
+        if (active == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- traverse until too few lanes are left (then go back and refill)
+        for (;;) {
+            while (T.node >= 0) trav_inner<COUNT>(a.S, T, sstack, stride, lstack, work);
+            if (T.node != NODE_SENTINEL) {
+                if (kind == 1) {
+                    if (trav_leaf<true, COUNT>(a.S, T, work)) {
+                        occluded = true;
+                        T.node = NODE_SENTINEL;
+                    } else {
+                        trav_pop(T, sstack, stride, lstack);
+                    }
+                } else {
+                    trav_leaf<false, COUNT>(a.S, T, work);
+                    trav_pop(T, sstack, stride, lstack);
+                }
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, T.node != NODE_SENTINEL);
+            if (act == 0 || (!exhausted && __popc(act) < REFILL_BELOW)) break;
+        }
+    }
+    if (COUNT) {
+        for (int off = 16; off; off >>= 1) {
+            work[0] += __shfl_down_sync(0xffffffffu, work[0], off);
+            work[1] += __shfl_down_sync(0xffffffffu, work[1], off);
+        }
+        if (lane == 0) {
+            atomicAdd(&C->node_visits, (unsigned long long)work[0]);
+            atomicAdd(&C->tri_tests, (unsigned long long)work[1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- k_shade
+// Everything of reflected_radiance except the mesh traversal.  Coherent: static warp -> slot mapping,
+// no work-fetch atomics; the only atomics are the queue pushes (3 per warp, overlapped) and the
+// accumulator REDs.
+__global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(RenderArgs a, int c) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SharedScene sh = stage_scene(a.S, smem_raw, false);
     DevCtrl* C = a.ctrl;
     const DevSceneHeader* hdr = a.S.hdr;
     const uint32_t head = C->ext_head[c], tail = C->ext_tail[c];
@@ -203,36 +401,32 @@ __global__ void __launch_bounds__(WF_THREADS, 2) k_extend_shade(RenderArgs a, in
     const unsigned lane = threadIdx.x & 31;
     const PathQueue Q = a.q[c], N = a.q[1 - c];
     const int light_obj = hdr->light_obj;
+    const bool light_is_mesh = hdr->light_geom == 2;
     const float3 Le = f3(sh.mats[light_obj].emitted);
-    uint32_t work[2] = {0, 0};
-    uint32_t n_ext = 0;
+    const int n_prims = a.S.n_prims;
+    __shared__ BlockPushSmem push_sm;
+    uint32_t n_ext = 0, n_ext_bvh = 0, n_sh = 0, n_sh_bvh = 0;
 
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&C->cursor_ext, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        const uint32_t i = base + lane;
+    // CTA-uniform trip count: all threads of the CTA walk the queue in lock step (push_all_block synchronises)
+    for (uint32_t base = blockIdx.x * SHADE_THREADS; base < count; base += gridDim.x * SHADE_THREADS) {
+        const uint32_t i = base + threadIdx.x;
         const bool valid = i < count;
-
-        bool ext_push = false, ext_front = false, sh_push = false, sh_front = false, pr_push = false, pr_front = false;
+        bool ext_push = false, ext_front = false, sh_push = false, pr_push = false;
         float4 eo = make_float4(0, 0, 0, 0), ed = eo, eb = eo, ev = eo;
+        float2 eh = make_float2(0.f, 0.f);
         float4 so = eo, sd = eo, sc = eo;
         float4 pd = eo, pc = eo;  // probe entry shares `so`
 
         if (valid) {
             const uint32_t idx = i < head ? i : tail + (i - head);
-            const bool use_bvh = i < head;
-            const float4 o4 = Q.o[idx], d4 = Q.d[idx];
-            const float3 o = f3(o4), d = f3(d4);
-            const uint32_t origin = __float_as_uint(o4.w);
-            const uint32_t acc = __float_as_uint(d4.w);
-            float t;
-            uint32_t id;
-            closest_hit<COUNT>(a.S, sh, o, d, origin, use_bvh, t, id, work);
-            ++n_ext;
+            const float2 h2 = Q.hit[idx];
+            const uint32_t id = __float_as_uint(h2.y);
             if (id != PC_NONE) {
-                const float4 b4 = Q.beta[idx];
+                const float t = h2.x;
+                const float4 o4 = Q.o[idx], d4 = Q.d[idx], b4 = Q.beta[idx];
+                const float3 o = f3(o4), d = f3(d4);
+                const uint32_t origin = __float_as_uint(o4.w);
+                const uint32_t acc = __float_as_uint(d4.w);
                 float3 beta = f3(b4);
                 const uint32_t sdw = __float_as_uint(b4.w);
                 const uint32_t sample = sdw >> 12, depth = sdw & 0xfffu;
@@ -256,14 +450,22 @@ __global__ void __launch_bounds__(WF_THREADS, 2) k_extend_shade(RenderArgs a, in
                 const bool dead_surface = mat.brdf == 0 && mat.k.x == 0.f && mat.k.y == 0.f && mat.k.z == 0.f;
                 const bool dead_path = beta.x == 0.f && beta.y == 0.f && beta.z == 0.f;
                 if (!dead_surface && !dead_path && depth < MAX_DEPTH_FIELD) {
-                    const float4 r0 = rng_block(rng_pixel, sample, depth, 0u, a.k0, a.k1);
+                    const VertexRng vr = rng_vertex(rng_pixel, sample, depth, a.k0, a.k1);
+                    // lobe / light-triangle selectors live in block 1 and are only drawn by Phong surfaces / mesh lights
+                    float lobe_u = 0.f, select_u = 0.f;
+                    if (mat.brdf == 2 || light_is_mesh) {
+                        const float4 r1 = rng_block(rng_pixel, sample, depth, 1u, a.k0, a.k1);
+                        lobe_u = r1.x;
+                        select_u = r1.y;
+                    }
+                    const float4 r0 = make_float4(vr.light_u1, vr.light_u2, vr.rr, select_u);
+                    const float4 rb = make_float4(vr.brdf_u1, vr.brdf_u2, lobe_u, 0.f);
+                    float3 next_dir = f3(0.f, 0.f, 0.f);
                     if (mat.brdf == 1) {  // specular branch, src/scene.rs:170-185
                         if (r0.z < p) {
-                            float3 inc = flip_across(ovec, hg.n);
+                            next_dir = flip_across(ovec, hg.n);
                             ext_push = true;
-                            ext_front = ray_hits_bvh_box(a.S, hg.pos, inc);
                             eo = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode | PC_SPEC_PENDING | PC_STALE_O));
-                            ed = make_float4(inc.x, inc.y, inc.z, __uint_as_float(acc));
                             eb = make_float4(beta.x, beta.y, beta.z, __uint_as_float((sample << 12) | (depth + 1u)));
                             ev = make_float4(ovec.x, ovec.y, ovec.z, 0.f);  // the recursion is handed `o`, not -i (src/scene.rs:178)
                         }
@@ -289,11 +491,20 @@ __global__ void __launch_bounds__(WF_THREADS, 2) k_extend_shade(RenderArgs a, in
                             contrib = beta * Le * f * (dot(hg.n, inc) / (pdf_light + pdf_fresh));
                         }
                         if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
-                            sh_push = true;
-                            sh_front = ray_hits_bvh_box(a.S, hg.pos, inc);
-                            so = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
-                            sd = make_float4(inc.x, inc.y, inc.z, dist);
-                            sc = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(acc));
+                            // mutually_visible (src/scene.rs:258-270): analytic part here, mesh part in k_shadow
+                            ++n_sh;
+                            const float tlim = dist - SHADOW_MARGIN;
+                            if (!analytic_occluded(sh, n_prims, hg.pos, inc, hg.pcode, tlim)) {
+                                if (ray_hits_bvh_box(a.S, hg.pos, inc, tlim)) {
+                                    sh_push = true;
+                                    ++n_sh_bvh;
+                                    so = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
+                                    sd = make_float4(inc.x, inc.y, inc.z, tlim);
+                                    sc = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(acc));
+                                } else {
+                                    accum_add(a.accum, acc, contrib);
+                                }
+                            }
                         }
                         if (a.estimator != 0) {  // src/scene.rs:203-214: own BRDF sample; counts only if it reaches the light
                             float3 i2;
@@ -307,121 +518,96 @@ __global__ void __launch_bounds__(WF_THREADS, 2) k_extend_shade(RenderArgs a, in
                                 float pdf_light2 = pdf_a2 * (dot(dv2, dv2) / dot(ny2, -i2));
                                 float3 c2 = beta * Le * brdf_eval(mat, hg.n, ovec, i2) * (dot(hg.n, i2) / (pdf2 + pdf_light2));
                                 if (c2.x != 0.f || c2.y != 0.f || c2.z != 0.f) {
-                                    pr_push = true;
-                                    pr_front = ray_hits_bvh_box(a.S, hg.pos, i2);
-                                    so = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
-                                    pd = make_float4(i2.x, i2.y, i2.z, 0.f);
-                                    pc = make_float4(c2.x, c2.y, c2.z, __uint_as_float(acc | SHADOW_PROBE));
+                                    // trace_ray(x, i2) and test hit.id == light_source
+                                    ++n_sh;
+                                    float ta;
+                                    uint32_t ida;
+                                    analytic_closest(sh, n_prims, hg.pos, i2, hg.pcode, ta, ida);
+                                    const bool needs_bvh = ray_hits_bvh_box(a.S, hg.pos, i2, ta);
+                                    if (!light_is_mesh) {
+                                        // the light is analytic: it must be the nearest analytic hit and no triangle may lie in front of it
+                                        if (ida != PC_NONE && sh.prims[ida].obj == light_obj) {
+                                            if (needs_bvh) {
+                                                pr_push = true;
+                                                pd = make_float4(i2.x, i2.y, i2.z, ta);
+                                                pc = make_float4(c2.x, c2.y, c2.z, __uint_as_float(acc));
+                                            } else {
+                                                accum_add(a.accum, acc, c2);
+                                            }
+                                        }
+                                    } else if (needs_bvh) {  // mesh light: nearest triangle below the analytic hit must belong to it
+                                        pr_push = true;
+                                        pd = make_float4(i2.x, i2.y, i2.z, ta);
+                                        pc = make_float4(c2.x, c2.y, c2.z, __uint_as_float(acc | SHADOW_PROBE));
+                                    }
+                                    if (pr_push) {
+                                        ++n_sh_bvh;
+                                        so = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
+                                    }
                                 }
                             }
                         }
                         // ---- russian roulette + continuation, src/scene.rs:231-240
                         if (r0.z < p) {
-                            float3 i1;
                             float pdf1;
-                            brdf_sample(mat, hg.n, ovec, rng_block(rng_pixel, sample, depth, 1u, a.k0, a.k1), i1, pdf1);
-                            if (i1.x != 0.f || i1.y != 0.f || i1.z != 0.f) {
+                            brdf_sample(mat, hg.n, ovec, rb, next_dir, pdf1);
+                            if (next_dir.x != 0.f || next_dir.y != 0.f || next_dir.z != 0.f) {
                                 float3 nb;
                                 if (mat.brdf == 0) nb = beta * f3(mat.k) * (1.0f / p);  // f (n.i) / pdf == kd exactly
-                                else nb = beta * brdf_eval(mat, hg.n, ovec, i1) * (dot(hg.n, i1) / (pdf1 * p));
+                                else nb = beta * brdf_eval(mat, hg.n, ovec, next_dir) * (dot(hg.n, next_dir) / (pdf1 * p));
                                 ext_push = true;
-                                ext_front = ray_hits_bvh_box(a.S, hg.pos, i1);
                                 eo = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
-                                ed = make_float4(i1.x, i1.y, i1.z, __uint_as_float(acc));
                                 eb = make_float4(nb.x, nb.y, nb.z, __uint_as_float((sample << 12) | (depth + 1u)));
                             }
                         }
+                    }
+                    if (ext_push) {
+                        // analytic half of the next trace_ray, here where every lane does it together
+                        float ta;
+                        uint32_t ida;
+                        analytic_closest(sh, n_prims, hg.pos, next_dir, __float_as_uint(eo.w), ta, ida);
+                        ext_front = ray_hits_bvh_box(a.S, hg.pos, next_dir, ta);
+                        ed = make_float4(next_dir.x, next_dir.y, next_dir.z, __uint_as_float(acc));
+                        eh = make_float2(ta, __uint_as_float(ida));
+                        ++n_ext;
+                        n_ext_bvh += ext_front ? 1u : 0u;
                     }
                 }
             }
         }
         // ---- compaction: all 32 lanes take part
-        uint32_t slot = push_two_ended(&C->ext_head[1 - c], &C->ext_tail[1 - c], ext_push, ext_front);
+        const PushSlots ps = push_all_block(push_sm, &C->ext_head[1 - c], &C->ext_tail[1 - c], &C->sh_head[1 - c], ext_push, ext_front, sh_push, pr_push);
         if (ext_push) {
-            N.o[slot] = eo;
-            N.d[slot] = ed;
-            N.beta[slot] = eb;
-            if (__float_as_uint(eo.w) & PC_STALE_O) N.ov[slot] = ev;
+            N.o[ps.ext] = eo;
+            N.d[ps.ext] = ed;
+            N.beta[ps.ext] = eb;
+            N.hit[ps.ext] = eh;
+            if (__float_as_uint(eo.w) & PC_STALE_O) N.ov[ps.ext] = ev;
         }
-        slot = push_two_ended(&C->sh_head, &C->sh_tail, sh_push, sh_front);
+        const ShadowQueue SQ = a.sq[1 - c];
         if (sh_push) {
-            a.sq.o[slot] = so;
-            a.sq.d[slot] = sd;
-            a.sq.c[slot] = sc;
+            SQ.o[ps.sh] = so;
+            SQ.d[ps.sh] = sd;
+            SQ.c[ps.sh] = sc;
         }
-        if (a.estimator != 0) {
-            slot = push_two_ended(&C->sh_head, &C->sh_tail, pr_push, pr_front);
-            if (pr_push) {
-                a.sq.o[slot] = so;
-                a.sq.d[slot] = pd;
-                a.sq.c[slot] = pc;
-            }
+        if (pr_push) {
+            SQ.o[ps.pr] = so;
+            SQ.d[ps.pr] = pd;
+            SQ.c[ps.pr] = pc;
         }
     }
     // counters
-    for (int off = 16; off; off >>= 1) n_ext += __shfl_down_sync(0xffffffffu, n_ext, off);
-    if (lane == 0 && n_ext) atomicAdd(&C->rays_extension, (unsigned long long)n_ext);
-    if (COUNT) {
-        for (int off = 16; off; off >>= 1) {
-            work[0] += __shfl_down_sync(0xffffffffu, work[0], off);
-            work[1] += __shfl_down_sync(0xffffffffu, work[1], off);
-        }
-        if (lane == 0) {
-            atomicAdd(&C->node_visits, (unsigned long long)work[0]);
-            atomicAdd(&C->tri_tests, (unsigned long long)work[1]);
-        }
+    for (int off = 16; off; off >>= 1) {
+        n_ext += __shfl_down_sync(0xffffffffu, n_ext, off);
+        n_ext_bvh += __shfl_down_sync(0xffffffffu, n_ext_bvh, off);
+        n_sh += __shfl_down_sync(0xffffffffu, n_sh, off);
+        n_sh_bvh += __shfl_down_sync(0xffffffffu, n_sh_bvh, off);
     }
-}
-
-// ---------------------------------------------------------------- k_shadow
-template <bool COUNT>
-__global__ void __launch_bounds__(WF_THREADS, 3) k_shadow(RenderArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SharedScene sh = stage_scene(a.S, smem_raw);
-    DevCtrl* C = a.ctrl;
-    const uint32_t head = C->sh_head, tail = C->sh_tail;
-    const uint32_t count = head + (a.SP - tail);
-    const unsigned lane = threadIdx.x & 31;
-    const int light_obj = a.S.hdr->light_obj;
-    uint32_t work[2] = {0, 0};
-    uint32_t n_sh = 0;
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&C->cursor_sh, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        const uint32_t i = base + lane;
-        if (i < count) {
-            const uint32_t idx = i < head ? i : tail + (i - head);
-            const bool use_bvh = i < head;
-            const float4 o4 = a.sq.o[idx], d4 = a.sq.d[idx];
-            const float3 o = f3(o4), d = f3(d4);
-            const uint32_t origin = __float_as_uint(o4.w);
-            const uint32_t accw = __float_as_uint(a.sq.c[idx].w);
-            ++n_sh;
-            bool add;
-            if (accw & SHADOW_PROBE) {
-                float t;
-                uint32_t id;
-                closest_hit<COUNT>(a.S, sh, o, d, origin, use_bvh, t, id, work);
-                add = id != PC_NONE && object_of(a.S, sh, id) == light_obj;
-            } else {
-                add = !occluded<COUNT>(a.S, sh, o, d, origin, use_bvh, d4.w, work);
-            }
-            if (add) accum_add(a.accum, accw & ~SHADOW_PROBE, f3(a.sq.c[idx]));
-        }
-    }
-    for (int off = 16; off; off >>= 1) n_sh += __shfl_down_sync(0xffffffffu, n_sh, off);
-    if (lane == 0 && n_sh) atomicAdd(&C->rays_shadow, (unsigned long long)n_sh);
-    if (COUNT) {
-        for (int off = 16; off; off >>= 1) {
-            work[0] += __shfl_down_sync(0xffffffffu, work[0], off);
-            work[1] += __shfl_down_sync(0xffffffffu, work[1], off);
-        }
-        if (lane == 0) {
-            atomicAdd(&C->node_visits, (unsigned long long)work[0]);
-            atomicAdd(&C->tri_tests, (unsigned long long)work[1]);
-        }
+    if (lane == 0) {
+        if (n_ext) atomicAdd(&C->rays_extension, (unsigned long long)n_ext);
+        if (n_ext_bvh) atomicAdd(&C->rays_bvh, (unsigned long long)n_ext_bvh);
+        if (n_sh) atomicAdd(&C->rays_shadow, (unsigned long long)n_sh);
+        if (n_sh_bvh) atomicAdd(&C->shadow_bvh, (unsigned long long)n_sh_bvh);
     }
 }
 
@@ -436,7 +622,7 @@ __device__ __forceinline__ unsigned char to_u8(float v) {
     return (unsigned char)v;
 }
 
-// mode 0: out_rgb8 in tile order (lp*3); mode 1: scan-line frame (y*width + x)*3
+// scanline 0: out_rgb8 in tile order (lp*3); 1: scan-line frame (y*width + x)*3
 __global__ void k_resolve(RenderArgs a, unsigned char* __restrict__ out_rgb8, float4* __restrict__ out_sub, int scanline) {
     int lp = blockIdx.x * blockDim.x + threadIdx.x;
     if (lp >= a.n_local_tiles * 1024) return;
@@ -507,7 +693,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace_rays(DevScene S, long long
         }
         float t;
         uint32_t id;
-        closest_hit<COUNT>(S, sh, o, d, PC_NONE, ray_hits_bvh_box(S, o, d), t, id, work);
+        analytic_closest(sh, S.n_prims, o, d, PC_NONE, t, id);
+        if (ray_hits_bvh_box(S, o, d, t)) bvh_traverse<false, COUNT>(S, sh, o, d, PC_NONE, t, id, 0.0f, work);
         if (id == PC_NONE) {
             obj[i] = -1; tri[i] = -1; tout[i] = INFINITY;
         } else if (id < TRI_BASE) {
