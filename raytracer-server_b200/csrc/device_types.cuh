@@ -60,9 +60,11 @@ struct DevScene {          // passed to kernels by value
     const DevMaterial* mats;
     const float4* nodes;   // 4 x float4 per node
     const float4* tris;    // 3 x float4 per triangle, leaf order
+    const float4* tri_nrm; // unit geometric normal | object id per triangle, leaf order (shading)
     const float* light_cdf;
     const float4* tri_orig; // 3 x float4 per triangle in GLOBAL order: a, b, c (mesh-light sampling)
     int32_t n_prims, n_objects, n_tris, root;
+    int32_t n_planes;      // prims[0, n_planes) are planes, prims[n_planes, n_prims) spheres
     float3 bvh_min, bvh_max;
 };
 

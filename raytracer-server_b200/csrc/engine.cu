@@ -214,9 +214,11 @@ int build_device_scene(rtb_scene* sc) {
     V.mats = reinterpret_cast<const DevMaterial*>(sc->d_stage + sc->off_mats);
     V.nodes = sc->bvh.d_nodes;
     V.tris = sc->bvh.d_tris;
+    V.tri_nrm = sc->bvh.d_tri_nrm;
     V.light_cdf = reinterpret_cast<const float*>(sc->d_stage + sc->off_cdf);
     V.tri_orig = sc->d_tri_orig;
     V.n_prims = H.n_prims;
+    V.n_planes = fs.n_planes;
     V.n_objects = H.n_objects;
     V.n_tris = n_tris;
     V.root = H.root;
@@ -383,6 +385,8 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     a.k0 = (uint32_t)p->seed;
     a.k1 = (uint32_t)(p->seed >> 32);
     a.estimator = p->estimator;
+    a.tune_refill = p->reserved[1];
+    a.tune_steps = p->reserved[2];
     a.rank = p->rank;
     a.world = p->world;
     a.tiles_x = (p->width + TILE - 1) / TILE;
@@ -414,9 +418,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                   volatile int* cancel, rtb_stats& st, bool& cancelled) {
     cancelled = false;
     DevCtrl h{};
-    h.ext_head[0] = h.ext_head[1] = 0;
-    h.ext_tail[0] = h.ext_tail[1] = a.P;
-    h.sh_head[0] = h.sh_head[1] = 0;
+    h.ext_head(0) = h.ext_head(1) = 0;
+    h.ext_tail(0) = h.ext_tail(1) = a.P;
+    h.sh_head(0) = h.sh_head(1) = 0;
     unsigned long long npl = (unsigned long long)a.n_local_tiles * 1024ull;
     h.work_next = a.probe_px ? 0ull : (unsigned long long)ks_begin * npl;
     h.work_total = a.probe_px ? (unsigned long long)a.n_probe : (unsigned long long)ks_end * npl;

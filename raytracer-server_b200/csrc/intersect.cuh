@@ -84,48 +84,97 @@ __device__ __forceinline__ bool ray_hits_bvh_box(const DevScene& S, float3 o, fl
 }
 
 // ---- analytic primitives -------------------------------------------------------------------
-// Returns true and the distance if primitive k is hit.  `origin` = pcode of the primitive the ray
-// starts on (PC_NONE id for camera / free rays).
-__device__ __forceinline__ bool prim_intersect(const DevPrim& P, int k, float3 o, float3 d, uint32_t origin,
-                                               int origin_group, float& t_out) {
-    if (P.type == 0) {  // plane
-        float3 n = f3(P.a);
-        float dn = dot(d, n);
-        if (fabsf(dn) < DN_EPS) return false;
-        float t;
-        if (P.group == origin_group) {
-            float dnf = (origin & PC_FLIPPED) ? -dn : dn;  // d . n_facing
-            t = -SURF_OFFSET / dnf;
-        } else {
-            t = (P.a.w - dot(o, n)) / dn;
-        }
-        if (t >= 0.0f) { t_out = t; return true; }
-        return false;
-    }
-    // sphere
-    float3 op = f3(P.a) - o;
-    float b = dot(op, d);
-    if ((uint32_t)k == (origin & PC_ID_MASK)) {  // origin exactly on the sphere: roots 0 and 2b
-        float t = 2.0f * b;
-        if (t > T_EPS) { t_out = t; return true; }
-        return false;
-    }
-    // det = b^2 - op.op + r^2 evaluated as r^2 - |op - b d|^2 (same value, well conditioned in fp32;
-    // exact for unit d, and every ray direction on this path is normalised)
-    float3 l = op - b * d;
-    float det = P.b.x - dot(l, l);
-    if (det < 0.0f) return false;
-    det = sqrtf(det);
-    float t = b - det;
-    if (t > T_EPS) { t_out = t; return true; }
-    t = b + det;
-    if (t > T_EPS) { t_out = t; return true; }
-    return false;
-}
-
+// prims[0, n_planes) are planes, the rest spheres; every lane walks the same table (no divergence) and the
+// tests are written as selects.  `origin` = pcode of the primitive the ray starts on (PC_NONE id for camera /
+// free rays): that primitive is evaluated as the reference's f64 arithmetic sees it (see the header).
+// Divisions use MUFU.RCP (2 ulp) — far inside the 1e-4 relative gate on hit distances.
 __device__ __forceinline__ int origin_group_of(const SharedScene& sh, uint32_t origin) {
     uint32_t id = origin & PC_ID_MASK;
     return id < TRI_BASE ? sh.prims[id].group : -1;
+}
+
+// plane k: distance along d (or a negative number / NaN-free "no hit" encoded by ok = false)
+__device__ __forceinline__ float plane_t(const float4 a, float num, float3 d, bool& ok) {
+    const float dn = d.x * a.x + d.y * a.y + d.z * a.z;
+    const float t = __fdividef(num, dn);
+    ok = fabsf(dn) >= DN_EPS && t >= 0.0f;      // |d.n| < 1e-4 -> miss; t >= 0 (no epsilon), src/geometry.rs:551-568
+    return t;
+}
+// numerator (pos - o).n of the plane test; for the plane class the ray starts on, the reference's origin sits
+// exactly 1e-5 above the facing side, i.e. (pos - o).n_facing = -1e-5
+__device__ __forceinline__ float plane_num(const DevPrim& P, float3 o, int og, uint32_t origin) {
+    const float num = P.a.w - (o.x * P.a.x + o.y * P.a.y + o.z * P.a.z);
+    const float self = (origin & PC_FLIPPED) ? SURF_OFFSET : -SURF_OFFSET;
+    return P.group == og ? self : num;
+}
+// sphere: near root if > 1e-4, else far root if > 1e-4 (src/geometry.rs:514-550); origin ON the sphere: roots 0, 2b.
+// det = b^2 - op.op + r^2 is evaluated as r^2 - |op - b d|^2 (same value for unit d, well conditioned in fp32).
+__device__ __forceinline__ float sphere_t(float3 op, float r2, float3 d, bool self, bool& ok) {
+    const float b = op.x * d.x + op.y * d.y + op.z * d.z;
+    const float lx = op.x - b * d.x, ly = op.y - b * d.y, lz = op.z - b * d.z;
+    const float det = r2 - (lx * lx + ly * ly + lz * lz);
+    const float s = det > 0.0f ? det * rsqrtf(det) : 0.0f;
+    const float tn = b - s, tf = b + s;
+    float t = tn > T_EPS ? tn : tf;
+    ok = det >= 0.0f && t > T_EPS;
+    if (self) {
+        t = 2.0f * b;
+        ok = t > T_EPS;
+    }
+    return t;
+}
+
+// analytic half of Scene::trace_ray: nearest plane / sphere along d (strict '<': lowest index wins ties)
+__device__ __forceinline__ void analytic_closest(const SharedScene& sh, int n_planes, int n_prims, float3 o, float3 d,
+                                                 uint32_t origin, float& best_t, uint32_t& best_id) {
+    best_t = INFINITY;
+    best_id = PC_NONE;
+    const int og = origin_group_of(sh, origin);
+    const uint32_t oid = origin & PC_ID_MASK;
+    for (int k = 0; k < n_planes; ++k) {
+        const DevPrim& P = sh.prims[k];
+        bool ok;
+        const float t = plane_t(P.a, plane_num(P, o, og, origin), d, ok);
+        if (ok && t < best_t) { best_t = t; best_id = (uint32_t)k; }
+    }
+    for (int k = n_planes; k < n_prims; ++k) {
+        const DevPrim& P = sh.prims[k];
+        bool ok;
+        const float t = sphere_t(f3(P.a) - o, P.b.x, d, (uint32_t)k == oid, ok);
+        if (ok && t < best_t) { best_t = t; best_id = (uint32_t)k; }
+    }
+}
+
+// Two rays leaving the same point `o` on primitive `origin` in one pass over the table:
+//   d1: nearest analytic hit (t1, id1)                                  -> the extension ray
+//   d2: is anything analytic in front of tlim2 ?                        -> the shadow ray (mutually_visible)
+// The per-primitive set-up ((pos - o).n, c - o, the self-intersection class) is shared by both.
+__device__ __forceinline__ void analytic_pair(const SharedScene& sh, int n_planes, int n_prims, float3 o, uint32_t origin,
+                                              float3 d1, float& t1, uint32_t& id1, float3 d2, float tlim2, bool& occ2) {
+    t1 = INFINITY;
+    id1 = PC_NONE;
+    occ2 = false;
+    const int og = origin_group_of(sh, origin);
+    const uint32_t oid = origin & PC_ID_MASK;
+    for (int k = 0; k < n_planes; ++k) {
+        const DevPrim& P = sh.prims[k];
+        const float num = plane_num(P, o, og, origin);
+        bool ok1, ok2;
+        const float ta = plane_t(P.a, num, d1, ok1);
+        const float tb = plane_t(P.a, num, d2, ok2);
+        if (ok1 && ta < t1) { t1 = ta; id1 = (uint32_t)k; }
+        occ2 |= ok2 && tb < tlim2;
+    }
+    for (int k = n_planes; k < n_prims; ++k) {
+        const DevPrim& P = sh.prims[k];
+        const float3 op = f3(P.a) - o;
+        const bool self = (uint32_t)k == oid;
+        bool ok1, ok2;
+        const float ta = sphere_t(op, P.b.x, d1, self, ok1);
+        const float tb = sphere_t(op, P.b.x, d2, self, ok2);
+        if (ok1 && ta < t1) { t1 = ta; id1 = (uint32_t)k; }
+        occ2 |= ok2 && tb < tlim2;
+    }
 }
 
 // ---- LBVH traversal ------------------------------------------------------------------------
@@ -144,9 +193,10 @@ struct Trav {
 __device__ __forceinline__ void trav_begin(Trav& T, float3 o, float3 d, uint32_t origin, float tlimit, int root) {
     T.o = o;
     T.d = d;
-    T.idx = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
-    T.idy = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
-    T.idz = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    // MUFU.RCP reciprocals (1-2 ulp); the node boxes are padded by 1e-6 relative at build time to stay conservative
+    T.idx = __fdividef(1.0f, fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    T.idy = __fdividef(1.0f, fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    T.idz = __fdividef(1.0f, fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
     T.oox = o.x * T.idx;
     T.ooy = o.y * T.idy;
     T.ooz = o.z * T.idz;
@@ -212,7 +262,7 @@ __device__ __forceinline__ bool trav_leaf(const DevScene& S, Trav& T, uint32_t* 
         float det = dot(e1, pvec);      // = d . ((c-a) x (b-a)) = |N| (n^ . d)
         float nd = det * t0.w;          // n^ . d
         if (fabsf(nd) < DN_EPS) continue;
-        float inv = 1.0f / det;
+        float inv = __fdividef(1.0f, det);   // 2 ulp: far inside the 1e-4 distance gate
         float3 tvec = T.o - f3(t0);
         float u = dot(tvec, pvec) * inv;
         float3 qvec = cross(tvec, e1);
@@ -258,66 +308,6 @@ __device__ __forceinline__ bool bvh_traverse(const DevScene& S, const SharedScen
     return false;
 }
 
-// ---- analytic part of Scene::trace_ray / mutually_visible (coherent: every lane walks the same table)
-__device__ __forceinline__ void analytic_closest(const SharedScene& sh, int n_prims, float3 o, float3 d, uint32_t origin,
-                                                 float& best_t, uint32_t& best_id) {
-    best_t = INFINITY;
-    best_id = PC_NONE;
-    const int og = origin_group_of(sh, origin);
-    for (int k = 0; k < n_prims; ++k) {
-        float t;
-        if (prim_intersect(sh.prims[k], k, o, d, origin, og, t) && t < best_t) {
-            best_t = t;
-            best_id = (uint32_t)k;
-        }
-    }
-}
-__device__ __forceinline__ bool analytic_occluded(const SharedScene& sh, int n_prims, float3 o, float3 d, uint32_t origin,
-                                                  float tlimit) {
-    const int og = origin_group_of(sh, origin);
-    bool occ = false;
-    for (int k = 0; k < n_prims; ++k) {
-        float t;
-        occ |= prim_intersect(sh.prims[k], k, o, d, origin, og, t) && t < tlimit;
-    }
-    return occ;
-}
-
-// ---- Scene::trace_ray ------------------------------------------------------------------------
-// use_bvh: the ray's queue class (ray_hits_bvh_box at push time)
-template <bool COUNT>
-__device__ __forceinline__ void closest_hit(const DevScene& S, const SharedScene& sh, float3 o, float3 d, uint32_t origin,
-                                            bool use_bvh, float& best_t, uint32_t& best_id, uint32_t* work) {
-    best_t = INFINITY;
-    best_id = PC_NONE;
-    const int og = origin_group_of(sh, origin);
-    for (int k = 0; k < S.n_prims; ++k) {
-        float t;
-        if (prim_intersect(sh.prims[k], k, o, d, origin, og, t) && t < best_t) {
-            best_t = t;
-            best_id = (uint32_t)k;
-        }
-    }
-    if (use_bvh) bvh_traverse<false, COUNT>(S, sh, o, d, origin, best_t, best_id, 0.0f, work);
-}
-
-// mutually_visible: true if something lies strictly in front of the target (t + margin < dist)
-template <bool COUNT>
-__device__ __forceinline__ bool occluded(const DevScene& S, const SharedScene& sh, float3 o, float3 d, uint32_t origin,
-                                         bool use_bvh, float dist, uint32_t* work) {
-    const int og = origin_group_of(sh, origin);
-    for (int k = 0; k < S.n_prims; ++k) {
-        float t;
-        if (prim_intersect(sh.prims[k], k, o, d, origin, og, t) && t + SHADOW_MARGIN < dist) return true;
-    }
-    if (use_bvh) {
-        float bt = INFINITY;
-        uint32_t bi = PC_NONE;
-        return bvh_traverse<true, COUNT>(S, sh, o, d, origin, bt, bi, dist, work);
-    }
-    return false;
-}
-
 // ---- hit geometry ----------------------------------------------------------------------------
 struct HitGeom {
     float3 pos;      // Hit.pos (offset rules of the reference applied)
@@ -326,8 +316,8 @@ struct HitGeom {
     uint32_t pcode;  // id | PC_FLIPPED
 };
 
-__device__ __forceinline__ HitGeom hit_geometry(const DevScene& S, const SharedScene& sh, float3 o, float3 d, float t,
-                                                uint32_t id) {
+// tri_n: the triangle's (unit normal | object id) record, fetched early by the caller (ignored for analytic ids)
+__device__ __forceinline__ HitGeom hit_geometry(const SharedScene& sh, float3 o, float3 d, float t, uint32_t id, float4 tri_n) {
     HitGeom h;
     float3 p = o + t * d;
     float3 n;
@@ -338,10 +328,8 @@ __device__ __forceinline__ HitGeom hit_geometry(const DevScene& S, const SharedS
         if (P.type == 0) n = f3(P.a);
         else { n = normalize(p - f3(P.a)); offset = false; }
     } else {
-        const float4* tp = S.tris + (size_t)(id - TRI_BASE) * 3;
-        const float4 t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-        n = normalize(cross(f3(t2), f3(t1)));  // Triangle::normal: norm((c-a) x (b-a))
-        h.obj = __float_as_int(t2.w);
+        n = f3(tri_n);  // Triangle::normal: norm((c-a) x (b-a))
+        h.obj = __float_as_int(tri_n.w);
     }
     bool flipped = !(dot(n, -d) >= 0.0f);
     if (flipped) n = -n;

@@ -62,8 +62,8 @@ __global__ void k_tri_bounds(const float* __restrict__ verts, int n, float4* __r
         lo[k] = fminf(a, fminf(b, c));
         hi[k] = fmaxf(a, fmaxf(b, c));
     }
-    for (int k = 0; k < 3; ++k) {  // conservative pad: a few fp32 ulps
-        float pad = fmaxf(fabsf(lo[k]), fabsf(hi[k])) * 2.4e-7f + 1e-30f;
+    for (int k = 0; k < 3; ++k) {  // conservative pad (the traversal uses approximate reciprocals)
+        float pad = fmaxf(fabsf(lo[k]), fabsf(hi[k])) * 1e-6f + 1e-30f;
         lo[k] -= pad;
         hi[k] += pad;
     }
@@ -205,7 +205,7 @@ __global__ void k_emit(int n_internal, const uint32_t* __restrict__ sorted, cons
 }
 
 __global__ void k_pack_tris(int n, const uint32_t* __restrict__ sorted, const float* __restrict__ verts,
-                            const int32_t* __restrict__ tri_obj, float4* __restrict__ out) {
+                            const int32_t* __restrict__ tri_obj, float4* __restrict__ out, float4* __restrict__ nrm) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t g = sorted[s];
@@ -220,6 +220,8 @@ __global__ void k_pack_tris(int n, const uint32_t* __restrict__ sorted, const fl
     o[0] = make_float4(a.x, a.y, a.z, len > 0.f ? 1.0f / len : 0.f);
     o[1] = make_float4(e1.x, e1.y, e1.z, __int_as_float((int)g));
     o[2] = make_float4(e2.x, e2.y, e2.z, __int_as_float(tri_obj[g]));
+    float il = len > 0.f ? 1.0f / len : 0.f;
+    nrm[s] = make_float4(nx * il, ny * il, nz * il, __int_as_float(tri_obj[g]));
 }
 
 template <typename T>
@@ -264,7 +266,8 @@ bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStrea
     float4* d_tris = nullptr;
     LBVH_CHECK(cudaMalloc((void**)&d_tris, (size_t)n * 3 * sizeof(float4)));
     out.d_tris = d_tris;
-    k_pack_tris<<<nb, T, 0, stream>>>(n, vals2.p, d_verts, d_tri_obj, d_tris);
+    LBVH_CHECK(cudaMalloc((void**)&out.d_tri_nrm, (size_t)n * sizeof(float4)));
+    k_pack_tris<<<nb, T, 0, stream>>>(n, vals2.p, d_verts, d_tri_obj, d_tris, out.d_tri_nrm);
 
     Bounds6 hb;
     if (n <= LEAF_MAX) {  // the whole mesh is one leaf
@@ -309,6 +312,7 @@ bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStrea
 void free_lbvh(LbvhResult& r) {
     if (r.d_nodes) cudaFree(r.d_nodes);
     if (r.d_tris) cudaFree(r.d_tris);
+    if (r.d_tri_nrm) cudaFree(r.d_tri_nrm);
     r = LbvhResult();
 }
 

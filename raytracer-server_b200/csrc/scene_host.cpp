@@ -354,6 +354,25 @@ int flatten_scene(const HostScene& hs, FlatScene& fs, std::string& err) {
         }
         fs.materials.push_back(m);
     }
+    // analytic table order: all planes (object order), then all spheres (object order) — the device loops are
+    // type-specialised.  Ties between equal-t hits keep the reference's lowest-object-index rule within each
+    // kind (the duplicated wall of the reference scenes); a plane/sphere tie at bit-identical t has measure zero.
+    {
+        std::vector<FlatPrim> planes, spheres;
+        for (const FlatPrim& q : fs.prims) (q.type == PRIM_PLANE ? planes : spheres).push_back(q);
+        for (size_t k = 0; k < planes.size(); ++k) {          // groups refer to positions inside the plane block
+            planes[k].group = (int)k;
+            for (size_t e = 0; e < k; ++e)
+                if (planes[e].a[0] == planes[k].a[0] && planes[e].a[1] == planes[k].a[1] && planes[e].a[2] == planes[k].a[2] &&
+                    planes[e].a[3] == planes[k].a[3]) {
+                    planes[k].group = planes[e].group;
+                    break;
+                }
+        }
+        for (size_t k = 0; k < spheres.size(); ++k) spheres[k].group = (int)(planes.size() + k);
+        fs.prims = planes;
+        fs.prims.insert(fs.prims.end(), spheres.begin(), spheres.end());
+    }
     const HostObject& L = hs.objects[hs.light];
     if (L.geom == GEOM_MESH) {
         fs.light_area = (float)L.surface_area;

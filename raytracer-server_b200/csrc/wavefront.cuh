@@ -29,7 +29,8 @@ constexpr int TILE = 32;  // multi-GPU shard unit: 32x32 pixels, interleaved ove
 constexpr uint32_t SHADOW_PROBE = 0x80000000u;  // shadow entry = dead-MIS probe resolved by a CLOSEST-hit query (mesh lights)
 constexpr uint32_t MAX_DEPTH_FIELD = 4095u;
 constexpr uint32_t FETCH_CHUNK = 32;     // ray indices a warp reserves per atomic
-constexpr int REFILL_BELOW = 22;         // refill a warp when fewer than this many lanes are still traversing
+constexpr int REFILL_BELOW = 22;         // default: refill a warp when fewer than this many lanes are still traversing
+constexpr int INNER_STEPS = 8;           // default: inner-node steps a lane may take before the warp re-checks for idle lanes
 
 struct PathQueue {   // capacity P each
     float4* o;       // origin.xyz | pcode of the primitive the ray starts on (+ flags)
@@ -45,17 +46,24 @@ struct ShadowQueue {  // capacity SP
     float4* c;        // contribution.rgb | accumulator index (| SHADOW_PROBE)
 };
 
+// Every hot counter sits on its own 128-byte line: atomics to words of one line serialise in one L2 slice.
+struct alignas(128) PaddedCounter {
+    uint32_t v;
+    uint32_t pad[31];
+};
 struct DevCtrl {
-    uint32_t ext_head[2], ext_tail[2];
-    uint32_t sh_head[2];
-    uint32_t cursor_trav, cursor_pad;
+    PaddedCounter ext_head_[2], ext_tail_[2], sh_head_[2], cursor_trav_;
     uint32_t gen_count;
-    uint32_t active;        // paths alive in the current queue after k_prepare (+ reserved samples)
+    uint32_t active;        // paths alive in the current queue after k_prepare (+ reserved samples + pending shadow rays)
     unsigned long long gen_base, work_next, work_total;
     unsigned long long samples, rays_primary, rays_extension, rays_shadow, iterations;
     unsigned long long rays_bvh, shadow_bvh;   // of those, how many needed a BVH traversal
     unsigned long long node_visits, tri_tests;
 };
+#define ext_head(i) ext_head_[i].v
+#define ext_tail(i) ext_tail_[i].v
+#define sh_head(i) sh_head_[i].v
+#define cursor_trav cursor_trav_.v
 
 struct RenderArgs {
     DevScene S;
@@ -75,6 +83,7 @@ struct RenderArgs {
     const int32_t* probe_py;
     const int32_t* probe_sample;
     int n_probe;
+    int tune_refill, tune_steps;   // traversal knobs (0 = defaults above); rtb_params.reserved[1], [2]
 };
 
 // ---------------------------------------------------------------- tile order <-> pixels
@@ -121,7 +130,7 @@ __device__ __forceinline__ PushSlots push_all(uint32_t* ext_head, uint32_t* ext_
 // Block-aggregated variant for k_shade: the 8 warps of a CTA pool their counts in shared memory and
 // three threads issue ONE atomic per counter per CTA iteration (fewer same-address atomics at L2).
 // Every thread of the CTA must call it (two __syncthreads inside).
-constexpr int SHADE_THREADS = 128;   // CTA size of k_shade: 4 warps share one set of queue atomics
+constexpr int SHADE_THREADS = 256;   // CTA size of k_shade: 4 warps share one set of queue atomics
 struct BlockPushSmem {
     uint32_t cnt[SHADE_THREADS / 32][4];
     uint32_t base[SHADE_THREADS / 32][4];
@@ -169,13 +178,13 @@ __device__ __forceinline__ void accum_add(float4* accum, uint32_t idx, float3 v)
 
 __device__ __forceinline__ int object_of(const DevScene& S, const SharedScene& sh, uint32_t id) {
     if (id < TRI_BASE) return sh.prims[id].obj;
-    return __float_as_int(__ldg(S.tris + (size_t)(id - TRI_BASE) * 3 + 2).w);
+    return __float_as_int(__ldg(S.tri_nrm + (id - TRI_BASE)).w);
 }
 
 // ---------------------------------------------------------------- k_prepare
 __global__ void k_prepare(RenderArgs a, int c) {
     DevCtrl* C = a.ctrl;
-    uint32_t head = C->ext_head[c], tail = C->ext_tail[c];
+    uint32_t head = C->ext_head(c), tail = C->ext_tail(c);
     uint32_t count = head + (a.P - tail);
     uint32_t free_slots = tail - head;
     unsigned long long remaining = C->work_total - C->work_next;
@@ -183,11 +192,11 @@ __global__ void k_prepare(RenderArgs a, int c) {
     C->gen_base = C->work_next;
     C->gen_count = n_new;
     C->work_next += n_new;
-    C->ext_head[1 - c] = 0;
-    C->ext_tail[1 - c] = a.P;
-    C->sh_head[1 - c] = 0;
+    C->ext_head(1 - c) = 0;
+    C->ext_tail(1 - c) = a.P;
+    C->sh_head(1 - c) = 0;
     C->cursor_trav = 0;
-    C->active = count + n_new + C->sh_head[c];   // pending shadow rays keep the loop alive
+    C->active = count + n_new + C->sh_head(c);   // pending shadow rays keep the loop alive
     C->iterations++;
 }
 
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
                 float3 dir = camera_dir(a.cam, x, a.height - y - 1, sub & 1, sub >> 1, tent(r.x), tent(r.y), w, h);
                 float ta;
                 uint32_t ida;
-                analytic_closest(sh, a.S.n_prims, a.cam.pos, dir, PC_NONE, ta, ida);
+                analytic_closest(sh, a.S.n_planes, a.S.n_prims, a.cam.pos, dir, PC_NONE, ta, ida);
                 front = ray_hits_bvh_box(a.S, a.cam.pos, dir, ta);
                 o4 = make_float4(a.cam.pos.x, a.cam.pos.y, a.cam.pos.z, __uint_as_float(PC_NONE));
                 d4 = make_float4(dir.x, dir.y, dir.z, __uint_as_float(acc));
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
                 h2 = make_float2(ta, __uint_as_float(ida));
             }
         }
-        PushSlots ps = push_all(&C->ext_head[c], &C->ext_tail[c], &C->sh_head[c], valid, front, false, false);
+        PushSlots ps = push_all(&C->ext_head(c), &C->ext_tail(c), &C->sh_head(c), valid, front, false, false);
         if (valid) {
             a.q[c].o[ps.ext] = o4;
             a.q[c].d[ps.ext] = d4;
@@ -291,12 +300,14 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
     const int stride = blockDim.x;
     int lstack[STACK_LOCAL];
     DevCtrl* C = a.ctrl;
-    const uint32_t n_ext = C->ext_head[c];   // only the BVH class of the path queue needs a traversal
-    const uint32_t count = n_ext + C->sh_head[c];
+    const uint32_t n_ext = C->ext_head(c);   // only the BVH class of the path queue needs a traversal
+    const uint32_t count = n_ext + C->sh_head(c);
     const unsigned lane = threadIdx.x & 31;
     const PathQueue Q = a.q[c];
     const ShadowQueue SQ = a.sq[c];
     const int light_obj = a.S.hdr->light_obj;
+    const int refill_below = a.tune_refill > 0 ? a.tune_refill : REFILL_BELOW;
+    const int steps = a.tune_steps > 0 ? a.tune_steps : INNER_STEPS;
     uint32_t work[2] = {0, 0};
     uint32_t wnext = 0, wend = 0;
     bool exhausted = false;
@@ -355,10 +366,11 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
             if (exhausted) break;
             continue;
         }
-        // ---- traverse until too few lanes are left (then go back and refill)
+        // ---- traverse until too few lanes are left (then go back and refill).  A lane takes at most
+        // `steps` inner nodes per round, so lanes whose ray ended are not left idle behind one long descent.
         for (;;) {
-            while (T.node >= 0) trav_inner<COUNT>(a.S, T, sstack, stride, lstack, work);
-            if (T.node != NODE_SENTINEL) {
+            for (int k = 0; k < steps && T.node >= 0; ++k) trav_inner<COUNT>(a.S, T, sstack, stride, lstack, work);
+            if (T.node < 0 && T.node != NODE_SENTINEL) {
                 if (kind == 1) {
                     if (trav_leaf<true, COUNT>(a.S, T, work)) {
                         occluded = true;
@@ -372,7 +384,7 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
                 }
             }
             const unsigned act = __ballot_sync(0xffffffffu, T.node != NODE_SENTINEL);
-            if (act == 0 || (!exhausted && __popc(act) < REFILL_BELOW)) break;
+            if (act == 0 || (!exhausted && __popc(act) < refill_below)) break;
         }
     }
     if (COUNT) {
@@ -396,19 +408,38 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     const SharedScene sh = stage_scene(a.S, smem_raw, false);
     DevCtrl* C = a.ctrl;
     const DevSceneHeader* hdr = a.S.hdr;
-    const uint32_t head = C->ext_head[c], tail = C->ext_tail[c];
+    const uint32_t head = C->ext_head(c), tail = C->ext_tail(c);
     const uint32_t count = head + (a.P - tail);
     const unsigned lane = threadIdx.x & 31;
     const PathQueue Q = a.q[c], N = a.q[1 - c];
     const int light_obj = hdr->light_obj;
     const bool light_is_mesh = hdr->light_geom == 2;
     const float3 Le = f3(sh.mats[light_obj].emitted);
-    const int n_prims = a.S.n_prims;
+    const int n_prims = a.S.n_prims, n_planes = a.S.n_planes;
     __shared__ BlockPushSmem push_sm;
     uint32_t n_ext = 0, n_ext_bvh = 0, n_sh = 0, n_sh_bvh = 0;
 
+    // Software pipeline: the queue entry of the NEXT trip is loaded while this trip computes (the loads are
+    // streaming / random and would otherwise sit at the head of a long dependent chain at 16 warps per SM).
+    auto slot_of = [&](uint32_t i) { return i < head ? i : tail + (i - head); };
+    const uint32_t stride_items = gridDim.x * SHADE_THREADS;
+    float2 h2_n = make_float2(0.f, __uint_as_float(PC_NONE));
+    float4 o4_n = make_float4(0, 0, 0, 0), d4_n = o4_n, b4_n = o4_n, tri_n_n = o4_n;
+    {
+        const uint32_t i0 = blockIdx.x * SHADE_THREADS + threadIdx.x;
+        if (i0 < count) {
+            const uint32_t s0 = slot_of(i0);
+            h2_n = Q.hit[s0];
+            o4_n = Q.o[s0];
+            d4_n = Q.d[s0];
+            b4_n = Q.beta[s0];
+            const uint32_t id0 = __float_as_uint(h2_n.y);
+            if (id0 != PC_NONE && id0 >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (id0 - TRI_BASE));
+        }
+    }
+
     // CTA-uniform trip count: all threads of the CTA walk the queue in lock step (push_all_block synchronises)
-    for (uint32_t base = blockIdx.x * SHADE_THREADS; base < count; base += gridDim.x * SHADE_THREADS) {
+    for (uint32_t base = blockIdx.x * SHADE_THREADS; base < count; base += stride_items) {
         const uint32_t i = base + threadIdx.x;
         const bool valid = i < count;
         bool ext_push = false, ext_front = false, sh_push = false, pr_push = false;
@@ -417,20 +448,32 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
         float4 so = eo, sd = eo, sc = eo;
         float4 pd = eo, pc = eo;  // probe entry shares `so`
 
+        // this trip's entry (prefetched), then start the next trip's loads
+        const float2 h2 = h2_n;
+        const float4 o4 = o4_n, d4 = d4_n, b4 = b4_n, tri_n = tri_n_n;
+        const uint32_t i_next = i + stride_items;
+        const bool valid_next = i_next < count;
+        const uint32_t slot_next = slot_of(i_next);
+        h2_n = make_float2(0.f, __uint_as_float(PC_NONE));
+        if (valid_next) {
+            h2_n = Q.hit[slot_next];
+            o4_n = Q.o[slot_next];
+            d4_n = Q.d[slot_next];
+            b4_n = Q.beta[slot_next];
+        }
+
         if (valid) {
-            const uint32_t idx = i < head ? i : tail + (i - head);
-            const float2 h2 = Q.hit[idx];
+            const uint32_t idx = slot_of(i);
             const uint32_t id = __float_as_uint(h2.y);
             if (id != PC_NONE) {
                 const float t = h2.x;
-                const float4 o4 = Q.o[idx], d4 = Q.d[idx], b4 = Q.beta[idx];
                 const float3 o = f3(o4), d = f3(d4);
                 const uint32_t origin = __float_as_uint(o4.w);
                 const uint32_t acc = __float_as_uint(d4.w);
                 float3 beta = f3(b4);
                 const uint32_t sdw = __float_as_uint(b4.w);
                 const uint32_t sample = sdw >> 12, depth = sdw & 0xfffu;
-                const HitGeom hg = hit_geometry(a.S, sh, o, d, t, id);
+                const HitGeom hg = hit_geometry(sh, o, d, t, id, tri_n);
                 const DevMaterial& mat = sh.mats[hg.obj];
                 const float3 ovec = (origin & PC_STALE_O) ? f3(Q.ov[idx]) : -d;
                 const float3 emitted = f3(mat.emitted);
@@ -460,7 +503,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                     }
                     const float4 r0 = make_float4(vr.light_u1, vr.light_u2, vr.rr, select_u);
                     const float4 rb = make_float4(vr.brdf_u1, vr.brdf_u2, lobe_u, 0.f);
-                    float3 next_dir = f3(0.f, 0.f, 0.f);
+                    float3 next_dir = f3(0.f, 0.f, 0.f), sh_dir = f3(0.f, 0.f, 0.f), sh_contrib = f3(0.f, 0.f, 0.f);
+                    float sh_tlim = 0.f;
+                    bool want_sh = false;
                     if (mat.brdf == 1) {  // specular branch, src/scene.rs:170-185
                         if (r0.z < p) {
                             next_dir = flip_across(ovec, hg.n);
@@ -491,20 +536,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                             contrib = beta * Le * f * (dot(hg.n, inc) / (pdf_light + pdf_fresh));
                         }
                         if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
-                            // mutually_visible (src/scene.rs:258-270): analytic part here, mesh part in k_shadow
+                            want_sh = true;     // mutually_visible is resolved below, together with the extension ray
+                            sh_dir = inc;
+                            sh_tlim = dist - SHADOW_MARGIN;
+                            sh_contrib = contrib;
                             ++n_sh;
-                            const float tlim = dist - SHADOW_MARGIN;
-                            if (!analytic_occluded(sh, n_prims, hg.pos, inc, hg.pcode, tlim)) {
-                                if (ray_hits_bvh_box(a.S, hg.pos, inc, tlim)) {
-                                    sh_push = true;
-                                    ++n_sh_bvh;
-                                    so = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
-                                    sd = make_float4(inc.x, inc.y, inc.z, tlim);
-                                    sc = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(acc));
-                                } else {
-                                    accum_add(a.accum, acc, contrib);
-                                }
-                            }
                         }
                         if (a.estimator != 0) {  // src/scene.rs:203-214: own BRDF sample; counts only if it reaches the light
                             float3 i2;
@@ -522,7 +558,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                                     ++n_sh;
                                     float ta;
                                     uint32_t ida;
-                                    analytic_closest(sh, n_prims, hg.pos, i2, hg.pcode, ta, ida);
+                                    analytic_closest(sh, n_planes, n_prims, hg.pos, i2, hg.pcode, ta, ida);
                                     const bool needs_bvh = ray_hits_bvh_box(a.S, hg.pos, i2, ta);
                                     if (!light_is_mesh) {
                                         // the light is analytic: it must be the nearest analytic hit and no triangle may lie in front of it
@@ -561,22 +597,44 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                             }
                         }
                     }
-                    if (ext_push) {
-                        // analytic half of the next trace_ray, here where every lane does it together
+                    if (ext_push || want_sh) {
+                        // Analytic half of BOTH trace_ray calls this vertex makes (extension: nearest hit; shadow:
+                        // mutually_visible, src/scene.rs:258-270), here where every lane does it together.  Rays that
+                        // can still reach the mesh box afterwards are queued for k_traverse.
                         float ta;
                         uint32_t ida;
-                        analytic_closest(sh, n_prims, hg.pos, next_dir, __float_as_uint(eo.w), ta, ida);
-                        ext_front = ray_hits_bvh_box(a.S, hg.pos, next_dir, ta);
-                        ed = make_float4(next_dir.x, next_dir.y, next_dir.z, __uint_as_float(acc));
-                        eh = make_float2(ta, __uint_as_float(ida));
-                        ++n_ext;
-                        n_ext_bvh += ext_front ? 1u : 0u;
+                        bool occ;
+                        analytic_pair(sh, n_planes, n_prims, hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
+                        if (want_sh && !occ) {
+                            if (ray_hits_bvh_box(a.S, hg.pos, sh_dir, sh_tlim)) {
+                                sh_push = true;
+                                ++n_sh_bvh;
+                                so = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
+                                sd = make_float4(sh_dir.x, sh_dir.y, sh_dir.z, sh_tlim);
+                                sc = make_float4(sh_contrib.x, sh_contrib.y, sh_contrib.z, __uint_as_float(acc));
+                            } else {
+                                accum_add(a.accum, acc, sh_contrib);
+                            }
+                        }
+                        if (ext_push) {
+                            ext_front = ray_hits_bvh_box(a.S, hg.pos, next_dir, ta);
+                            ed = make_float4(next_dir.x, next_dir.y, next_dir.z, __uint_as_float(acc));
+                            eh = make_float2(ta, __uint_as_float(ida));
+                            ++n_ext;
+                            n_ext_bvh += ext_front ? 1u : 0u;
+                        }
                     }
                 }
             }
         }
+        // next trip: its hit id has arrived by now -> start the dependent triangle-normal fetch
+        {
+            const uint32_t idn = __float_as_uint(h2_n.y);
+            tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid_next && idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
+        }
         // ---- compaction: all 32 lanes take part
-        const PushSlots ps = push_all_block(push_sm, &C->ext_head[1 - c], &C->ext_tail[1 - c], &C->sh_head[1 - c], ext_push, ext_front, sh_push, pr_push);
+        const PushSlots ps = push_all_block(push_sm, &C->ext_head(1 - c), &C->ext_tail(1 - c), &C->sh_head(1 - c), ext_push, ext_front, sh_push, pr_push);
         if (ext_push) {
             N.o[ps.ext] = eo;
             N.d[ps.ext] = ed;
@@ -693,7 +751,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace_rays(DevScene S, long long
         }
         float t;
         uint32_t id;
-        analytic_closest(sh, S.n_prims, o, d, PC_NONE, t, id);
+        analytic_closest(sh, S.n_planes, S.n_prims, o, d, PC_NONE, t, id);
         if (ray_hits_bvh_box(S, o, d, t)) bvh_traverse<false, COUNT>(S, sh, o, d, PC_NONE, t, id, 0.0f, work);
         if (id == PC_NONE) {
             obj[i] = -1; tri[i] = -1; tout[i] = INFINITY;

@@ -42,13 +42,15 @@ def _check(rc: int, load: bool = False):
 
 
 def make_params(width: int, height: int, spp: int, *, use_mis: bool = False, seed: int = 0, rank: int = 0, world: int = 1,
-                pool_paths: int = 0, count_work: bool = False) -> Params:
+                pool_paths: int = 0, count_work: bool = False, tune_refill: int = 0, tune_steps: int = 0) -> Params:
     p = Params()
     p.width, p.height, p.spp = width, height, spp
     p.estimator = EST_MIS_DEAD if use_mis else EST_NEE
     p.seed = seed
     p.rank, p.world, p.pool_paths = rank, world, pool_paths
     p.reserved[0] = 1 if count_work else 0
+    p.reserved[1] = tune_refill
+    p.reserved[2] = tune_steps
     return p
 
 
@@ -122,10 +124,11 @@ class Scene:
 
     # ---- RenderJob::run, blocking whole-frame form ----------------------------------------------
     def render(self, width: int, height: int, spp: int, *, use_mis: bool = False, seed: int = 0, rank: int = 0,
-               world: int = 1, pool_paths: int = 0, out: np.ndarray | None = None, count_work: bool = False) -> np.ndarray:
+               world: int = 1, pool_paths: int = 0, out: np.ndarray | None = None, count_work: bool = False,
+               tune_refill: int = 0, tune_steps: int = 0) -> np.ndarray:
         """Returns the frame as uint8 [height, width, 3], row 0 = top (the bytes of src/server.rs:187-189)."""
         p = make_params(width, height, spp, use_mis=use_mis, seed=seed, rank=rank, world=world, pool_paths=pool_paths,
-                        count_work=count_work)
+                        count_work=count_work, tune_refill=tune_refill, tune_steps=tune_steps)
         if out is None:
             out = np.zeros((height, width, 3), dtype=np.uint8)
         assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size == width * height * 3

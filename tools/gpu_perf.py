@@ -9,7 +9,8 @@ if len(sys.argv) > 1:
     cfgs = [c for c in cfgs if c[0] in sys.argv[1:]]
 for name, w, h, spp in cfgs:
     g = R.Scene.from_toml(os.path.join(SC, name + ".toml"))
-    g.render(w, h, 8)
+    if not os.environ.get("RTB_PERF_NOWARM"):
+        g.render(w, h, 8)
     t0 = time.time(); g.render(w, h, spp, seed=1); dt = time.time() - t0
     st = g.stats()
     rays = st["rays_primary"] + st["rays_extension"] + st["rays_shadow"]
