@@ -16,9 +16,9 @@ cleared, every sample is re-traced; the seed changes per step).
   e2e      : same metric through the host-buffer C-ABI call (rtb_scene_upload from pinned memory +
              rtb_render into a host buffer: H2D of the flattened scene and D2H of the frame inside
              the timed region)
-  roofline : the dominant kernel k_extend_shade (closest hit + shading + queue compaction) against
-             the HBM peak by its algorithmic queue bytes; `fp32` repeats it against the measured
-             FP32 FMA peak with SURVEY §8(d)'s flop model, which is the bound that actually applies
+  roofline : the kernel with the largest share of the step (k_shade or k_traverse) against the HBM peak
+             by its algorithmic queue bytes; `fp32` is the whole step against the measured FP32 FMA
+             peak with SURVEY §8(d)'s flop model; `roofline_other` is the second kernel
   cpu_baseline / --impl reference : oracle/ (f64 C++ port of the reference, octree-faithful, live
              NEE) on the host cores, bounded sample of the same frame.
 """
@@ -38,9 +38,16 @@ SCENES = os.path.join(ROOT, "tests", "golden", "scenes")
 SCENE = "flying_unicorn"
 METRIC = "samples/sec (Mrays/sec alongside) on flying_unicorn"
 UNIT = "samples/s"
-# algorithmic HBM bytes per path vertex in k_extend_shade (DESIGN.md "Kernels"):
-# read o,d,beta 48 B + write surviving o,d,beta 48 B + write NEE candidate 48 B
-EXT_BYTES_PER_VERTEX = 144.0
+# algorithmic HBM bytes of the two hot kernels per unit (DESIGN.md "Kernels and rooflines"):
+#   k_shade    per path vertex read  : hit 8 + origin/direction/throughput 3 x 16        = 56 B
+#              per extension ray written: origin/direction/throughput/hit                = 56 B
+#              per queued shadow ray written: origin/direction/contribution              = 48 B
+#              per NEE contribution added directly: one 16-byte RED                       = 16 B
+#   k_traverse per BVH extension ray: origin/direction 32 + hit read 8 + hit write 8     = 48 B
+#              per BVH shadow ray   : origin/direction/contribution 48 + one RED 16      = 64 B
+#              (+ the LBVH itself, 4 MB, which lives in L1/L2)
+SHADE_B_VERTEX, SHADE_B_EXT, SHADE_B_SHQ, SHADE_B_RED = 56.0, 56.0, 48.0, 16.0
+TRAV_B_EXT, TRAV_B_SH = 48.0, 64.0
 
 
 def workload(n_gpus: int):
@@ -210,9 +217,10 @@ def main():
         p = R.make_params(W, H, SPP, seed=1000 + i, rank=rank, world=world)
         scene.render_device(p, shard.data_ptr())
         st = scene.stats()
-        for k in ("samples", "rays_primary", "rays_extension", "rays_shadow", "kernel_launches", "iterations"):
+        for k in ("samples", "rays_primary", "rays_extension", "rays_shadow", "kernel_launches", "iterations", "rays_bvh",
+                  "shadow_bvh"):
             totals[k] = totals.get(k, 0) + st[k]
-        for k in ("render_ms", "extend_ms", "resolve_ms"):
+        for k in ("render_ms", "extend_ms", "shade_ms", "resolve_ms"):
             totals[k] = totals.get(k, 0.0) + st[k]
         if world > 1:
             dist.all_gather_into_tensor(gathered, shard)
@@ -268,11 +276,14 @@ def main():
         d2h = int(sharding.local_pixels(W, H, rank, world) * 3) if world > 1 else W * H * 3
         e2e_value = e2e_samples / e2e_dt * world
 
-        # ---- roofline of the dominant kernel (k_extend_shade), measured live over the timed region
+        # ---- rooflines of the two hot kernels, measured live over the timed region (CUDA events around every launch,
+        # recorded on the render stream inside librtb200 and summed); the one with the larger share is `roofline`
         n_launch = max(1.0, totals["iterations"])
-        ext_vertices = totals["rays_primary"] + totals["rays_extension"]
-        avg_launch_s = totals["extend_ms"] * 1e-3 / n_launch
-        achieved_gbs = ext_vertices * EXT_BYTES_PER_VERTEX / (totals["extend_ms"] * 1e-3) / 1e9
+        vertices = totals["rays_primary"] + totals["rays_extension"]      # path vertices shaded == closest-hit rays
+        shadow_direct = totals["rays_shadow"] - totals["shadow_bvh"]       # upper bound of the REDs issued by k_shade
+        shade_bytes = (vertices * SHADE_B_VERTEX + totals["rays_extension"] * SHADE_B_EXT + totals["shadow_bvh"] * SHADE_B_SHQ
+                       + shadow_direct * SHADE_B_RED)
+        trav_bytes = totals["rays_bvh"] * TRAV_B_EXT + totals["shadow_bvh"] * TRAV_B_SH
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -280,12 +291,23 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
+        traffic = {}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("k_extend_shade_dram_bytes_per_launch")
+                traffic = json.load(f)
         except Exception:
             pass
+
+        def roof(kernel, ms, nbytes):
+            gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "traffic": traffic.get(kernel + "_dram_bytes_per_launch"),
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
+                    "algorithmic_bytes_per_launch": nbytes / n_launch, "avg_launch_ms": ms / n_launch,
+                    "share_of_step": ms / max(totals["render_ms"], 1e-9)}
+
+        roofs = [roof("k_shade", totals["shade_ms"], shade_bytes), roof("k_traverse", totals["extend_ms"], trav_bytes)]
+        roofs.sort(key=lambda r: -r["share_of_step"])
         # FP32 view: flop model of SURVEY §8(d) with node visits / triangle tests measured by a counting pass
         pc = R.make_params(640, 360, 16, seed=9, count_work=True)
         cnt_frame = torch.zeros(sharding.shard_stride(640, 360, 1), dtype=torch.uint8, device=dev)
@@ -299,7 +321,7 @@ def main():
         fp32_peak = R.fp32_peak_tflops(local_rank)
         step_s = totals["render_ms"] * 1e-3
         fp32_achieved = ((totals["rays_primary"] + totals["rays_extension"] + totals["rays_shadow"]) * flops_per_ray
-                         + ext_vertices * flops_per_vertex) / step_s / 1e12
+                         + vertices * flops_per_vertex) / step_s / 1e12
 
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -313,7 +335,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "reference scene fixtures (tests/golden/scenes), Philox seeds per step",
             "config": {"workload": wl["name"], "width": W, "height": H, "spp": SPP, "samples_per_step": samples_per_step_total,
                        "parallelism": f"tiles32x32 interleaved x{world}" if world > 1 else "single GPU",
-                       "l2": "path/shadow queues 2 x 256 MiB + 192 MiB and 127 MiB of accumulators stream through HBM every iteration (> 126 MB L2); no L2 flush needed"},
+                       "l2": "every iteration streams the path / shadow queues (> 1.2 GB at the default 8 Mi path slots) and the 127 MiB accumulator buffer through HBM, far more than the 126 MB L2; no flush needed"},
             "mrays_per_s": rays / elapsed / 1e6,
             "rays_per_sample": rays / max(1.0, job["samples"]),
             "device_ms_per_step": totals["render_ms"] / max(1, args.steps),
@@ -321,14 +343,14 @@ def main():
                     "ms_per_step": e2e_dt / e2e_steps * 1e3, "api": "rtb_scene_upload + rtb_render (host RGB8 frame)"},
             "gpu_launches": int(job["kernel_launches"]),
             "clocks": clk,
-            "roofline": {"kernel": "k_extend_shade", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "bytes_per_vertex": EXT_BYTES_PER_VERTEX, "avg_launch_ms": avg_launch_s * 1e3,
-                         "share_of_step": totals["extend_ms"] / max(totals["render_ms"], 1e-9),
-                         "fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
-                                  "flops_per_ray": flops_per_ray, "flops_per_vertex": flops_per_vertex,
-                                  "bvh_nodes_per_ray": n_node, "tri_tests_per_ray": n_tri,
-                                  "peak_source": "rtb_fp32_peak FMA chain, this run"}},
+            "roofline": dict(roofs[0], fp32={"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                                             "frac": fp32_achieved / fp32_peak, "flops_per_ray": flops_per_ray,
+                                             "flops_per_vertex": flops_per_vertex, "bvh_nodes_per_ray": n_node,
+                                             "tri_tests_per_ray": n_tri, "scope": "whole step, flop model of SURVEY 8(d)",
+                                             "peak_source": "rtb_fp32_peak FMA chain, this run"}),
+            "roofline_other": roofs[1],
+            "bvh_ray_fraction": {"extension": totals["rays_bvh"] / max(1.0, vertices),
+                                 "shadow": totals["shadow_bvh"] / max(1.0, totals["rays_shadow"])},
             "cpu_baseline": cpu,
         }
     if dist is not None:

@@ -505,7 +505,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
 // full render of this rank's tiles into the context's accumulators, then resolve
 int render_into_context(rtb_scene* sc, const rtb_params* p, RenderContext* c, RenderArgs& a, volatile int* cancel, rtb_stats& st,
                         bool& cancelled) {
-    uint32_t P = p->pool_paths > 0 ? (uint32_t)p->pool_paths : (1u << 22);
+    uint32_t P = p->pool_paths > 0 ? (uint32_t)p->pool_paths : (1u << 23);
     P = std::max<uint32_t>(P, 1024u);
     P = (P + 31u) & ~31u;
     uint32_t SP = p->estimator == RTB_EST_NEE ? P : 2 * P;
@@ -920,7 +920,7 @@ void job_worker(rtb_job* j) {
         j->finished = true;
         j->cv.notify_all();
     };
-    uint32_t P = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 22);
+    uint32_t P = p.pool_paths > 0 ? (uint32_t)p.pool_paths : (1u << 23);
     P = (std::max<uint32_t>(P, 1024u) + 31u) & ~31u;
     uint32_t SP = p.estimator == RTB_EST_NEE ? P : 2 * P;
     const size_t accum_elems = (size_t)p.width * p.height * 4;
