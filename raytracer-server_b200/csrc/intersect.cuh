@@ -230,19 +230,30 @@ __device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, int* ssta
     float tmax0 = fminf(fminf(fmaxf(a0, a1), fmaxf(a2, a3)), fminf(fmaxf(a4, a5), T.tlimit));
     float tmin1 = fmaxf(fmaxf(fminf(b0, b1), fminf(b2, b3)), fmaxf(fminf(b4, b5), 0.0f));
     float tmax1 = fminf(fminf(fmaxf(b0, b1), fmaxf(b2, b3)), fminf(fmaxf(b4, b5), T.tlimit));
-    bool h0 = tmin0 <= tmax0, h1 = tmin1 <= tmax1;
-    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-    if (h0 && h1) {
-        bool swap = tmin1 < tmin0;
-        int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-        if (T.sp < STACK_SMEM) sstack[T.sp * stride] = farc;
-        else lstack[T.sp - STACK_SMEM] = farc;
-        ++T.sp;
-        T.node = nearc;
-    } else if (h0 || h1) {
-        T.node = h0 ? c0 : c1;
-    } else {
-        trav_pop(T, sstack, stride, lstack);
+    const bool h0 = tmin0 <= tmax0, h1 = tmin1 <= tmax1;
+    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    // Select-based step (no three-way branch): the lane always peeks at its stack top; "both hit" pushes the
+    // farther child, "none hit" pops.  Only the (rare) spill beyond STACK_SMEM levels branches.
+    const bool both = h0 && h1, none = !h0 && !h1;
+    const bool swap = tmin1 < tmin0;
+    const int nearc = both ? (swap ? c1 : c0) : (h0 ? c0 : c1);
+    const int farc = swap ? c0 : c1;
+    if (T.sp < STACK_SMEM) {
+        int* slot = sstack + max(T.sp - (none ? 1 : 0), 0) * stride;   // push target, or the top entry when popping
+        const int top = *slot;
+        if (both) *slot = farc;
+        T.node = none ? (T.sp == 0 ? NODE_SENTINEL : top) : nearc;
+        T.sp += both ? 1 : (none && T.sp > 0 ? -1 : 0);
+    } else {  // spill levels (local memory); T.sp == STACK_SMEM pops from shared memory via trav_pop
+        if (both) {
+            lstack[T.sp - STACK_SMEM] = farc;
+            ++T.sp;
+            T.node = nearc;
+        } else if (none) {
+            trav_pop(T, sstack, stride, lstack);
+        } else {
+            T.node = nearc;
+        }
     }
 }
 
