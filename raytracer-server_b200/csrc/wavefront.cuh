@@ -135,6 +135,18 @@ struct BlockPushSmem {
     uint32_t cnt[SHADE_THREADS / 32][4];
     uint32_t base[SHADE_THREADS / 32][4];
 };
+// k_shade writes its outputs ONE TRIP LATE: a trip stages its new rays in shared memory and issues the queue
+// atomics without waiting; the next trip (a few microseconds of arithmetic later) picks the returned bases up
+// and flushes the staged rays.  The round trip of the global atomics is hidden behind a whole trip.
+struct ShadeStage {
+    float4 eo[SHADE_THREADS], ed[SHADE_THREADS], eb[SHADE_THREADS], ev[SHADE_THREADS];
+    float4 so[SHADE_THREADS], sd[SHADE_THREADS], sc[SHADE_THREADS], pd[SHADE_THREADS], pc[SHADE_THREADS];
+    float2 eh[SHADE_THREADS];
+    uint32_t meta[SHADE_THREADS];               // bit0 ext, bit1 front, bit2 shadow, bit3 probe, bits 8.. ranks
+    uint32_t cnt[2][SHADE_THREADS / 32][4];     // per-warp counts {front, back, shadow+probe}, double buffered
+    uint32_t base[SHADE_THREADS / 32][4];       // per-warp bases of the trip being flushed
+};
+
 __device__ __forceinline__ PushSlots push_all_block(BlockPushSmem& sm, uint32_t* ext_head, uint32_t* ext_tail, uint32_t* sh_head,
                                                     bool ext_push, bool ext_front, bool sh_push, bool pr_push) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -399,6 +411,56 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
     }
 }
 
+// threads 0..2 (class = threadIdx.x: front, back, shadow): turn the base returned by LAST trip's atomic into
+// per-warp bases for the staged trip, then issue THIS trip's atomic without waiting for it
+__device__ __forceinline__ void shade_reserve(ShadeStage& st, int cbuf, bool have_prev, uint32_t& pend_base, uint32_t* ctr_front,
+                                              uint32_t* ctr_back, uint32_t* ctr_sh) {
+    const int cls = threadIdx.x;
+    if (have_prev) {
+        const uint32_t b = pend_base;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SHADE_THREADS / 32; ++w) {
+            st.base[w][cls] = cls == 1 ? b - run : b + run;   // the back class grows downward
+            run += st.cnt[cbuf ^ 1][w][cls];
+        }
+    }
+    if (ctr_front) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < SHADE_THREADS / 32; ++w) tot += st.cnt[cbuf][w][cls];
+        pend_base = 0;
+        if (tot) pend_base = cls == 0 ? atomicAdd(ctr_front, tot) : (cls == 1 ? atomicSub(ctr_back, tot) : atomicAdd(ctr_sh, tot));
+    }
+}
+// every thread writes the rays it staged one trip ago
+__device__ __forceinline__ void shade_flush(const ShadeStage& st, const PathQueue& N, const ShadowQueue& SQ) {
+    const unsigned warp = threadIdx.x >> 5;
+    const uint32_t m = st.meta[threadIdx.x];
+    if (m & 1u) {
+        const uint32_t r = (m >> 8) & 63u;
+        const uint32_t slot = (m & 2u) ? st.base[warp][0] + r : st.base[warp][1] - 1u - r;
+        const float4 eo = st.eo[threadIdx.x];
+        N.o[slot] = eo;
+        N.d[slot] = st.ed[threadIdx.x];
+        N.beta[slot] = st.eb[threadIdx.x];
+        N.hit[slot] = st.eh[threadIdx.x];
+        if (__float_as_uint(eo.w) & PC_STALE_O) N.ov[slot] = st.ev[threadIdx.x];
+    }
+    if (m & 4u) {
+        const uint32_t slot = st.base[warp][2] + ((m >> 14) & 63u);
+        SQ.o[slot] = st.so[threadIdx.x];
+        SQ.d[slot] = st.sd[threadIdx.x];
+        SQ.c[slot] = st.sc[threadIdx.x];
+    }
+    if (m & 8u) {
+        const uint32_t slot = st.base[warp][2] + ((m >> 20) & 63u);
+        SQ.o[slot] = st.so[threadIdx.x];
+        SQ.d[slot] = st.pd[threadIdx.x];
+        SQ.c[slot] = st.pc[threadIdx.x];
+    }
+}
+
 // ---------------------------------------------------------------- k_shade
 // Everything of reflected_radiance except the mesh traversal.  Coherent: static warp -> slot mapping,
 // no work-fetch atomics; the only atomics are the queue pushes (3 per warp, overlapped) and the
@@ -416,7 +478,15 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     const bool light_is_mesh = hdr->light_geom == 2;
     const float3 Le = f3(sh.mats[light_obj].emitted);
     const int n_prims = a.S.n_prims, n_planes = a.S.n_planes;
-    __shared__ BlockPushSmem push_sm;
+    __shared__ ShadeStage st;
+    uint32_t pend_base = 0;   // threads 0..2: value returned by last trip's atomic for class threadIdx.x
+    bool have_prev = false;   // CTA-uniform: a staged trip is waiting to be flushed
+    int cbuf = 0;
+    const unsigned warp = threadIdx.x >> 5;
+    const ShadowQueue SQ = a.sq[1 - c];
+    uint32_t* const ctr_front = &C->ext_head(1 - c);
+    uint32_t* const ctr_back = &C->ext_tail(1 - c);
+    uint32_t* const ctr_sh = &C->sh_head(1 - c);
     uint32_t n_ext = 0, n_ext_bvh = 0, n_sh = 0, n_sh_bvh = 0;
 
     // Software pipeline: the queue entry of the NEXT trip is loaded while this trip computes (the loads are
@@ -633,26 +703,43 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
             tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid_next && idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
         }
-        // ---- compaction: all 32 lanes take part
-        const PushSlots ps = push_all_block(push_sm, &C->ext_head(1 - c), &C->ext_tail(1 - c), &C->sh_head(1 - c), ext_push, ext_front, sh_push, pr_push);
-        if (ext_push) {
-            N.o[ps.ext] = eo;
-            N.d[ps.ext] = ed;
-            N.beta[ps.ext] = eb;
-            N.hit[ps.ext] = eh;
-            if (__float_as_uint(eo.w) & PC_STALE_O) N.ov[ps.ext] = ev;
+        // ---- compaction, one trip late (see ShadeStage): all threads of the CTA take part
+        const unsigned mf = __ballot_sync(0xffffffffu, ext_push && ext_front);
+        const unsigned mb = __ballot_sync(0xffffffffu, ext_push && !ext_front);
+        const unsigned ms = __ballot_sync(0xffffffffu, sh_push);
+        const unsigned mp = __ballot_sync(0xffffffffu, pr_push);
+        if (lane == 0) {
+            st.cnt[cbuf][warp][0] = __popc(mf);
+            st.cnt[cbuf][warp][1] = __popc(mb);
+            st.cnt[cbuf][warp][2] = __popc(ms) + __popc(mp);
         }
-        const ShadowQueue SQ = a.sq[1 - c];
-        if (sh_push) {
-            SQ.o[ps.sh] = so;
-            SQ.d[ps.sh] = sd;
-            SQ.c[ps.sh] = sc;
+        __syncthreads();
+        if (threadIdx.x < 3) shade_reserve(st, cbuf, have_prev, pend_base, ctr_front, ctr_back, ctr_sh);
+        __syncthreads();
+        if (have_prev) shade_flush(st, N, SQ);
+        {   // stage this trip
+            const unsigned below = (1u << lane) - 1u;
+            const uint32_t r_ext = ext_front ? __popc(mf & below) : __popc(mb & below);
+            const uint32_t r_sh = __popc(ms & below), r_pr = __popc(ms) + __popc(mp & below);
+            st.meta[threadIdx.x] = (ext_push ? 1u : 0u) | (ext_front ? 2u : 0u) | (sh_push ? 4u : 0u) | (pr_push ? 8u : 0u) |
+                                   (r_ext << 8) | (r_sh << 14) | (r_pr << 20);
+            if (ext_push) {
+                st.eo[threadIdx.x] = eo; st.ed[threadIdx.x] = ed; st.eb[threadIdx.x] = eb; st.eh[threadIdx.x] = eh;
+                if (__float_as_uint(eo.w) & PC_STALE_O) st.ev[threadIdx.x] = ev;
+            }
+            if (sh_push || pr_push) st.so[threadIdx.x] = so;
+            if (sh_push) { st.sd[threadIdx.x] = sd; st.sc[threadIdx.x] = sc; }
+            if (pr_push) { st.pd[threadIdx.x] = pd; st.pc[threadIdx.x] = pc; }
         }
-        if (pr_push) {
-            SQ.o[ps.pr] = so;
-            SQ.d[ps.pr] = pd;
-            SQ.c[ps.pr] = pc;
-        }
+        have_prev = true;
+        cbuf ^= 1;
+    }
+    // epilogue: flush the last staged trip
+    if (have_prev) {
+        __syncthreads();
+        if (threadIdx.x < 3) shade_reserve(st, cbuf, true, pend_base, nullptr, nullptr, nullptr);
+        __syncthreads();
+        shade_flush(st, N, SQ);
     }
     // counters
     for (int off = 16; off; off >>= 1) {
