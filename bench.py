@@ -335,7 +335,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "reference scene fixtures (tests/golden/scenes), Philox seeds per step",
             "config": {"workload": wl["name"], "width": W, "height": H, "spp": SPP, "samples_per_step": samples_per_step_total,
                        "parallelism": f"tiles32x32 interleaved x{world}" if world > 1 else "single GPU",
-                       "l2": "every iteration streams the path / shadow queues (> 1.2 GB at the default 8 Mi path slots) and the 127 MiB accumulator buffer through HBM, far more than the 126 MB L2; no flush needed"},
+                       "l2": "every iteration streams the path / shadow queues (several GB: 32 Mi path slots x 240 B at this frame size) and the 127 MiB accumulator buffer through HBM, far more than the 126 MB L2; no flush needed"},
             "mrays_per_s": rays / elapsed / 1e6,
             "rays_per_sample": rays / max(1.0, job["samples"]),
             "device_ms_per_step": totals["render_ms"] / max(1, args.steps),

@@ -176,6 +176,9 @@ int rtb_job_next(rtb_job* job, uint16_t* x, uint16_t* y, uint8_t* n, uint8_t* rg
  * each record occupies 6+3n bytes back to back.  Returns the number of records written (0 = complete,
  * RTB_ESTOPPED = cancelled and nothing written). */
 int rtb_job_next_messages(rtb_job* job, uint8_t* buf, int64_t buf_bytes, int32_t max_records, int64_t* bytes_written);
+/* whole-frame form (progressive display): copies the latest finished pass (height*width*3 bytes, row 0 = top)
+ * and its 0-based pass index; 1 = frame copied, 0 = all passes delivered, RTB_ESTOPPED after a cancel */
+int rtb_job_next_frame(rtb_job* job, uint8_t* rgb8_out, int32_t* pass_index);
 int rtb_job_cancel(rtb_job* job);
 int rtb_job_end(rtb_job* job);
 

@@ -62,7 +62,7 @@ class ObjectInfo(C.Structure):
 EXPORTS = [
     "rtb_last_error", "rtb_scene_load_toml", "rtb_scene_load_toml_string", "rtb_scene_destroy", "rtb_scene_get_info", "rtb_scene_object",
     "rtb_scene_upload", "rtb_scene_triangles", "rtb_render", "rtb_local_pixels", "rtb_tile_map", "rtb_render_device",
-    "rtb_untile_device", "rtb_get_stats", "rtb_job_begin", "rtb_job_next", "rtb_job_next_messages", "rtb_job_cancel",
+    "rtb_untile_device", "rtb_get_stats", "rtb_job_begin", "rtb_job_next", "rtb_job_next_messages", "rtb_job_next_frame", "rtb_job_cancel",
     "rtb_job_end", "rtb_trace_primary", "rtb_trace_rays", "rtb_sample_radiance", "rtb_fp32_peak",
 ]
 
@@ -100,6 +100,7 @@ def lib():
     L.rtb_job_next.argtypes = [vp, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.POINTER(C.c_uint8),
                                C.POINTER(C.c_uint8)]
     L.rtb_job_next_messages.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
+    L.rtb_job_next_frame.argtypes = [vp, C.POINTER(C.c_uint8), ip]
     L.rtb_job_cancel.argtypes = [vp]
     L.rtb_job_end.argtypes = [vp]
     L.rtb_trace_primary.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, ip, ip, fp]

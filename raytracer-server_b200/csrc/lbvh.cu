@@ -17,8 +17,12 @@
 
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
 
 namespace rtb {
 namespace {
@@ -233,9 +237,99 @@ struct DevBuf {
 
 }  // namespace
 
+// ---- EXPERIMENT (RTB_BVH=sah): host-side binned-SAH build into the same node format, to measure how much
+// traversal time the LBVH's tree quality costs.  Not the product path.
+namespace {
+struct HB { float lo[3], hi[3]; };
+struct SahBuilder {
+    const float* v; int n;
+    std::vector<HB> tb; std::vector<float> cen;   // per triangle
+    std::vector<int> order;
+    std::vector<float4> nodes;                    // 4 per node
+    static float area(const HB& b) { float dx=b.hi[0]-b.lo[0], dy=b.hi[1]-b.lo[1], dz=b.hi[2]-b.lo[2]; return 2.f*(dx*dy+dy*dz+dz*dx); }
+    static void grow(HB& a, const HB& b) { for (int k=0;k<3;++k){ a.lo[k]=fminf(a.lo[k],b.lo[k]); a.hi[k]=fmaxf(a.hi[k],b.hi[k]); } }
+    static HB empty() { HB b; for (int k=0;k<3;++k){ b.lo[k]=FLT_MAX; b.hi[k]=-FLT_MAX; } return b; }
+    // returns encoded ref (>=0 node, <0 leaf) and the box
+    int build(int first, int count, HB& box) {
+        box = empty();
+        HB cb = empty();
+        for (int i=first;i<first+count;++i){ int t=order[i]; grow(box,tb[t]); for(int k=0;k<3;++k){ cb.lo[k]=fminf(cb.lo[k],cen[3*t+k]); cb.hi[k]=fmaxf(cb.hi[k],cen[3*t+k]); } }
+        if (count <= 4) {
+            bool make_leaf = count <= 2;
+            if (!make_leaf) {  // SAH decides below; fall through to try a split
+            }
+            if (make_leaf) return ~((first << 3) | (count - 1));
+        }
+        const int NB = 16;
+        float best = FLT_MAX; int bax=-1, bsplit=-1;
+        for (int ax=0; ax<3; ++ax) {
+            float ext = cb.hi[ax]-cb.lo[ax];
+            if (!(ext > 0.f)) continue;
+            HB bb[NB]; int bc[NB];
+            for (int b=0;b<NB;++b){ bb[b]=empty(); bc[b]=0; }
+            for (int i=first;i<first+count;++i){ int t=order[i]; int b=(int)((cen[3*t+ax]-cb.lo[ax])/ext*NB); if(b>=NB)b=NB-1; if(b<0)b=0; grow(bb[b],tb[t]); bc[b]++; }
+            float ra[NB]; HB acc=empty();
+            for (int b=NB-1;b>0;--b){ grow(acc,bb[b]); ra[b]=area(acc); }
+            acc=empty(); int lc=0; int rc=count;
+            for (int b=0;b<NB-1;++b){ grow(acc,bb[b]); lc+=bc[b]; rc=count-lc; if(lc==0||rc==0) continue; float cost=area(acc)*lc+ra[b+1]*rc; if(cost<best){best=cost;bax=ax;bsplit=b;} }
+        }
+        float leaf_cost = area(box) * count;
+        if (bax < 0 || (count <= 4 && best >= leaf_cost)) {
+            if (count <= 8) return ~((first << 3) | (count - 1));
+            // degenerate: median split on order
+            int mid = first + count/2; HB lb, rb; int idx=(int)nodes.size()/4; nodes.resize(nodes.size()+4);
+            int l = build(first, mid-first, lb), r = build(mid, first+count-mid, rb);
+            emit(idx, l, r, lb, rb); return idx;
+        }
+        float ext = cb.hi[bax]-cb.lo[bax];
+        int mid = (int)(std::partition(order.begin()+first, order.begin()+first+count, [&](int t){ int b=(int)((cen[3*t+bax]-cb.lo[bax])/ext*NB); if(b>=NB)b=NB-1; if(b<0)b=0; return b<=bsplit; }) - order.begin());
+        if (mid==first || mid==first+count) mid = first+count/2;
+        int idx=(int)nodes.size()/4; nodes.resize(nodes.size()+4);
+        HB lb, rb;
+        int l = build(first, mid-first, lb), r = build(mid, first+count-mid, rb);
+        emit(idx, l, r, lb, rb);
+        return idx;
+    }
+    void emit(int idx, int l, int r, const HB& a, const HB& b) {
+        float4* o = &nodes[(size_t)idx*4];
+        o[0]=make_float4(a.lo[0],a.hi[0],a.lo[1],a.hi[1]);
+        o[1]=make_float4(b.lo[0],b.hi[0],b.lo[1],b.hi[1]);
+        o[2]=make_float4(a.lo[2],a.hi[2],b.lo[2],b.hi[2]);
+        int li=l, ri=r; float fl, fr; memcpy(&fl,&li,4); memcpy(&fr,&ri,4);
+        o[3]=make_float4(fl,fr,0.f,0.f);
+    }
+};
+}  // namespace
+
+static bool build_sah_host(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err) {
+    std::vector<float> hv((size_t)n*9);
+    LBVH_CHECK(cudaMemcpyAsync(hv.data(), d_verts, hv.size()*sizeof(float), cudaMemcpyDeviceToHost, stream));
+    LBVH_CHECK(cudaStreamSynchronize(stream));
+    SahBuilder B; B.v=hv.data(); B.n=n; B.tb.resize(n); B.cen.resize((size_t)3*n); B.order.resize(n);
+    HB all=SahBuilder::empty();
+    for (int i=0;i<n;++i){ HB b=SahBuilder::empty(); for(int k=0;k<3;++k){ for(int q=0;q<3;++q){ float x=hv[(size_t)i*9+3*q+k]; b.lo[k]=fminf(b.lo[k],x); b.hi[k]=fmaxf(b.hi[k],x);} float pad=fmaxf(fabsf(b.lo[k]),fabsf(b.hi[k]))*1e-6f+1e-30f; b.lo[k]-=pad; b.hi[k]+=pad; B.cen[3*i+k]=0.5f*(b.lo[k]+b.hi[k]); } B.tb[i]=b; SahBuilder::grow(all,b); B.order[i]=i; }
+    HB rootbox; int root = B.build(0, n, rootbox);
+    std::vector<uint32_t> ord(B.order.begin(), B.order.end());
+    uint32_t* d_ord=nullptr;
+    LBVH_CHECK(cudaMalloc((void**)&d_ord, (size_t)n*4));
+    LBVH_CHECK(cudaMemcpyAsync(d_ord, ord.data(), (size_t)n*4, cudaMemcpyHostToDevice, stream));
+    LBVH_CHECK(cudaMalloc((void**)&out.d_tris, (size_t)n*3*sizeof(float4)));
+    LBVH_CHECK(cudaMalloc((void**)&out.d_tri_nrm, (size_t)n*sizeof(float4)));
+    k_pack_tris<<<(n+255)/256, 256, 0, stream>>>(n, d_ord, d_verts, d_tri_obj, out.d_tris, out.d_tri_nrm);
+    out.n_nodes=(int)B.nodes.size()/4;
+    LBVH_CHECK(cudaMalloc((void**)&out.d_nodes, (size_t)(out.n_nodes?out.n_nodes:1)*4*sizeof(float4)));
+    if (out.n_nodes) LBVH_CHECK(cudaMemcpyAsync(out.d_nodes, B.nodes.data(), B.nodes.size()*sizeof(float4), cudaMemcpyHostToDevice, stream));
+    LBVH_CHECK(cudaStreamSynchronize(stream));
+    cudaFree(d_ord);
+    out.root=root; out.n_leaves=out.n_nodes+1;
+    for (int k=0;k<3;++k){ out.bmin[k]=all.lo[k]; out.bmax[k]=all.hi[k]; }
+    return true;
+}
+
 bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err) {
     out = LbvhResult();
     if (n <= 0) return true;
+    if (const char* e = getenv("RTB_BVH")) if (std::string(e) == "sah") return build_sah_host(d_verts, d_tri_obj, n, stream, out, err);
     const int T = 256;
     const int nb = (n + T - 1) / T;
     const int ni = n - 1;

@@ -221,6 +221,22 @@ class RenderJob:
                 yield raw[off: off + 6 + 3 * n]
                 off += 6 + 3 * n
 
+    def frames(self):
+        """Progressive display: yields (pass_index, frame uint8 [h, w, 3]) once per finished pass."""
+        L = _abi.lib()
+        h, w = self.params.height, self.params.width
+        idx = C.c_int32()
+        while True:
+            frame = np.empty((h, w, 3), dtype=np.uint8)
+            rc = L.rtb_job_next_frame(self._h, frame.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(idx))
+            if rc == _abi.RTB_ESTOPPED:
+                self.cancelled = True
+                return
+            _check(rc)
+            if rc == 0:
+                return
+            yield idx.value, frame
+
     def stop(self):
         if self._h.value:
             _abi.lib().rtb_job_cancel(self._h)

@@ -160,6 +160,21 @@ def test_progressive_passes_converge(gpu_scene, rtb):
     assert errs[-1] <= 0.01 and errs[0] > errs[-1]     # the last pass IS the final frame; earlier ones are noisier
 
 
+def test_progressive_whole_frames(gpu_scene, rtb):
+    # BASELINE config 5: 1 sample per pixel per frame, cycling the four sub-pixels (4 frames = reference spp 4)
+    g = gpu_scene("cornell_box")
+    W, H, spp = 200, 150, 32
+    final = g.render(W, H, spp, seed=8).astype(int)
+    job = rtb.RenderJob(g, W, H, spp, seed=8, passes=spp)
+    got = list(job.frames())
+    job.close()
+    assert [i for i, _ in got] == list(range(spp))
+    errs = [np.abs(f.astype(int) - final).mean() for _, f in got]
+    assert errs[-1] <= 0.01 and errs[0] > errs[3] > errs[-1]
+    # after the first frame only sub-pixel 0 has a sample: the frame is a quarter as bright as the final one at most
+    assert got[0][1].mean() < 0.75 * final.mean()
+
+
 def test_job_cancel(gpu_scene, rtb):
     g = gpu_scene("flying_unicorn")
     job = rtb.RenderJob(g, 1920, 1080, 4096, seed=1)   # seconds of work
