@@ -10,6 +10,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -509,6 +510,10 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     st.kernel_launches += launches;
     st.bvh_node_visits += h.node_visits;
     st.bvh_tri_tests += h.tri_tests;
+    if (count_work && getenv("RTB_DEBUG_TRAVERSE"))
+        fprintf(stderr, "[rtb] traverse slots: rounds %llu inner-offered %llu used %llu (%.1f%%) | leaf phases %llu lanes %llu (%.1f of 32) | refills %llu lanes %llu (%.1f per refill)\n",
+                h.dbg[0], h.dbg[1], h.node_visits, 100.0 * h.node_visits / (double)std::max<unsigned long long>(1, h.dbg[1]), h.dbg[2], h.dbg[3],
+                (double)h.dbg[3] / (double)std::max<unsigned long long>(1, h.dbg[2]), h.dbg[4], h.dbg[5], (double)h.dbg[5] / (double)std::max<unsigned long long>(1, h.dbg[4]));
     st.render_ms += ms;
     st.extend_ms += ext_ms;
     st.shade_ms += shade_ms;

@@ -360,16 +360,23 @@ int flatten_scene(const HostScene& hs, FlatScene& fs, std::string& err) {
     {
         std::vector<FlatPrim> planes, spheres;
         for (const FlatPrim& q : fs.prims) (q.type == PRIM_PLANE ? planes : spheres).push_back(q);
-        for (size_t k = 0; k < planes.size(); ++k) {          // groups refer to positions inside the plane block
-            planes[k].group = (int)k;
-            for (size_t e = 0; e < k; ++e)
-                if (planes[e].a[0] == planes[k].a[0] && planes[e].a[1] == planes[k].a[1] && planes[e].a[2] == planes[k].a[2] &&
-                    planes[e].a[3] == planes[k].a[3]) {
-                    planes[k].group = planes[e].group;
-                    break;
-                }
+        // A plane that coincides exactly with an earlier one (every reference scene repeats one wall as object 5,
+        // scenes/*.toml) can never be reported: trace_ray keeps the lowest object index on equal t (src/scene.rs:277-284)
+        // and an occlusion test is unchanged by a second copy.  It stays an object (material table) but is dropped
+        // from the device primitive table.
+        {
+            std::vector<FlatPrim> uniq;
+            for (const FlatPrim& q : planes) {
+                bool dup = false;
+                for (const FlatPrim& e : uniq)
+                    dup |= e.a[0] == q.a[0] && e.a[1] == q.a[1] && e.a[2] == q.a[2] && e.a[3] == q.a[3];
+                if (!dup) uniq.push_back(q);
+            }
+            planes.swap(uniq);
         }
+        for (size_t k = 0; k < planes.size(); ++k) planes[k].group = (int)k;   // self-intersection class = own index
         for (size_t k = 0; k < spheres.size(); ++k) spheres[k].group = (int)(planes.size() + k);
+        fs.n_planes = (int)planes.size();
         fs.prims = planes;
         fs.prims.insert(fs.prims.end(), spheres.begin(), spheres.end());
     }

@@ -59,6 +59,8 @@ struct DevCtrl {
     unsigned long long samples, rays_primary, rays_extension, rays_shadow, iterations;
     unsigned long long rays_bvh, shadow_bvh;   // of those, how many needed a BVH traversal
     unsigned long long node_visits, tri_tests;
+    // counting build only: SIMD-slot accounting of k_traverse (lane-slots offered vs used)
+    unsigned long long dbg[8];   // 0 rounds, 1 inner slot-steps offered (32 x trips), 2 leaf phases, 3 leaf lanes, 4 refills, 5 refilled lanes, 6 rays, 7 -
 };
 #define ext_head(i) ext_head_[i].v
 #define ext_tail(i) ext_tail_[i].v
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
     const int refill_below = a.tune_refill > 0 ? a.tune_refill : REFILL_BELOW;
     const int steps = a.tune_steps > 0 ? a.tune_steps : INNER_STEPS;
     uint32_t work[2] = {0, 0};
+    unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t wnext = 0, wend = 0;
     bool exhausted = false;
     Trav T;
@@ -370,6 +373,7 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
                         trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), d4.w, a.S.root);
                     }
                 }
+                if (COUNT && lane == 0) { dbg[4] += 1; dbg[5] += min((uint32_t)__popc(idle_mask), wend - wnext); }
                 wnext = min(wnext + (uint32_t)__popc(idle_mask), wend);
             }
         }
@@ -381,7 +385,14 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
         // ---- traverse until too few lanes are left (then go back and refill).  A lane takes at most
         // `steps` inner nodes per round, so lanes whose ray ended are not left idle behind one long descent.
         for (;;) {
-            for (int k = 0; k < steps && T.node >= 0; ++k) trav_inner<COUNT>(a.S, T, sstack, stride, lstack, work);
+            int trips = 0;
+            for (int k = 0; k < steps && T.node >= 0; ++k) { trav_inner<COUNT>(a.S, T, sstack, stride, lstack, work); ++trips; }
+            if (COUNT) {
+                int mx = trips;
+                for (int off = 16; off; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                const unsigned lm = __ballot_sync(0xffffffffu, T.node < 0 && T.node != NODE_SENTINEL);
+                if (lane == 0) { dbg[0] += 1; dbg[1] += 32ull * mx; dbg[2] += lm ? 1 : 0; dbg[3] += __popc(lm); }
+            }
             if (T.node < 0 && T.node != NODE_SENTINEL) {
                 if (kind == 1) {
                     if (trav_leaf<true, COUNT>(a.S, T, work)) {
@@ -407,6 +418,7 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
         if (lane == 0) {
             atomicAdd(&C->node_visits, (unsigned long long)work[0]);
             atomicAdd(&C->tri_tests, (unsigned long long)work[1]);
+            for (int k = 0; k < 6; ++k) atomicAdd(&C->dbg[k], dbg[k]);
         }
     }
 }
