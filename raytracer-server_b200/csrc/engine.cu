@@ -65,6 +65,10 @@ struct RenderContext {
     size_t h_rgb_cap = 0;
     int32_t* d_probe = nullptr;
     size_t probe_cap = 0;
+    volatile unsigned long long* h_state = nullptr;   // mapped pinned {iteration, live paths} (graph mode)
+    unsigned long long* d_state = nullptr;
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one iteration (4 kernels) for cur = 0 / 1 ...
+    std::vector<unsigned char> graph_args;                 // ... captured for exactly these kernel arguments
     int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0, grid_shade = 0;
 
     ~RenderContext() {
@@ -72,6 +76,8 @@ struct RenderContext {
         if (stream) cudaStreamSynchronize(stream);
         cudaFree(qbuf); cudaFree(sbuf); cudaFree(accum); cudaFree(ctrl); cudaFree(d_rgb); cudaFree(d_probe);
         if (h_active) cudaFreeHost(h_active);
+        if (h_state) cudaFreeHost((void*)h_state);
+        for (auto& e : graph_exec) if (e) cudaGraphExecDestroy(e);
         if (h_rgb) cudaFreeHost(h_rgb);
         for (auto& e : ring_ev) if (e) cudaEventDestroy(e);
         for (auto& e : ext_ev) cudaEventDestroy(e);
@@ -307,6 +313,8 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CU_TRY(cudaMalloc((void**)&c->ctrl, sizeof(DevCtrl)));
         CU_TRY(cudaMallocHost((void**)&c->h_active, sizeof(uint32_t) * RenderContext::RING));
+        CU_TRY(cudaHostAlloc((void**)&c->h_state, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
+        CU_TRY(cudaHostGetDevicePointer((void**)&c->d_state, (void*)c->h_state, 0));
         for (auto& e : c->ring_ev) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU_TRY(cudaEventCreate(&c->ev_begin));
         CU_TRY(cudaEventCreate(&c->ev_end));
@@ -427,6 +435,7 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     }
     a.accum = c->accum;
     a.ctrl = c->ctrl;
+    a.trav_warps = (uint32_t)c->grid_ext * (WF_THREADS / 32);
 }
 
 // The wavefront loop: runs samples [ks_begin, ks_end) (ks = k*4 + sub-pixel) of every local pixel,
@@ -434,6 +443,7 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
 int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_begin, uint32_t ks_end, bool count_work,
                   volatile int* cancel, rtb_stats& st, bool& cancelled) {
     cancelled = false;
+    a.trav_warps = (uint32_t)(count_work ? c->grid_ext_count : c->grid_ext) * (WF_THREADS / 32);   // must match the launched grid
     DevCtrl h{};
     h.ext_head(0) = h.ext_head(1) = 0;
     h.ext_tail(0) = h.ext_tail(1) = a.P;
@@ -450,6 +460,63 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     int cur = 0;
     uint64_t it = 0;
     bool done = h.work_total == h.work_next;
+    // Small frames are launch-bound (four tiny kernels per iteration): replay one captured CUDA graph per
+    // iteration and let k_prepare publish the live-path count to mapped host memory instead of copying it back.
+    const bool use_graph = !count_work && a.P <= (1u << 21) && !getenv("RTB_NO_GRAPH");
+    if (use_graph && !done) {
+        RenderArgs ag = a;
+        ag.host_state = c->d_state;
+        c->h_state[0] = 0;
+        c->h_state[1] = 1;
+        cudaError_t ge = cudaSuccess;
+        const bool cached = c->graph_exec[0] && c->graph_args.size() == sizeof(RenderArgs) &&
+                            std::memcmp(c->graph_args.data(), &ag, sizeof(RenderArgs)) == 0;
+        if (!cached) {   // progressive passes re-use the graphs: the sample range lives in the control block, not in the arguments
+            for (auto& e : c->graph_exec) if (e) { cudaGraphExecDestroy(e); e = nullptr; }
+            for (int k = 0; k < 2 && ge == cudaSuccess; ++k) {
+                cudaGraph_t g = nullptr;
+                ge = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+                if (ge != cudaSuccess) break;
+                k_prepare<<<1, 1, 0, c->stream>>>(ag, k);
+                k_generate<<<c->grid_gen, WF_THREADS, smem_tab, c->stream>>>(ag, k);
+                k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
+                k_shade<<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
+                ge = cudaStreamEndCapture(c->stream, &g);
+                if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->graph_exec[k], g, 0);
+                if (g) cudaGraphDestroy(g);
+            }
+            if (ge != cudaSuccess) {
+                for (auto& e : c->graph_exec) if (e) { cudaGraphExecDestroy(e); e = nullptr; }
+                c->graph_args.clear();
+                return fail(RTB_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ge));
+            }
+            c->graph_args.assign(reinterpret_cast<unsigned char*>(&ag), reinterpret_cast<unsigned char*>(&ag) + sizeof(RenderArgs));
+        }
+        cudaGraphExec_t* exec = c->graph_exec;
+        const uint64_t run_ahead = 24;
+        while (!done) {
+            if (cancel && *cancel) { cancelled = true; break; }
+            ge = cudaGraphLaunch(exec[cur], c->stream);
+            if (ge != cudaSuccess) break;
+            launches += 4;
+            ++it;
+            cur ^= 1;
+            for (;;) {   // {iteration, live paths} as published by the newest k_prepare that has run
+                const unsigned long long seen = c->h_state[0];
+                if (seen >= 1 && c->h_state[1] == 0 && c->h_state[0] == seen) { done = true; break; }
+                if (it - seen < run_ahead) break;
+                if (cudaStreamQuery(c->stream) == cudaSuccess && c->h_state[0] == seen && it - seen >= run_ahead) {
+                    // everything launched has run; the published state is final for those iterations
+                    if (c->h_state[1] == 0) done = true;
+                    break;
+                }
+            }
+        }
+        cudaError_t se = cudaStreamSynchronize(c->stream);
+        if (ge != cudaSuccess || se != cudaSuccess)
+            return fail(RTB_ECUDA, std::string("graph launch: ") + cudaGetErrorString(ge != cudaSuccess ? ge : se));
+        done = true;
+    }
     int outstanding = 0;
     uint64_t oldest = 0;
     while (!done) {

@@ -86,6 +86,10 @@ struct RenderArgs {
     const int32_t* probe_sample;
     int n_probe;
     int tune_refill, tune_steps;   // traversal knobs (0 = defaults above); rtb_params.reserved[1], [2]
+    // graph mode (small frames): k_prepare publishes {iteration, live paths} to mapped pinned host memory so the
+    // host can stop launching without a copy or an event per iteration
+    volatile unsigned long long* host_state;
+    uint32_t trav_warps;   // warps in the k_traverse grid: each owns the static first chunk [w*32, w*32+32)
 };
 
 // ---------------------------------------------------------------- tile order <-> pixels
@@ -209,17 +213,23 @@ __global__ void k_prepare(RenderArgs a, int c) {
     C->ext_head(1 - c) = 0;
     C->ext_tail(1 - c) = a.P;
     C->sh_head(1 - c) = 0;
-    C->cursor_trav = 0;
+    C->cursor_trav = a.trav_warps * FETCH_CHUNK;   // chunks below that are handed out statically (no atomic)
     C->active = count + n_new + C->sh_head(c);   // pending shadow rays keep the loop alive
     C->iterations++;
+    if (a.host_state) {
+        a.host_state[1] = C->active;
+        __threadfence_system();
+        a.host_state[0] = C->iterations;
+    }
 }
 
 // ---------------------------------------------------------------- k_generate
 __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SharedScene sh = stage_scene(a.S, smem_raw, false);
     DevCtrl* C = a.ctrl;
     const uint32_t n = C->gen_count;
+    if (blockIdx.x * WF_THREADS >= n) return;   // tail iterations: most CTAs have nothing to generate
+    const SharedScene sh = stage_scene(a.S, smem_raw, false);
     const unsigned long long base = C->gen_base;
     const unsigned lane = threadIdx.x & 31;
     const uint32_t nwarps_total = (gridDim.x * blockDim.x) >> 5;
@@ -324,8 +334,12 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
     const int steps = a.tune_steps > 0 ? a.tune_steps : INNER_STEPS;
     uint32_t work[2] = {0, 0};
     unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t wnext = 0, wend = 0;
+    // first chunk: static (warp w owns [w*32, w*32+32)), later chunks from the atomic cursor, which k_prepare
+    // starts behind the static region — a launch with few rays does no atomics at all
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t wnext = min(gwarp * FETCH_CHUNK, count), wend = min(gwarp * FETCH_CHUNK + FETCH_CHUNK, count);
     bool exhausted = false;
+    if (blockIdx.x * (WF_THREADS / 32) * FETCH_CHUNK >= count) return;   // whole CTA beyond the static region of a small launch
     Trav T;
     T.node = NODE_SENTINEL;
     T.sp = 0;
@@ -479,11 +493,12 @@ __device__ __forceinline__ void shade_flush(const ShadeStage& st, const PathQueu
 // accumulator REDs.
 __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SharedScene sh = stage_scene(a.S, smem_raw, false);
     DevCtrl* C = a.ctrl;
     const DevSceneHeader* hdr = a.S.hdr;
     const uint32_t head = C->ext_head(c), tail = C->ext_tail(c);
     const uint32_t count = head + (a.P - tail);
+    if (blockIdx.x * SHADE_THREADS >= count) return;   // tail iterations: this CTA has no queue entries
+    const SharedScene sh = stage_scene(a.S, smem_raw, false);
     const unsigned lane = threadIdx.x & 31;
     const PathQueue Q = a.q[c], N = a.q[1 - c];
     const int light_obj = hdr->light_obj;
