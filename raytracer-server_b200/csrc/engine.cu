@@ -325,14 +325,15 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         // The attribute is per kernel, not per scene: always opt in to the largest table set
         // (MAX_OBJECTS primitives + materials), never to this scene's own (smaller) size.
         const int smem_max = (int)shared_tables_bytes(MAX_OBJECTS, MAX_OBJECTS);
-        CU_TRY(cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CU_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         int b = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false>, WF_THREADS, smem_stack));
         c->grid_ext = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true>, WF_THREADS, smem_stack));
         c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade, SHADE_THREADS, smem_tab));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<false>, SHADE_THREADS, smem_tab));
         c->grid_shade = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate, WF_THREADS, smem_tab));
         c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
@@ -462,6 +463,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     bool done = h.work_total == h.work_next;
     // Small frames are launch-bound (four tiny kernels per iteration): replay one captured CUDA graph per
     // iteration and let k_prepare publish the live-path count to mapped host memory instead of copying it back.
+    // compile-time specialisation of k_shade for the common case (see its definition)
+    bool fast_shade = a.estimator == 0 && !a.probe_px && sc->fs.light_geom == GEOM_SPHERE && !getenv("RTB_NO_FAST_SHADE");
+    for (const FlatMaterial& m : sc->fs.materials) fast_shade = fast_shade && m.brdf != BRDF_PHONG;
     const bool use_graph = !count_work && a.P <= (1u << 21) && !getenv("RTB_NO_GRAPH");
     if (use_graph && !done) {
         RenderArgs ag = a;
@@ -480,7 +484,8 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 k_prepare<<<1, 1, 0, c->stream>>>(ag, k);
                 k_generate<<<c->grid_gen, WF_THREADS, smem_tab, c->stream>>>(ag, k);
                 k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
-                k_shade<<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
+                if (fast_shade) k_shade<true><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
+            else k_shade<false><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
                 ge = cudaStreamEndCapture(c->stream, &g);
                 if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->graph_exec[k], g, 0);
                 if (g) cudaGraphDestroy(g);
@@ -533,7 +538,8 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         CU_TRY(cudaEventRecord(ev[1], c->stream));
-        k_shade<<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
+        if (fast_shade) k_shade<true><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
+        else k_shade<false><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
         CU_TRY(cudaEventRecord(ev[2], c->stream));
         ++ext_iters;
         launches += 4;

@@ -98,8 +98,9 @@ __device__ __forceinline__ float powi_f(float c, int p) {
     for (int k = 0; k < p; ++k) r *= c;
     return r;
 }
+template <bool FAST = false>
 __device__ __forceinline__ float3 brdf_eval(const DevMaterial& m, float3 n, float3 o, float3 i) {
-    if (m.brdf == 0) return f3(m.k) * INV_PI_F;
+    if (FAST || m.brdf == 0) return f3(m.k) * INV_PI_F;   // FAST callers only evaluate diffuse surfaces
     if (m.brdf == 1) {
         float3 r = flip_across(o, n);
         bool eq = fabsf(i.x - r.x) < 0.001f && fabsf(i.y - r.y) < 0.001f && fabsf(i.z - r.z) < 0.001f;
@@ -115,8 +116,9 @@ __device__ __forceinline__ float3 brdf_eval(const DevMaterial& m, float3 n, floa
 }
 
 // ---- BRDF::sample_incoming (src/scene.rs:56-98); xi = {u1, u2, lobe} ---------------------------
+template <bool FAST = false>
 __device__ __forceinline__ void brdf_sample(const DevMaterial& m, float3 n, float3 o, float4 xi, float3& i, float& pdf) {
-    if (m.brdf == 0) {
+    if (FAST || m.brdf == 0) {   // FAST callers only sample diffuse surfaces
         float z = sqrtf(xi.x);
         float r = sqrtf(1.0f - z * z);
         float s, c;
@@ -150,9 +152,10 @@ __device__ __forceinline__ void brdf_sample(const DevMaterial& m, float3 n, floa
 }
 
 // ---- Geometry::sample for the light (src/geometry.rs:573-595); xi = {u1, u2, -, select} --------
+template <bool FAST = false>
 __device__ __forceinline__ void light_sample(const DevScene& S, const DevPrim* prims, const DevSceneHeader* hdr, float4 xi,
                                              float3& y, float3& ny, float& pdf) {
-    if (hdr->light_geom == 0) {  // sphere: uniform over the whole surface
+    if (FAST || hdr->light_geom == 0) {  // sphere: uniform over the whole surface
         const DevPrim& L = prims[hdr->light_prim];
         float z = 2.0f * xi.x - 1.0f;
         float r = sqrtf(fmaxf(1.0f - z * z, 0.0f));

@@ -491,6 +491,10 @@ __device__ __forceinline__ void shade_flush(const ShadeStage& st, const PathQueu
 // Everything of reflected_radiance except the mesh traversal.  Coherent: static warp -> slot mapping,
 // no work-fetch atomics; the only atomics are the queue pushes (3 per warp, overlapped) and the
 // accumulator REDs.
+// FAST = the reference scenes' case, resolved at compile time: live NEE estimator, Diffuse / Specular materials
+// only, sphere light, no probe items.  The general instantiation keeps every branch (dead-MIS estimator, Phong,
+// mesh lights, rtb_sample_radiance probes).
+template <bool FAST>
 __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevCtrl* C = a.ctrl;
@@ -502,7 +506,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     const unsigned lane = threadIdx.x & 31;
     const PathQueue Q = a.q[c], N = a.q[1 - c];
     const int light_obj = hdr->light_obj;
-    const bool light_is_mesh = hdr->light_geom == 2;
+    const bool light_is_mesh = FAST ? false : hdr->light_geom == 2;
+    const bool mis = FAST ? false : a.estimator != 0;
+    const bool probe_mode = FAST ? false : a.probe_px != nullptr;
     const float3 Le = f3(sh.mats[light_obj].emitted);
     const int n_prims = a.S.n_prims, n_planes = a.S.n_planes;
     __shared__ ShadeStage st;
@@ -586,14 +592,14 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                     beta = beta * f3(pm.k) * (1.0f / pp);
                 }
                 const float p = depth <= 5u ? 1.0f : 0.9f;  // MAX_BOUNCES / SURVIVAL_PROBABILITY (src/scene.rs:109-110,164-168)
-                const uint32_t rng_pixel = a.probe_px ? (uint32_t)(a.probe_py[acc] * a.width + a.probe_px[acc]) : acc >> 2;
+                const uint32_t rng_pixel = probe_mode ? (uint32_t)(a.probe_py[acc] * a.width + a.probe_px[acc]) : acc >> 2;
                 const bool dead_surface = mat.brdf == 0 && mat.k.x == 0.f && mat.k.y == 0.f && mat.k.z == 0.f;
                 const bool dead_path = beta.x == 0.f && beta.y == 0.f && beta.z == 0.f;
                 if (!dead_surface && !dead_path && depth < MAX_DEPTH_FIELD) {
                     const VertexRng vr = rng_vertex(rng_pixel, sample, depth, a.k0, a.k1);
                     // lobe / light-triangle selectors live in block 1 and are only drawn by Phong surfaces / mesh lights
                     float lobe_u = 0.f, select_u = 0.f;
-                    if (mat.brdf == 2 || light_is_mesh) {
+                    if (!FAST && (mat.brdf == 2 || light_is_mesh)) {
                         const float4 r1 = rng_block(rng_pixel, sample, depth, 1u, a.k0, a.k1);
                         lobe_u = r1.x;
                         select_u = r1.y;
@@ -615,14 +621,14 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                         // ---- direct light
                         float3 y, ny;
                         float pdf_a;
-                        light_sample(a.S, sh.prims, hdr, r0, y, ny, pdf_a);
+                        light_sample<FAST>(a.S, sh.prims, hdr, r0, y, ny, pdf_a);
                         float3 dv = y - hg.pos;
                         float r2 = dot(dv, dv);
                         float dist = sqrtf(r2);
                         float3 inc = dv * (1.0f / dist);
-                        float3 f = brdf_eval(mat, hg.n, ovec, inc);
+                        float3 f = brdf_eval<FAST>(mat, hg.n, ovec, inc);
                         float3 contrib;
-                        if (a.estimator == 0) {  // live NEE, src/scene.rs:217-229 (no cosine is clamped)
+                        if (!mis) {  // live NEE, src/scene.rs:217-229 (no cosine is clamped)
                             float g = dot(hg.n, inc) * dot(ny, -inc) / (r2 * pdf_a);
                             contrib = beta * Le * f * g;
                         } else {                 // dead branch, src/scene.rs:191-201
@@ -639,7 +645,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                             sh_contrib = contrib;
                             ++n_sh;
                         }
-                        if (a.estimator != 0) {  // src/scene.rs:203-214: own BRDF sample; counts only if it reaches the light
+                        if (mis) {  // src/scene.rs:203-214: own BRDF sample; counts only if it reaches the light
                             float3 i2;
                             float pdf2;
                             brdf_sample(mat, hg.n, ovec, rng_block(rng_pixel, sample, depth, 4u, a.k0, a.k1), i2, pdf2);
@@ -683,10 +689,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                         // ---- russian roulette + continuation, src/scene.rs:231-240
                         if (r0.z < p) {
                             float pdf1;
-                            brdf_sample(mat, hg.n, ovec, rb, next_dir, pdf1);
+                            brdf_sample<FAST>(mat, hg.n, ovec, rb, next_dir, pdf1);
                             if (next_dir.x != 0.f || next_dir.y != 0.f || next_dir.z != 0.f) {
                                 float3 nb;
-                                if (mat.brdf == 0) nb = beta * f3(mat.k) * (1.0f / p);  // f (n.i) / pdf == kd exactly
+                                if (FAST || mat.brdf == 0) nb = beta * f3(mat.k) * (1.0f / p);  // f (n.i) / pdf == kd exactly
                                 else nb = beta * brdf_eval(mat, hg.n, ovec, next_dir) * (dot(hg.n, next_dir) / (pdf1 * p));
                                 ext_push = true;
                                 eo = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
