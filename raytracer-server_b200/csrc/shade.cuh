@@ -85,6 +85,14 @@ __device__ __forceinline__ float3 camera_dir(const Camera& c, int x, int y_sampl
     return normalize(c.cx * fx + c.cy * fy + c.dir);
 }
 
+// sin / cos of 2*pi*u for u in (0,1) on the SFU: the argument is folded to (-pi, pi), where MUFU.SIN / MUFU.COS are
+// good to ~4e-7 absolute (sin(2 pi u) = -sin(2 pi u - pi), same for cos)
+__device__ __forceinline__ void sincos_2pi(float u, float& s, float& c) {
+    const float x = fmaf(u, 2.0f * PI_F, -PI_F);
+    s = -__sinf(x);
+    c = -__cosf(x);
+}
+
 // ---- create_local_coord (src/scene.rs:112-123) ------------------------------------------------
 __device__ __forceinline__ void local_coord(float3 n, float3& u, float3& v) {
     float3 a = fabsf(n.x) > 0.1f ? f3(0.f, 1.f, 0.f) : f3(1.f, 0.f, 0.f);
@@ -122,7 +130,7 @@ __device__ __forceinline__ void brdf_sample(const DevMaterial& m, float3 n, floa
         float z = sqrtf(xi.x);
         float r = sqrtf(1.0f - z * z);
         float s, c;
-        sincospif(2.0f * xi.y, &s, &c);
+        sincos_2pi(xi.y, s, c);
         float3 u, v;
         local_coord(n, u, v);
         i = normalize(u * (r * c) + v * (r * s) + n * z);
@@ -160,7 +168,7 @@ __device__ __forceinline__ void light_sample(const DevScene& S, const DevPrim* p
         float z = 2.0f * xi.x - 1.0f;
         float r = sqrtf(fmaxf(1.0f - z * z, 0.0f));
         float s, c;
-        sincospif(2.0f * xi.y, &s, &c);
+        sincos_2pi(xi.y, s, c);
         float3 n = normalize(f3(r * c, r * s, z));
         float rad = L.a.w;
         y = f3(L.a) + n * rad;

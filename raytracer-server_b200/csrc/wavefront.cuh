@@ -624,12 +624,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                         light_sample<FAST>(a.S, sh.prims, hdr, r0, y, ny, pdf_a);
                         float3 dv = y - hg.pos;
                         float r2 = dot(dv, dv);
-                        float dist = sqrtf(r2);
-                        float3 inc = dv * (1.0f / dist);
+                        float inv_dist = rsqrtf(r2);
+                        float dist = r2 * inv_dist;
+                        float3 inc = dv * inv_dist;
                         float3 f = brdf_eval<FAST>(mat, hg.n, ovec, inc);
                         float3 contrib;
                         if (!mis) {  // live NEE, src/scene.rs:217-229 (no cosine is clamped)
-                            float g = dot(hg.n, inc) * dot(ny, -inc) / (r2 * pdf_a);
+                            float g = __fdividef(dot(hg.n, inc) * dot(ny, -inc), r2 * pdf_a);
                             contrib = beta * Le * f * g;
                         } else {                 // dead branch, src/scene.rs:191-201
                             float pdf_light = pdf_a * (r2 / dot(ny, -inc));
