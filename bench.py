@@ -298,10 +298,17 @@ def main():
         except Exception:
             pass
 
+        # measured DRAM traffic (ncu --set full, profiles/traffic.json) is stored per unit and scaled to this run's
+        # units per launch, because the path pool (hence a launch) is sized per frame
+        traffic_per_launch = {
+            "k_shade": traffic.get("k_shade_dram_bytes_per_vertex", 0.0) * vertices / n_launch or None,
+            "k_traverse": traffic.get("k_traverse_dram_bytes_per_bvh_ray", 0.0) * (totals["rays_bvh"] + totals["shadow_bvh"]) / n_launch or None,
+        }
+
         def roof(kernel, ms, nbytes):
             gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "traffic": traffic.get(kernel + "_dram_bytes_per_launch"),
+                    "traffic": traffic_per_launch[kernel],
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
                     "algorithmic_bytes_per_launch": nbytes / n_launch, "avg_launch_ms": ms / n_launch,
                     "share_of_step": ms / max(totals["render_ms"], 1e-9)}
