@@ -291,3 +291,47 @@ def test_mesh_light_sampling_quirk(rtb, oracle_mod):
     fin = np.isfinite(Lo).all(axis=1) & np.isfinite(Lg).all(axis=1)
     err = np.abs(Lg[fin] - Lo[fin]).max(axis=1) / (np.abs(Lo[fin]).max(axis=1) + 1e-3)
     assert fin.mean() > 0.99 and np.median(err) < 2e-5 and (err > 1e-3).mean() < 0.03
+
+
+def test_mesh_only_scene_and_tiny_meshes(rtb, oracle_mod, tmp_path):
+    # no analytic surface except the light: rays can miss everything (received_radiance returns 0, src/scene.rs:156-158);
+    # a 2-triangle mesh is a single LBVH leaf (no inner node at all), the prism a small tree
+    (tmp_path / "quad.obj").write_text("v -6 0 -6\nv 6 0 -6\nv 6 0 6\nv -6 0 6\nf 1 2 3\nf 1 3 4\n")
+    text = """
+[camera]
+pos = [0.0, 6.0, 14.0]
+dir = [0.0, -0.35, -1.0]
+[[objects]]
+brdf = { type = "diffuse", kd = [0.7, 0.6, 0.5] }
+geometry = { type = "mesh", path = "quad.obj" }
+[[objects]]
+brdf = { type = "diffuse", kd = [0.3, 0.8, 0.3] }
+geometry = { type = "prism", pos = [-1.0, 0.0, -1.0], size = [2.0, 3.0, 2.0] }
+transforms = [ { rotate_y = 0.5 } ]
+[[objects]]
+emitted = [30.0, 30.0, 30.0]
+brdf = { type = "diffuse", kd = [0.0, 0.0, 0.0] }
+geometry = { type = "sphere", pos = [3.0, 7.0, 2.0], r = 1.0 }
+"""
+    g = rtb.Scene.from_toml_string(text, assets_dir=str(tmp_path))
+    o = oracle_mod.OracleScene.from_toml_string(text, str(tmp_path))
+    assert g.info.n_planes == 0 and g.info.n_triangles == 14
+    W, H = 160, 120
+    org, dirs = o.primary_rays(W, H)
+    ro, rg = o.trace_rays(org, dirs), g.trace_primary(W, H)
+    mism = (ro["obj"] != rg["obj"]) | (ro["tri"] != rg["tri"])
+    assert (ro["obj"] < 0).mean() > 0.2 and (ro["obj"] == 0).any() and (ro["obj"] == 1).any()
+    if mism.any():
+        idx = np.flatnonzero(mism)
+        assert ambiguous_mask(o, org[idx], dirs[idx], {k: v[idx] for k, v in ro.items()}, rg["t"][idx]).all()
+    assert mism.mean() < 1e-3
+    n, spp = 6000, 16
+    rng = np.random.default_rng(3)
+    px, py, si = rng.integers(0, W, n), rng.integers(0, H, n), rng.integers(0, spp, n)
+    Lo = o.sample_radiance(W, H, spp, 5, px, py, si)
+    Lg = g.sample_radiance(W, H, spp, px, py, si, seed=5).astype(np.float64)
+    err = np.abs(Lg - Lo).max(axis=1) / (np.abs(Lo).max(axis=1) + 1e-3)
+    assert np.median(err) < 1e-5 and (err > 1e-3).mean() < 0.02
+    io = o.render(80, 60, 32, seed=2, nthreads=-NCPU)["rgb8"]
+    ig = g.render(80, 60, 32, seed=2)
+    assert psnr(ig, io) >= 40.0
