@@ -129,6 +129,35 @@ typedef struct rtb_stats {
 int rtb_scene_load_toml(const char* toml_path, const char* assets_dir, int device, rtb_scene** out);
 int rtb_scene_load_toml_string(const char* toml_text, const char* assets_dir, int device, rtb_scene** out);
 void rtb_scene_destroy(rtb_scene* scene);
+
+/* ---- programmatic scene (no TOML): the objects a host already has in memory ---------------------
+ * One entry per Object (src/scene.rs:10-15).  Geometry is final (no transforms are applied):
+ * sphere {pos, r}; plane {pos, n}; mesh = n_triangles x 9 floats (a, b, c per triangle, vertex order as in
+ * Mesh::triangle, src/geometry.rs:872-877).  Same light rule and error codes as the TOML path. */
+typedef struct rtb_object_desc {
+    double emitted[3];
+    int32_t brdf;           /* 0 diffuse {k = kd}, 1 specular {k = ks}, 2 phong {k = kd, ks, power; color_d; color_s} */
+    int32_t geometry;       /* 0 sphere, 1 plane, 2 mesh */
+    double k[3];
+    double color_d[3];
+    double color_s[3];
+    double pos[3];
+    double n[3];            /* plane normal */
+    double r;               /* sphere radius */
+    const float* triangles; /* mesh: n_triangles * 9 floats */
+    int64_t n_triangles;
+} rtb_object_desc;
+
+typedef struct rtb_scene_desc {
+    double camera_pos[3];
+    double camera_dir[3];
+    int32_t n_objects;
+    int32_t reserved;
+    const rtb_object_desc* objects;
+} rtb_scene_desc;
+
+int rtb_scene_create(const rtb_scene_desc* desc, int device, rtb_scene** out);
+
 int rtb_scene_get_info(const rtb_scene* scene, rtb_scene_info* info);
 int rtb_scene_object(const rtb_scene* scene, int32_t index, rtb_object_info* out);
 /* re-copy the flattened host scene (pinned) to the device; returns bytes copied via *bytes */

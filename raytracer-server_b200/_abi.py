@@ -52,6 +52,17 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ObjectDesc(C.Structure):
+    _fields_ = [("emitted", C.c_double * 3), ("brdf", C.c_int32), ("geometry", C.c_int32), ("k", C.c_double * 3),
+                ("color_d", C.c_double * 3), ("color_s", C.c_double * 3), ("pos", C.c_double * 3), ("n", C.c_double * 3),
+                ("r", C.c_double), ("triangles", C.POINTER(C.c_float)), ("n_triangles", C.c_int64)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("camera_pos", C.c_double * 3), ("camera_dir", C.c_double * 3), ("n_objects", C.c_int32),
+                ("reserved", C.c_int32), ("objects", C.POINTER(ObjectDesc))]
+
+
 class ObjectInfo(C.Structure):
     _fields_ = [("brdf", C.c_int32), ("geometry", C.c_int32), ("n_triangles", C.c_int32), ("first_triangle", C.c_int32),
                 ("emitted", C.c_double * 3), ("k", C.c_double * 3), ("color_d", C.c_double * 3),
@@ -60,7 +71,7 @@ class ObjectInfo(C.Structure):
 
 
 EXPORTS = [
-    "rtb_last_error", "rtb_scene_load_toml", "rtb_scene_load_toml_string", "rtb_scene_destroy", "rtb_scene_get_info", "rtb_scene_object",
+    "rtb_last_error", "rtb_scene_load_toml", "rtb_scene_load_toml_string", "rtb_scene_create", "rtb_scene_destroy", "rtb_scene_get_info", "rtb_scene_object",
     "rtb_scene_upload", "rtb_scene_triangles", "rtb_render", "rtb_local_pixels", "rtb_tile_map", "rtb_render_device",
     "rtb_untile_device", "rtb_get_stats", "rtb_job_begin", "rtb_job_next", "rtb_job_next_messages", "rtb_job_next_frame", "rtb_job_cancel",
     "rtb_job_end", "rtb_trace_primary", "rtb_trace_rays", "rtb_sample_radiance", "rtb_fp32_peak",
@@ -81,6 +92,7 @@ def lib():
     L.rtb_last_error.restype = C.c_char_p
     L.rtb_scene_load_toml.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
     L.rtb_scene_load_toml_string.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.rtb_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(vp)]
     L.rtb_scene_destroy.argtypes = [vp]
     L.rtb_scene_destroy.restype = None
     L.rtb_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]

@@ -675,6 +675,48 @@ int rtb_scene_load_toml_string(const char* toml_text, const char* assets_dir, in
     return finish_scene(sc, rc, err, out);
 }
 
+int rtb_scene_create(const rtb_scene_desc* desc, int device, rtb_scene** out) {
+    if (!desc || !out || (desc->n_objects > 0 && !desc->objects)) return fail(RTB_EINVAL, "NULL argument");
+    *out = nullptr;
+    rtb_scene* sc = new rtb_scene();
+    sc->device = device;
+    sc->hs.cam_pos = {desc->camera_pos[0], desc->camera_pos[1], desc->camera_pos[2]};
+    sc->hs.cam_dir = {desc->camera_dir[0], desc->camera_dir[1], desc->camera_dir[2]};
+    std::string err;
+    int rc = RTB_OK;
+    for (int i = 0; i < desc->n_objects && rc == RTB_OK; ++i) {
+        const rtb_object_desc& d = desc->objects[i];
+        HostObject o;
+        o.emitted = {d.emitted[0], d.emitted[1], d.emitted[2]};
+        if (d.brdf < 0 || d.brdf > 2 || d.geometry < 0 || d.geometry > 2) { rc = RTB_EPARSE; err = "object " + std::to_string(i) + ": unknown brdf / geometry kind"; break; }
+        o.brdf = d.brdf;
+        if (d.brdf == BRDF_PHONG) {
+            if (d.k[2] < 0) { rc = RTB_EPARSE; err = "phong power must be >= 0"; break; }
+            o.phong_kd = d.k[0]; o.phong_ks = d.k[1]; o.phong_power = (int)d.k[2];
+            o.color_d = {d.color_d[0], d.color_d[1], d.color_d[2]};
+            o.color_s = {d.color_s[0], d.color_s[1], d.color_s[2]};
+        } else {
+            o.k = {d.k[0], d.k[1], d.k[2]};
+        }
+        o.geom = d.geometry;
+        o.pos = {d.pos[0], d.pos[1], d.pos[2]};
+        o.n = {d.n[0], d.n[1], d.n[2]};
+        o.r = d.r;
+        if (d.geometry == GEOM_MESH) {
+            if (d.n_triangles <= 0 || !d.triangles) { rc = RTB_EMESH; err = "object " + std::to_string(i) + ": mesh has no faces"; break; }
+            o.vertices.reserve((size_t)d.n_triangles * 3);
+            for (int64_t t = 0; t < d.n_triangles * 3; ++t) {
+                o.vertices.push_back({d.triangles[3 * t], d.triangles[3 * t + 1], d.triangles[3 * t + 2]});
+                o.indices.push_back((uint32_t)t);
+            }
+            init_mesh_tables(o);
+        }
+        sc->hs.objects.push_back(std::move(o));
+    }
+    if (rc == RTB_OK) rc = finish_host_scene(sc->hs, err);
+    return finish_scene(sc, rc, err, out);
+}
+
 void rtb_scene_destroy(rtb_scene* scene) { delete scene; }
 
 int rtb_scene_get_info(const rtb_scene* scene, rtb_scene_info* info) {

@@ -247,21 +247,7 @@ int load_scene_text(const std::string& text, const std::string& assets_dir, Host
             build_object(*spec, assets_dir, o);
             out.objects.push_back(std::move(o));
         }
-        // Scene::new, src/scene.rs:126-141: first object with any |emitted component| >= 1e-5
-        out.light = -1;
-        for (size_t i = 0; i < out.objects.size(); ++i) {
-            const D3& e = out.objects[i].emitted;
-            bool zero = std::fabs(e.x) < 0.00001 && std::fabs(e.y) < 0.00001 && std::fabs(e.z) < 0.00001;
-            if (!zero) { out.light = (int)i; break; }
-        }
-        if (out.light < 0) {
-            err = "scene has no emitter (the reference hits unreachable!() at src/scene.rs:136)";
-            return RTB_ENOLIGHT;
-        }
-        if (out.objects[out.light].geom == GEOM_PLANE) {
-            err = "the light is a plane: Geometry::sample is unimplemented!() for planes (src/geometry.rs:593)";
-            return RTB_EUNSUPPORTED;
-        }
+        if (int rc = finish_host_scene(out, err)) return rc;
         return RTB_OK;
     } catch (const toml::ParseError& e) {
         err = e.what();
@@ -270,6 +256,27 @@ int load_scene_text(const std::string& text, const std::string& assets_dir, Host
         err = e.msg;
         return e.code;
     }
+}
+
+void init_mesh_tables(HostObject& o) { mesh_init(o); }
+
+int finish_host_scene(HostScene& out, std::string& err) {
+    // Scene::new, src/scene.rs:126-141: first object with any |emitted component| >= 1e-5
+    out.light = -1;
+    for (size_t i = 0; i < out.objects.size(); ++i) {
+        const D3& e = out.objects[i].emitted;
+        bool zero = std::fabs(e.x) < 0.00001 && std::fabs(e.y) < 0.00001 && std::fabs(e.z) < 0.00001;
+        if (!zero) { out.light = (int)i; break; }
+    }
+    if (out.light < 0) {
+        err = "scene has no emitter (the reference hits unreachable!() at src/scene.rs:136)";
+        return RTB_ENOLIGHT;
+    }
+    if (out.objects[out.light].geom == GEOM_PLANE) {
+        err = "the light is a plane: Geometry::sample is unimplemented!() for planes (src/geometry.rs:593)";
+        return RTB_EUNSUPPORTED;
+    }
+    return RTB_OK;
 }
 
 int load_scene_file(const std::string& path, const std::string& assets_dir, HostScene& out, std::string& err) {

@@ -90,4 +90,8 @@ struct FlatScene {
 
 int flatten_scene(const HostScene& hs, FlatScene& out, std::string& err);
 
+// shared tail of every way to build a HostScene: Scene::new's light rule (src/scene.rs:126-141) + mesh tables
+int finish_host_scene(HostScene& hs, std::string& err);
+void init_mesh_tables(HostObject& o);   // Mesh::new: Heron areas, cumulative weights, bounding box
+
 }  // namespace rtb

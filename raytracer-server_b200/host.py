@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import EST_MIS_DEAD, EST_NEE, ObjectInfo, Params, SceneInfo, Stats
+from ._abi import EST_MIS_DEAD, EST_NEE, ObjectDesc, ObjectInfo, Params, SceneDesc, SceneInfo, Stats
 
 
 class RtbError(RuntimeError):
@@ -79,6 +79,45 @@ class Scene:
         rc = _abi.lib().rtb_scene_load_toml_string(text.encode(), os.fsencode(assets_dir) if assets_dir else None, device,
                                                    C.byref(h))
         _check(rc, load=True)
+        return cls(h.value, name)
+
+    @classmethod
+    def from_objects(cls, camera_pos, camera_dir, objects: list, device: int = 0, name: str = "") -> "Scene":
+        """Programmatic scene (rtb_scene_create).  Each object is a dict: emitted (opt), brdf = ("diffuse", kd) |
+        ("specular", ks) | ("phong", kd, ks, power, color_d, color_s), geometry = ("sphere", pos, r) |
+        ("plane", pos, n) | ("mesh", triangles[n, 3, 3])."""
+        arr = (ObjectDesc * max(1, len(objects)))()
+        keep = []
+        for d, ob in zip(arr, objects):
+            d.emitted[:] = list(map(float, ob.get("emitted", (0.0, 0.0, 0.0))))
+            b = ob["brdf"]
+            d.brdf = {"diffuse": 0, "specular": 1, "phong": 2}[b[0]]
+            if b[0] == "phong":
+                d.k[:] = [float(b[1]), float(b[2]), float(b[3])]
+                d.color_d[:] = list(map(float, b[4]))
+                d.color_s[:] = list(map(float, b[5]))
+            else:
+                d.k[:] = list(map(float, b[1]))
+            g = ob["geometry"]
+            d.geometry = {"sphere": 0, "plane": 1, "mesh": 2}[g[0]]
+            if g[0] == "sphere":
+                d.pos[:] = list(map(float, g[1]))
+                d.r = float(g[2])
+            elif g[0] == "plane":
+                d.pos[:] = list(map(float, g[1]))
+                d.n[:] = list(map(float, g[2]))
+            else:
+                tri = np.ascontiguousarray(g[1], dtype=np.float32).reshape(-1, 9)
+                keep.append(tri)
+                d.triangles = tri.ctypes.data_as(C.POINTER(C.c_float))
+                d.n_triangles = tri.shape[0]
+        desc = SceneDesc()
+        desc.camera_pos[:] = list(map(float, camera_pos))
+        desc.camera_dir[:] = list(map(float, camera_dir))
+        desc.n_objects = len(objects)
+        desc.objects = arr
+        h = C.c_void_p()
+        _check(_abi.lib().rtb_scene_create(C.byref(desc), device, C.byref(h)), load=True)
         return cls(h.value, name)
 
     def close(self):

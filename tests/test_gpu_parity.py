@@ -335,3 +335,53 @@ geometry = { type = "sphere", pos = [3.0, 7.0, 2.0], r = 1.0 }
     io = o.render(80, 60, 32, seed=2, nthreads=-NCPU)["rgb8"]
     ig = g.render(80, 60, 32, seed=2)
     assert psnr(ig, io) >= 40.0
+
+
+def test_random_triangle_soup_lbvh(rtb, oracle_mod, tmp_path):
+    # LBVH stress: an unstructured soup (overlapping boxes, slivers, wildly different sizes, duplicated centroids)
+    # handed over through rtb_scene_create; the oracle reads the same triangles from an OBJ file
+    rng = np.random.default_rng(12)
+    n = 3000
+    centres = rng.uniform(-10, 10, size=(n, 1, 3))
+    centres[:200] = centres[0]                       # 200 triangles share one centroid cell (equal Morton codes)
+    size = np.exp(rng.uniform(np.log(0.02), np.log(6.0), size=(n, 1, 1)))
+    tris = (centres + rng.normal(size=(n, 3, 3)) * size).astype(np.float32)
+    with open(tmp_path / "soup.obj", "w") as f:
+        for t in tris.reshape(-1, 3):
+            f.write(f"v {float(t[0])!r} {float(t[1])!r} {float(t[2])!r}\n")
+        for i in range(n):
+            f.write(f"f {3 * i + 1} {3 * i + 2} {3 * i + 3}\n")
+    text = """
+[camera]
+pos = [0.0, 0.0, 40.0]
+dir = [0.0, 0.0, -1.0]
+[[objects]]
+brdf = { type = "diffuse", kd = [0.7, 0.7, 0.7] }
+geometry = { type = "mesh", path = "soup.obj" }
+[[objects]]
+emitted = [20.0, 20.0, 20.0]
+brdf = { type = "diffuse", kd = [0.0, 0.0, 0.0] }
+geometry = { type = "sphere", pos = [0.0, 30.0, 0.0], r = 2.0 }
+"""
+    o = oracle_mod.OracleScene.from_toml_string(text, str(tmp_path))
+    g = rtb.Scene.from_objects((0, 0, 40), (0, 0, -1), [
+        {"brdf": ("diffuse", (0.7, 0.7, 0.7)), "geometry": ("mesh", tris)},
+        {"emitted": (20, 20, 20), "brdf": ("diffuse", (0, 0, 0)), "geometry": ("sphere", (0, 30, 0), 2.0)}])
+    assert g.info.n_triangles == n and np.array_equal(g.triangles(), o.mesh_triangles(0).astype(np.float32))
+    m = 150_000
+    org = rng.uniform(-25, 25, size=(m, 3)).astype(np.float32)
+    d = rng.normal(size=(m, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d /= np.linalg.norm(d.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    ro = o.trace_rays(org.astype(np.float64), d.astype(np.float64))
+    rg = g.trace_rays(org, d)
+    assert (ro["obj"] == 0).mean() > 0.2
+    mism = (ro["obj"] != rg["obj"]) | (ro["tri"] != rg["tri"])
+    assert mism.mean() < 3e-3
+    idx = np.flatnonzero(mism)
+    if idx.size:
+        amb = ambiguous_mask(o, org[idx].astype(np.float64), d[idx].astype(np.float64), {k: v[idx] for k, v in ro.items()}, rg["t"][idx])
+        assert (~amb).sum() <= max(3, 0.05 * idx.size)
+    ok = ~mism & (ro["obj"] >= 0)
+    rel = np.abs(rg["t"][ok].astype(np.float64) - ro["t"][ok]) / np.maximum(ro["t"][ok], 1e-2)
+    assert np.quantile(rel, 0.999) < T_REL_TOL

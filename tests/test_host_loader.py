@@ -182,3 +182,31 @@ def test_host_only_handles_refuse_to_compute(rtb):
     assert e.value.code == rtb.RTB_ECUDA if hasattr(rtb, "RTB_ECUDA") else True
     with pytest.raises(rtb.RtbError):
         sc.trace_primary(4, 4)
+
+
+def test_programmatic_scene_matches_toml(rtb):
+    # rtb_scene_create: the same objects handed over in memory instead of TOML
+    toml_scene = load(rtb, CAM + """
+[[objects]]
+brdf = { type = "diffuse", kd = [0.5, 0.6, 0.7] }
+geometry = { type = "prism", pos = [1.0, 2.0, 3.0], size = [1.0, 2.0, 4.0] }
+[[objects]]
+brdf = { type = "specular", ks = [0.9, 0.9, 0.9] }
+geometry = { type = "plane", pos = [0.0, -1.0, 0.0], n = [0.0, 1.0, 0.0] }
+""" + LIGHT)
+    tris = toml_scene.triangles()
+    sc = rtb.Scene.from_objects((0, 0, 10), (0, 0, -1), [
+        {"brdf": ("diffuse", (0.5, 0.6, 0.7)), "geometry": ("mesh", tris)},
+        {"brdf": ("specular", (0.9, 0.9, 0.9)), "geometry": ("plane", (0, -1, 0), (0, 1, 0))},
+        {"emitted": (1, 1, 1), "brdf": ("diffuse", (0, 0, 0)), "geometry": ("sphere", (0, 9, 0), 1.0)},
+    ], device=-1)
+    assert sc.info.n_objects == 3 and sc.light_source == 2 and sc.info.n_triangles == 12
+    assert np.array_equal(sc.triangles(), tris)
+    for i in range(3):
+        a, b = sc.object(i), toml_scene.object(i)
+        for key in ("brdf", "geometry", "emitted", "k", "pos", "n", "r", "n_triangles"):
+            assert a[key] == b[key], (i, key)
+        assert a["surface_area"] == pytest.approx(b["surface_area"], rel=1e-6)
+    with pytest.raises(rtb.LoadTomlError) as e:
+        rtb.Scene.from_objects((0, 0, 10), (0, 0, -1), [{"brdf": ("diffuse", (1, 1, 1)), "geometry": ("sphere", (0, 0, 0), 1.0)}], device=-1)
+    assert e.value.kind == "NoLight"
