@@ -437,6 +437,7 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     a.accum = c->accum;
     a.ctrl = c->ctrl;
     a.trav_warps = (uint32_t)c->grid_ext * (WF_THREADS / 32);
+    a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
 }
 
 // The wavefront loop: runs samples [ks_begin, ks_end) (ks = k*4 + sub-pixel) of every local pixel,
@@ -445,6 +446,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                   volatile int* cancel, rtb_stats& st, bool& cancelled) {
     cancelled = false;
     a.trav_warps = (uint32_t)(count_work ? c->grid_ext_count : c->grid_ext) * (WF_THREADS / 32);   // must match the launched grid
+    a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
     DevCtrl h{};
     h.ext_head(0) = h.ext_head(1) = 0;
     h.ext_tail(0) = h.ext_tail(1) = a.P;

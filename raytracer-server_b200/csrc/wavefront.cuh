@@ -30,6 +30,7 @@ constexpr uint32_t SHADOW_PROBE = 0x80000000u;  // shadow entry = dead-MIS probe
 constexpr uint32_t MAX_DEPTH_FIELD = 4095u;
 constexpr uint32_t FETCH_CHUNK = 32;     // ray indices a warp reserves per atomic
 constexpr int REFILL_BELOW = 22;         // default: refill a warp when fewer than this many lanes are still traversing
+constexpr uint32_t SHADE_CHUNK = 32;     // queue entries a k_shade warp reserves per atomic
 constexpr int INNER_STEPS = 8;           // default: inner-node steps a lane may take before the warp re-checks for idle lanes
 
 struct PathQueue {   // capacity P each
@@ -52,7 +53,7 @@ struct alignas(128) PaddedCounter {
     uint32_t pad[31];
 };
 struct DevCtrl {
-    PaddedCounter ext_head_[2], ext_tail_[2], sh_head_[2], cursor_trav_;
+    PaddedCounter ext_head_[2], ext_tail_[2], sh_head_[2], cursor_trav_, cursor_shade_;
     uint32_t gen_count;
     uint32_t active;        // paths alive in the current queue after k_prepare (+ reserved samples + pending shadow rays)
     unsigned long long gen_base, work_next, work_total;
@@ -66,6 +67,7 @@ struct DevCtrl {
 #define ext_tail(i) ext_tail_[i].v
 #define sh_head(i) sh_head_[i].v
 #define cursor_trav cursor_trav_.v
+#define cursor_shade cursor_shade_.v
 
 struct RenderArgs {
     DevScene S;
@@ -90,6 +92,7 @@ struct RenderArgs {
     // host can stop launching without a copy or an event per iteration
     volatile unsigned long long* host_state;
     uint32_t trav_warps;   // warps in the k_traverse grid: each owns the static first chunk [w*32, w*32+32)
+    uint32_t shade_warps;  // same for k_shade
 };
 
 // ---------------------------------------------------------------- tile order <-> pixels
@@ -136,21 +139,20 @@ __device__ __forceinline__ PushSlots push_all(uint32_t* ext_head, uint32_t* ext_
 // Block-aggregated variant for k_shade: the 8 warps of a CTA pool their counts in shared memory and
 // three threads issue ONE atomic per counter per CTA iteration (fewer same-address atomics at L2).
 // Every thread of the CTA must call it (two __syncthreads inside).
-constexpr int SHADE_THREADS = 256;   // CTA size of k_shade: 4 warps share one set of queue atomics
+constexpr int SHADE_THREADS = 256;   // CTA size of k_shade
 struct BlockPushSmem {
     uint32_t cnt[SHADE_THREADS / 32][4];
     uint32_t base[SHADE_THREADS / 32][4];
 };
-// k_shade writes its outputs ONE TRIP LATE: a trip stages its new rays in shared memory and issues the queue
-// atomics without waiting; the next trip (a few microseconds of arithmetic later) picks the returned bases up
-// and flushes the staged rays.  The round trip of the global atomics is hidden behind a whole trip.
+// k_shade writes its outputs ONE TRIP LATE: a trip stages its new rays in shared memory (a private column per
+// thread: no barrier) and lanes 0..2 issue the warp's queue atomics without waiting; the next trip (a few
+// microseconds of arithmetic later) picks the returned bases up and flushes the staged rays.  The round trip of
+// the global atomics is hidden behind a whole trip.
 struct ShadeStage {
     float4 eo[SHADE_THREADS], ed[SHADE_THREADS], eb[SHADE_THREADS], ev[SHADE_THREADS];
     float4 so[SHADE_THREADS], sd[SHADE_THREADS], sc[SHADE_THREADS], pd[SHADE_THREADS], pc[SHADE_THREADS];
     float2 eh[SHADE_THREADS];
     uint32_t meta[SHADE_THREADS];               // bit0 ext, bit1 front, bit2 shadow, bit3 probe, bits 8.. ranks
-    uint32_t cnt[2][SHADE_THREADS / 32][4];     // per-warp counts {front, back, shadow+probe}, double buffered
-    uint32_t base[SHADE_THREADS / 32][4];       // per-warp bases of the trip being flushed
 };
 
 __device__ __forceinline__ PushSlots push_all_block(BlockPushSmem& sm, uint32_t* ext_head, uint32_t* ext_tail, uint32_t* sh_head,
@@ -214,6 +216,7 @@ __global__ void k_prepare(RenderArgs a, int c) {
     C->ext_tail(1 - c) = a.P;
     C->sh_head(1 - c) = 0;
     C->cursor_trav = a.trav_warps * FETCH_CHUNK;   // chunks below that are handed out statically (no atomic)
+    C->cursor_shade = a.shade_warps * SHADE_CHUNK;
     C->active = count + n_new + C->sh_head(c);   // pending shadow rays keep the loop alive
     C->iterations++;
     if (a.host_state) {
@@ -437,35 +440,13 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
     }
 }
 
-// threads 0..2 (class = threadIdx.x: front, back, shadow): turn the base returned by LAST trip's atomic into
-// per-warp bases for the staged trip, then issue THIS trip's atomic without waiting for it
-__device__ __forceinline__ void shade_reserve(ShadeStage& st, int cbuf, bool have_prev, uint32_t& pend_base, uint32_t* ctr_front,
-                                              uint32_t* ctr_back, uint32_t* ctr_sh) {
-    const int cls = threadIdx.x;
-    if (have_prev) {
-        const uint32_t b = pend_base;
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < SHADE_THREADS / 32; ++w) {
-            st.base[w][cls] = cls == 1 ? b - run : b + run;   // the back class grows downward
-            run += st.cnt[cbuf ^ 1][w][cls];
-        }
-    }
-    if (ctr_front) {
-        uint32_t tot = 0;
-#pragma unroll
-        for (int w = 0; w < SHADE_THREADS / 32; ++w) tot += st.cnt[cbuf][w][cls];
-        pend_base = 0;
-        if (tot) pend_base = cls == 0 ? atomicAdd(ctr_front, tot) : (cls == 1 ? atomicSub(ctr_back, tot) : atomicAdd(ctr_sh, tot));
-    }
-}
-// every thread writes the rays it staged one trip ago
-__device__ __forceinline__ void shade_flush(const ShadeStage& st, const PathQueue& N, const ShadowQueue& SQ) {
-    const unsigned warp = threadIdx.x >> 5;
+// every thread writes the rays it staged one trip ago; bf / bb / bs = the warp's bases in the three queue classes
+__device__ __forceinline__ void shade_flush(const ShadeStage& st, const PathQueue& N, const ShadowQueue& SQ, uint32_t bf, uint32_t bb,
+                                            uint32_t bs) {
     const uint32_t m = st.meta[threadIdx.x];
     if (m & 1u) {
         const uint32_t r = (m >> 8) & 63u;
-        const uint32_t slot = (m & 2u) ? st.base[warp][0] + r : st.base[warp][1] - 1u - r;
+        const uint32_t slot = (m & 2u) ? bf + r : bb - 1u - r;   // the back class grows downward
         const float4 eo = st.eo[threadIdx.x];
         N.o[slot] = eo;
         N.d[slot] = st.ed[threadIdx.x];
@@ -474,13 +455,13 @@ __device__ __forceinline__ void shade_flush(const ShadeStage& st, const PathQueu
         if (__float_as_uint(eo.w) & PC_STALE_O) N.ov[slot] = st.ev[threadIdx.x];
     }
     if (m & 4u) {
-        const uint32_t slot = st.base[warp][2] + ((m >> 14) & 63u);
+        const uint32_t slot = bs + ((m >> 14) & 63u);
         SQ.o[slot] = st.so[threadIdx.x];
         SQ.d[slot] = st.sd[threadIdx.x];
         SQ.c[slot] = st.sc[threadIdx.x];
     }
     if (m & 8u) {
-        const uint32_t slot = st.base[warp][2] + ((m >> 20) & 63u);
+        const uint32_t slot = bs + ((m >> 20) & 63u);
         SQ.o[slot] = st.so[threadIdx.x];
         SQ.d[slot] = st.pd[threadIdx.x];
         SQ.c[slot] = st.pc[threadIdx.x];
@@ -488,9 +469,17 @@ __device__ __forceinline__ void shade_flush(const ShadeStage& st, const PathQueu
 }
 
 // ---------------------------------------------------------------- k_shade
-// Everything of reflected_radiance except the mesh traversal.  Coherent: static warp -> slot mapping,
-// no work-fetch atomics; the only atomics are the queue pushes (3 per warp, overlapped) and the
-// accumulator REDs.
+// Everything of reflected_radiance except the mesh traversal, as a PERSISTENT kernel of independent warps (no
+// CTA barrier after the table staging).  A lane keeps its path IN REGISTERS from vertex to vertex for as long as
+// the next nearest hit is already final after the analytic pass (the extension ray cannot reach the mesh box):
+// the recursion of src/scene.rs:161-244 becomes a loop, and only rays that need k_traverse go through a queue —
+//   * extension ray reaches the mesh box        -> front class of the other path queue, lane takes a new path
+//   * NEE candidate reaches the mesh box        -> shadow queue; the path itself is then parked in the back class
+//     (at most ONE shadow entry and ONE path entry per input path and iteration: the queue capacities hold)
+//   * path ends (roulette, dead surface, miss)  -> lane takes a new path
+// New paths come from the current queue: a warp owns one static chunk of SHADE_CHUNK entries and then reserves
+// further chunks from a work cursor one chunk ahead; every lane holds one PREFETCHED entry, so the (streaming)
+// queue loads of a new path are issued a whole trip before they are needed.
 // FAST = the reference scenes' case, resolved at compile time: live NEE estimator, Diffuse / Specular materials
 // only, sphere light, no probe items.  The general instantiation keeps every branch (dead-MIS estimator, Phong,
 // mesh lights, rtb_sample_radiance probes).
@@ -501,9 +490,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     const DevSceneHeader* hdr = a.S.hdr;
     const uint32_t head = C->ext_head(c), tail = C->ext_tail(c);
     const uint32_t count = head + (a.P - tail);
-    if (blockIdx.x * SHADE_THREADS >= count) return;   // tail iterations: this CTA has no queue entries
+    if (blockIdx.x * (SHADE_THREADS / 32) * SHADE_CHUNK >= count) return;   // CTA beyond the static region of a small launch
     const SharedScene sh = stage_scene(a.S, smem_raw, false);
     const unsigned lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
     const PathQueue Q = a.q[c], N = a.q[1 - c];
     const int light_obj = hdr->light_obj;
     const bool light_is_mesh = FAST ? false : hdr->light_geom == 2;
@@ -512,61 +502,80 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     const float3 Le = f3(sh.mats[light_obj].emitted);
     const int n_prims = a.S.n_prims, n_planes = a.S.n_planes;
     __shared__ ShadeStage st;
-    uint32_t pend_base = 0;   // threads 0..2: value returned by last trip's atomic for class threadIdx.x
-    bool have_prev = false;   // CTA-uniform: a staged trip is waiting to be flushed
-    int cbuf = 0;
-    const unsigned warp = threadIdx.x >> 5;
     const ShadowQueue SQ = a.sq[1 - c];
     uint32_t* const ctr_front = &C->ext_head(1 - c);
     uint32_t* const ctr_back = &C->ext_tail(1 - c);
     uint32_t* const ctr_sh = &C->sh_head(1 - c);
     uint32_t n_ext = 0, n_ext_bvh = 0, n_sh = 0, n_sh_bvh = 0;
-
-    // Software pipeline: the queue entry of the NEXT trip is loaded while this trip computes (the loads are
-    // streaming / random and would otherwise sit at the head of a long dependent chain at 16 warps per SM).
     auto slot_of = [&](uint32_t i) { return i < head ? i : tail + (i - head); };
-    const uint32_t stride_items = gridDim.x * SHADE_THREADS;
-    float2 h2_n = make_float2(0.f, __uint_as_float(PC_NONE));
-    float4 o4_n = make_float4(0, 0, 0, 0), d4_n = o4_n, b4_n = o4_n, tri_n_n = o4_n;
-    {
-        const uint32_t i0 = blockIdx.x * SHADE_THREADS + threadIdx.x;
-        if (i0 < count) {
-            const uint32_t s0 = slot_of(i0);
-            h2_n = Q.hit[s0];
-            o4_n = Q.o[s0];
-            d4_n = Q.d[s0];
-            b4_n = Q.beta[s0];
-            const uint32_t id0 = __float_as_uint(h2_n.y);
-            if (id0 != PC_NONE && id0 >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (id0 - TRI_BASE));
-        }
-    }
 
-    // CTA-uniform trip count: all threads of the CTA walk the queue in lock step (push_all_block synchronises)
-    for (uint32_t base = blockIdx.x * SHADE_THREADS; base < count; base += stride_items) {
-        const uint32_t i = base + threadIdx.x;
-        const bool valid = i < count;
+    // ---- work fetch (warp-uniform): static first chunk, then chunks from the cursor, reserved one ahead
+    const uint32_t gwarp = (blockIdx.x * SHADE_THREADS + threadIdx.x) >> 5;
+    uint32_t wnext = min(gwarp * SHADE_CHUNK, count), wend = min(gwarp * SHADE_CHUNK + SHADE_CHUNK, count);
+    bool exhausted = count <= a.shade_warps * SHADE_CHUNK;   // no dynamic chunks in a small launch: no atomics at all
+    uint32_t nbase = 0;                                      // lane 0: base of the chunk reserved ahead
+    if (!exhausted && lane == 0) nbase = atomicAdd(&C->cursor_shade, SHADE_CHUNK);
+
+    // ---- lane state: the path being shaded + one prefetched queue entry
+    bool cur_valid = false, cont = false, sp_valid = false, sp_nrm = false;
+    float2 h2 = make_float2(0.f, __uint_as_float(PC_NONE)), h2_n = h2;
+    float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, b4 = o4, tri_n = o4;   // cont: tri_n carries the stale `o` instead
+    float4 o4_n = o4, d4_n = o4, b4_n = o4, tri_n_n = o4;
+    uint32_t cur_slot = 0, sp_slot = 0;
+    uint32_t pend_base = 0;    // lanes 0..2: value returned by last trip's atomic for class = lane
+    unsigned prev_any = 0;     // warp-uniform: a staged trip is waiting to be flushed
+
+    for (;;) {
+        // (a) lanes without a path take their prefetched entry
+        if (!cur_valid && sp_valid) {
+            h2 = h2_n; o4 = o4_n; d4 = d4_n; b4 = b4_n;
+            cur_slot = sp_slot;
+            if (!sp_nrm) {
+                const uint32_t idn = __float_as_uint(h2_n.y);
+                tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
+            }
+            tri_n = tri_n_n;
+            cur_valid = true;
+            cont = false;
+            sp_valid = false;
+        }
+        // (b) refill the prefetch registers from the warp's chunk
+        {
+            const unsigned need = __ballot_sync(0xffffffffu, !sp_valid);
+            if (need && wnext < wend) {
+                const uint32_t my = wnext + __popc(need & below);
+                if (!sp_valid && my < wend) {
+                    sp_slot = slot_of(my);
+                    h2_n = Q.hit[sp_slot];
+                    o4_n = Q.o[sp_slot];
+                    d4_n = Q.d[sp_slot];
+                    b4_n = Q.beta[sp_slot];
+                    sp_valid = true;
+                    sp_nrm = false;
+                }
+                wnext = min(wnext + (uint32_t)__popc(need), wend);
+            }
+            if (wnext >= wend && !exhausted) {   // switch to the chunk reserved ahead, reserve the one after it
+                const uint32_t b = __shfl_sync(0xffffffffu, nbase, 0);
+                if (b >= count) exhausted = true;
+                else {
+                    wnext = b;
+                    wend = min(b + SHADE_CHUNK, count);
+                    if (lane == 0) nbase = atomicAdd(&C->cursor_shade, SHADE_CHUNK);
+                }
+            }
+        }
+        // (c) done when no lane holds a path or a prefetched entry and the queue is drained
+        if (__ballot_sync(0xffffffffu, cur_valid || sp_valid) == 0 && wnext >= wend && exhausted) break;
+
         bool ext_push = false, ext_front = false, sh_push = false, pr_push = false;
         float4 eo = make_float4(0, 0, 0, 0), ed = eo, eb = eo, ev = eo;
-        float2 eh = make_float2(0.f, 0.f);
+        float2 eh = make_float2(0.f, __uint_as_float(PC_NONE));
         float4 so = eo, sd = eo, sc = eo;
         float4 pd = eo, pc = eo;  // probe entry shares `so`
 
-        // this trip's entry (prefetched), then start the next trip's loads
-        const float2 h2 = h2_n;
-        const float4 o4 = o4_n, d4 = d4_n, b4 = b4_n, tri_n = tri_n_n;
-        const uint32_t i_next = i + stride_items;
-        const bool valid_next = i_next < count;
-        const uint32_t slot_next = slot_of(i_next);
-        h2_n = make_float2(0.f, __uint_as_float(PC_NONE));
-        if (valid_next) {
-            h2_n = Q.hit[slot_next];
-            o4_n = Q.o[slot_next];
-            d4_n = Q.d[slot_next];
-            b4_n = Q.beta[slot_next];
-        }
-
-        if (valid) {
-            const uint32_t idx = slot_of(i);
+        if (cur_valid) {
             const uint32_t id = __float_as_uint(h2.y);
             if (id != PC_NONE) {
                 const float t = h2.x;
@@ -578,7 +587,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                 const uint32_t sample = sdw >> 12, depth = sdw & 0xfffu;
                 const HitGeom hg = hit_geometry(sh, o, d, t, id, tri_n);
                 const DevMaterial& mat = sh.mats[hg.obj];
-                const float3 ovec = (origin & PC_STALE_O) ? f3(Q.ov[idx]) : -d;
+                const float3 ovec = (origin & PC_STALE_O) ? (cont ? f3(tri_n) : f3(Q.ov[cur_slot])) : -d;
                 const float3 emitted = f3(mat.emitted);
                 const bool emits = emitted.x != 0.f || emitted.y != 0.f || emitted.z != 0.f;
                 // emission: received_radiance adds emitted(obj0) (src/scene.rs:155); a specular vertex adds
@@ -731,28 +740,31 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
                 }
             }
         }
-        // next trip: its hit id has arrived by now -> start the dependent triangle-normal fetch
-        {
-            const uint32_t idn = __float_as_uint(h2_n.y);
-            tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid_next && idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
+        // ---- where does the path go?  In registers if its next hit is final and it queued no shadow ray.
+        bool keep = ext_push && !ext_front && !sh_push && !pr_push;
+        if (ext_push && !ext_front && __float_as_uint(eh.y) == PC_NONE) {   // left the scene: nothing to shade
+            keep = false;
+            ext_push = false;
         }
-        // ---- compaction, one trip late (see ShadeStage): all threads of the CTA take part
+        if (keep) ext_push = false;
+        // ---- compaction, one trip late (see ShadeStage)
         const unsigned mf = __ballot_sync(0xffffffffu, ext_push && ext_front);
         const unsigned mb = __ballot_sync(0xffffffffu, ext_push && !ext_front);
         const unsigned ms = __ballot_sync(0xffffffffu, sh_push);
         const unsigned mp = __ballot_sync(0xffffffffu, pr_push);
-        if (lane == 0) {
-            st.cnt[cbuf][warp][0] = __popc(mf);
-            st.cnt[cbuf][warp][1] = __popc(mb);
-            st.cnt[cbuf][warp][2] = __popc(ms) + __popc(mp);
+        if (prev_any) {
+            const uint32_t bf = __shfl_sync(0xffffffffu, pend_base, 0);
+            const uint32_t bb = __shfl_sync(0xffffffffu, pend_base, 1);
+            const uint32_t bs = __shfl_sync(0xffffffffu, pend_base, 2);
+            shade_flush(st, N, SQ, bf, bb, bs);
         }
-        __syncthreads();
-        if (threadIdx.x < 3) shade_reserve(st, cbuf, have_prev, pend_base, ctr_front, ctr_back, ctr_sh);
-        __syncthreads();
-        if (have_prev) shade_flush(st, N, SQ);
-        {   // stage this trip
-            const unsigned below = (1u << lane) - 1u;
+        prev_any = mf | mb | ms | mp;
+        if (prev_any) {
+            {   // ONE atomic instruction for the three classes (lane = class; the back class grows downward: add -n).
+                // Three separate atomics into the same destination register would serialise on its scoreboard.
+                const uint32_t n = lane == 0 ? (uint32_t)__popc(mf) : (lane == 1 ? 0u - (uint32_t)__popc(mb) : (uint32_t)(__popc(ms) + __popc(mp)));
+                if (lane < 3 && n != 0u) pend_base = atomicAdd(lane == 0 ? ctr_front : (lane == 1 ? ctr_back : ctr_sh), n);
+            }
             const uint32_t r_ext = ext_front ? __popc(mf & below) : __popc(mb & below);
             const uint32_t r_sh = __popc(ms & below), r_pr = __popc(ms) + __popc(mp & below);
             st.meta[threadIdx.x] = (ext_push ? 1u : 0u) | (ext_front ? 2u : 0u) | (sh_push ? 4u : 0u) | (pr_push ? 8u : 0u) |
@@ -765,15 +777,27 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
             if (sh_push) { st.sd[threadIdx.x] = sd; st.sc[threadIdx.x] = sc; }
             if (pr_push) { st.pd[threadIdx.x] = pd; st.pc[threadIdx.x] = pc; }
         }
-        have_prev = true;
-        cbuf ^= 1;
+        // ---- next vertex of the same path, straight from registers
+        cur_valid = keep;
+        if (keep) {
+            o4 = eo; d4 = ed; b4 = eb; h2 = eh;
+            tri_n = ev;      // stale `o` of a specular vertex (PC_STALE_O in eo.w); analytic hits need no triangle normal
+            cont = true;
+        }
+        // ---- the prefetched entry's hit id has arrived by now -> start the dependent triangle-normal fetch
+        if (sp_valid && !sp_nrm) {
+            const uint32_t idn = __float_as_uint(h2_n.y);
+            tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
+            sp_nrm = true;
+        }
     }
     // epilogue: flush the last staged trip
-    if (have_prev) {
-        __syncthreads();
-        if (threadIdx.x < 3) shade_reserve(st, cbuf, true, pend_base, nullptr, nullptr, nullptr);
-        __syncthreads();
-        shade_flush(st, N, SQ);
+    if (prev_any) {
+        const uint32_t bf = __shfl_sync(0xffffffffu, pend_base, 0);
+        const uint32_t bb = __shfl_sync(0xffffffffu, pend_base, 1);
+        const uint32_t bs = __shfl_sync(0xffffffffu, pend_base, 2);
+        shade_flush(st, N, SQ, bf, bb, bs);
     }
     // counters
     for (int off = 16; off; off >>= 1) {
