@@ -49,6 +49,7 @@ struct RenderContext {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     uint32_t P = 0, SP = 0;
+    uint32_t Pcap = 0, SPcap = 0;   // physical slots: P, SP + room for k_shade's unfilled segment tails
     float4* qbuf = nullptr;      // 2 queues x (4 float4 arrays + 1 float2 array) x P
     float4* sbuf = nullptr;      // 2 shadow queues x 3 arrays x SP
     float4* accum = nullptr;
@@ -338,17 +339,25 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate, WF_THREADS, smem_tab));
         c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
     }
+    // every k_shade warp may leave up to two unfilled SHADE_SEG segments per queue class behind in each iteration
+    const uint32_t seg_room = (uint32_t)c->grid_shade * (SHADE_THREADS / 32) * 2u * SHADE_SEG;
     if (c->P != P) {
         cudaFree(c->qbuf);
         c->qbuf = nullptr;
-        CU_TRY(cudaMalloc((void**)&c->qbuf, (size_t)P * 9 * sizeof(float4)));
+        c->P = 0;
+        const uint32_t cap = P + 2u * seg_room;   // front + back class
+        CU_TRY(cudaMalloc((void**)&c->qbuf, (size_t)cap * 9 * sizeof(float4)));
         c->P = P;
+        c->Pcap = cap;
     }
     if (c->SP != SP) {
         cudaFree(c->sbuf);
         c->sbuf = nullptr;
-        CU_TRY(cudaMalloc((void**)&c->sbuf, (size_t)SP * 6 * sizeof(float4)));
+        c->SP = 0;
+        const uint32_t cap = SP + seg_room;
+        CU_TRY(cudaMalloc((void**)&c->sbuf, (size_t)cap * 6 * sizeof(float4)));
         c->SP = SP;
+        c->SPcap = cap;
     }
     if (c->accum_cap < accum_elems) {
         cudaFree(c->accum);
@@ -420,19 +429,21 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     a.n_local_tiles = local_tiles(p);
     a.P = c->P;
     a.SP = c->SP;
+    a.Pcap = c->Pcap;
+    a.SPcap = c->SPcap;
     for (int k = 0; k < 2; ++k) {
-        float4* b = c->qbuf + (size_t)k * 4 * c->P;
+        float4* b = c->qbuf + (size_t)k * 4 * c->Pcap;
         a.q[k].o = b;
-        a.q[k].d = b + c->P;
-        a.q[k].beta = b + 2 * (size_t)c->P;
-        a.q[k].ov = b + 3 * (size_t)c->P;
-        a.q[k].hit = reinterpret_cast<float2*>(c->qbuf + (size_t)8 * c->P) + (size_t)k * c->P;
+        a.q[k].d = b + c->Pcap;
+        a.q[k].beta = b + 2 * (size_t)c->Pcap;
+        a.q[k].ov = b + 3 * (size_t)c->Pcap;
+        a.q[k].hit = reinterpret_cast<float2*>(c->qbuf + (size_t)8 * c->Pcap) + (size_t)k * c->Pcap;
     }
     for (int k = 0; k < 2; ++k) {
-        float4* b = c->sbuf + (size_t)k * 3 * c->SP;
+        float4* b = c->sbuf + (size_t)k * 3 * c->SPcap;
         a.sq[k].o = b;
-        a.sq[k].d = b + c->SP;
-        a.sq[k].c = b + 2 * (size_t)c->SP;
+        a.sq[k].d = b + c->SPcap;
+        a.sq[k].c = b + 2 * (size_t)c->SPcap;
     }
     a.accum = c->accum;
     a.ctrl = c->ctrl;
@@ -449,7 +460,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
     DevCtrl h{};
     h.ext_head(0) = h.ext_head(1) = 0;
-    h.ext_tail(0) = h.ext_tail(1) = a.P;
+    h.ext_tail(0) = h.ext_tail(1) = a.Pcap;
     h.sh_head(0) = h.sh_head(1) = 0;
     unsigned long long npl = (unsigned long long)a.n_local_tiles * 1024ull;
     h.work_next = a.probe_px ? 0ull : (unsigned long long)ks_begin * npl;

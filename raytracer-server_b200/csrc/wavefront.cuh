@@ -31,6 +31,9 @@ constexpr uint32_t MAX_DEPTH_FIELD = 4095u;
 constexpr uint32_t FETCH_CHUNK = 32;     // ray indices a warp reserves per atomic
 constexpr int REFILL_BELOW = 22;         // default: refill a warp when fewer than this many lanes are still traversing
 constexpr uint32_t SHADE_CHUNK = 32;     // queue entries a k_shade warp reserves per atomic
+constexpr uint32_t SHADE_SEG = 128;      // OUTPUT slots a k_shade warp reserves per atomic in each queue class
+constexpr uint32_t HIT_HOLE = 0xffffffffu;       // path-queue slot reserved by a k_shade warp but never filled (hit.y)
+constexpr uint32_t TLIM_HOLE = 0xff800000u;      // same for the shadow queue (d.w = -inf)
 constexpr int INNER_STEPS = 8;           // default: inner-node steps a lane may take before the warp re-checks for idle lanes
 
 struct PathQueue {   // capacity P each
@@ -55,6 +58,7 @@ struct alignas(128) PaddedCounter {
 struct DevCtrl {
     PaddedCounter ext_head_[2], ext_tail_[2], sh_head_[2], cursor_trav_, cursor_shade_;
     uint32_t gen_count;
+    uint32_t live[2], sh_live[2];   // FILLED entries of path / shadow queue c (the heads / tails also count reserved-but-unfilled slots)
     uint32_t active;        // paths alive in the current queue after k_prepare (+ reserved samples + pending shadow rays)
     unsigned long long gen_base, work_next, work_total;
     unsigned long long samples, rays_primary, rays_extension, rays_shadow, iterations;
@@ -77,7 +81,8 @@ struct RenderArgs {
     uint32_t k0, k1;
     int estimator;
     int rank, world, tiles_x, tiles_y, n_local_tiles;
-    uint32_t P, SP;
+    uint32_t P, SP;          // most paths / shadow rays alive at once
+    uint32_t Pcap, SPcap;    // physical slots per queue: P, SP + room for the unfilled tails of k_shade's per-warp segments
     PathQueue q[2];
     ShadowQueue sq[2];   // sq[c] is read by k_traverse(c) and was written by k_shade(1-c)
     float4* accum;       // [pixel*4 + sub] -> (r, g, b, -) sums
@@ -144,17 +149,6 @@ struct BlockPushSmem {
     uint32_t cnt[SHADE_THREADS / 32][4];
     uint32_t base[SHADE_THREADS / 32][4];
 };
-// k_shade writes its outputs ONE TRIP LATE: a trip stages its new rays in shared memory (a private column per
-// thread: no barrier) and lanes 0..2 issue the warp's queue atomics without waiting; the next trip (a few
-// microseconds of arithmetic later) picks the returned bases up and flushes the staged rays.  The round trip of
-// the global atomics is hidden behind a whole trip.
-struct ShadeStage {
-    float4 eo[SHADE_THREADS], ed[SHADE_THREADS], eb[SHADE_THREADS], ev[SHADE_THREADS];
-    float4 so[SHADE_THREADS], sd[SHADE_THREADS], sc[SHADE_THREADS], pd[SHADE_THREADS], pc[SHADE_THREADS];
-    float2 eh[SHADE_THREADS];
-    uint32_t meta[SHADE_THREADS];               // bit0 ext, bit1 front, bit2 shadow, bit3 probe, bits 8.. ranks
-};
-
 __device__ __forceinline__ PushSlots push_all_block(BlockPushSmem& sm, uint32_t* ext_head, uint32_t* ext_tail, uint32_t* sh_head,
                                                     bool ext_push, bool ext_front, bool sh_push, bool pr_push) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -204,20 +198,21 @@ __device__ __forceinline__ int object_of(const DevScene& S, const SharedScene& s
 // ---------------------------------------------------------------- k_prepare
 __global__ void k_prepare(RenderArgs a, int c) {
     DevCtrl* C = a.ctrl;
-    uint32_t head = C->ext_head(c), tail = C->ext_tail(c);
-    uint32_t count = head + (a.P - tail);
-    uint32_t free_slots = tail - head;
+    const uint32_t live = C->live[c];           // paths k_shade(1 - c) handed on
+    const uint32_t free_slots = a.P - live;
     unsigned long long remaining = C->work_total - C->work_next;
     uint32_t n_new = remaining < (unsigned long long)free_slots ? (uint32_t)remaining : free_slots;
     C->gen_base = C->work_next;
     C->gen_count = n_new;
     C->work_next += n_new;
     C->ext_head(1 - c) = 0;
-    C->ext_tail(1 - c) = a.P;
+    C->ext_tail(1 - c) = a.Pcap;
     C->sh_head(1 - c) = 0;
+    C->live[1 - c] = 0;
+    C->sh_live[1 - c] = 0;
     C->cursor_trav = a.trav_warps * FETCH_CHUNK;   // chunks below that are handed out statically (no atomic)
     C->cursor_shade = a.shade_warps * SHADE_CHUNK;
-    C->active = count + n_new + C->sh_head(c);   // pending shadow rays keep the loop alive
+    C->active = live + n_new + C->sh_live[c];   // pending shadow rays keep the loop alive
     C->iterations++;
     if (a.host_state) {
         a.host_state[1] = C->active;
@@ -376,18 +371,24 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
             else {
                 const uint32_t my = wnext + __popc(idle_mask & ((1u << lane) - 1u));
                 if (idle && my < wend) {
+                    // slots a k_shade warp reserved but did not fill are marked as holes: the lane stays idle this round
                     if (my < n_ext) {
-                        slot = my;
-                        kind = 0;
-                        const float4 o4 = Q.o[my], d4 = Q.d[my];
                         const float2 h2 = Q.hit[my];
-                        trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), h2.x, a.S.root);
+                        if (__float_as_uint(h2.y) != HIT_HOLE) {
+                            slot = my;
+                            kind = 0;
+                            const float4 o4 = Q.o[my], d4 = Q.d[my];
+                            trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), h2.x, a.S.root);
+                        }
                     } else {
-                        slot = my - n_ext;
-                        const float4 o4 = SQ.o[slot], d4 = SQ.d[slot];
-                        kind = (__float_as_uint(SQ.c[slot].w) & SHADOW_PROBE) ? 2 : 1;
-                        occluded = false;
-                        trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), d4.w, a.S.root);
+                        const float4 d4 = SQ.d[my - n_ext];
+                        if (__float_as_uint(d4.w) != TLIM_HOLE) {
+                            slot = my - n_ext;
+                            const float4 o4 = SQ.o[slot];
+                            kind = (__float_as_uint(SQ.c[slot].w) & SHADOW_PROBE) ? 2 : 1;
+                            occluded = false;
+                            trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), d4.w, a.S.root);
+                        }
                     }
                 }
                 if (COUNT && lane == 0) { dbg[4] += 1; dbg[5] += min((uint32_t)__popc(idle_mask), wend - wnext); }
@@ -440,33 +441,41 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
     }
 }
 
-// every thread writes the rays it staged one trip ago; bf / bb / bs = the warp's bases in the three queue classes
-__device__ __forceinline__ void shade_flush(const ShadeStage& st, const PathQueue& N, const ShadowQueue& SQ, uint32_t bf, uint32_t bb,
-                                            uint32_t bs) {
-    const uint32_t m = st.meta[threadIdx.x];
-    if (m & 1u) {
-        const uint32_t r = (m >> 8) & 63u;
-        const uint32_t slot = (m & 2u) ? bf + r : bb - 1u - r;   // the back class grows downward
-        const float4 eo = st.eo[threadIdx.x];
-        N.o[slot] = eo;
-        N.d[slot] = st.ed[threadIdx.x];
-        N.beta[slot] = st.eb[threadIdx.x];
-        N.hit[slot] = st.eh[threadIdx.x];
-        if (__float_as_uint(eo.w) & PC_STALE_O) N.ov[slot] = st.ev[threadIdx.x];
+// Output slots of k_shade: a warp reserves SHADE_SEG slots of a queue class with ONE atomic and hands them out
+// to its lanes over the following trips with warp-local arithmetic; the next segment is reserved while the
+// current one still has room for two trips, so the atomic's round trip is never waited for.  (Exact per-trip
+// reservations cost one global atomic per warp and trip, whose latency the warp ends up waiting for.)  The slots
+// left over when the kernel ends are marked as holes (HIT_HOLE / TLIM_HOLE), which the consumers skip.
+// All arguments but `lane` are warp-uniform; lane `cls` keeps the base of the reserved-ahead segment in `nb`.
+// DIR = +1: slots grow upward from the returned counter value; -1: downward (back class of the path queue).
+template <int DIR>
+__device__ __forceinline__ uint32_t seg_alloc(uint32_t& base, uint32_t& used, bool& has_next, uint32_t& nb, unsigned cls,
+                                              uint32_t* ctr, unsigned mask, unsigned lane) {
+    const uint32_t n = __popc(mask);
+    const uint32_t r = used + __popc(mask & ((1u << lane) - 1u));
+    const uint32_t step = (uint32_t)(DIR * (int)SHADE_SEG);
+    uint32_t slot;
+    if (used + n > SHADE_SEG) {   // runs over into the next segment
+        if (!has_next && lane == cls) nb = atomicAdd(ctr, step);
+        uint32_t nbase = __shfl_sync(0xffffffffu, nb, cls);
+        if (DIR < 0) nbase -= 1u;   // element 0 of a downward segment sits just below the old tail
+        slot = r < SHADE_SEG ? base + (uint32_t)(DIR * (int)r) : nbase + (uint32_t)(DIR * (int)(r - SHADE_SEG));
+        base = nbase;
+        used = used + n - SHADE_SEG;
+        has_next = false;
+    } else {
+        slot = base + (uint32_t)(DIR * (int)r);
+        used += n;
     }
-    if (m & 4u) {
-        const uint32_t slot = bs + ((m >> 14) & 63u);
-        SQ.o[slot] = st.so[threadIdx.x];
-        SQ.d[slot] = st.sd[threadIdx.x];
-        SQ.c[slot] = st.sc[threadIdx.x];
+    if (!has_next && used + 64u > SHADE_SEG) {
+        if (lane == cls) nb = atomicAdd(ctr, step);
+        has_next = true;
     }
-    if (m & 8u) {
-        const uint32_t slot = bs + ((m >> 20) & 63u);
-        SQ.o[slot] = st.so[threadIdx.x];
-        SQ.d[slot] = st.pd[threadIdx.x];
-        SQ.c[slot] = st.pc[threadIdx.x];
-    }
+    return slot;
 }
+// element k of the segment whose element 0 is `base`
+template <int DIR>
+__device__ __forceinline__ uint32_t seg_slot(uint32_t base, uint32_t k) { return base + (uint32_t)(DIR * (int)k); }
 
 // ---------------------------------------------------------------- k_shade
 // Everything of reflected_radiance except the mesh traversal, as a PERSISTENT kernel of independent warps (no
@@ -489,7 +498,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     DevCtrl* C = a.ctrl;
     const DevSceneHeader* hdr = a.S.hdr;
     const uint32_t head = C->ext_head(c), tail = C->ext_tail(c);
-    const uint32_t count = head + (a.P - tail);
+    const uint32_t count = head + (a.Pcap - tail);
     if (blockIdx.x * (SHADE_THREADS / 32) * SHADE_CHUNK >= count) return;   // CTA beyond the static region of a small launch
     const SharedScene sh = stage_scene(a.S, smem_raw, false);
     const unsigned lane = threadIdx.x & 31;
@@ -501,12 +510,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     const bool probe_mode = FAST ? false : a.probe_px != nullptr;
     const float3 Le = f3(sh.mats[light_obj].emitted);
     const int n_prims = a.S.n_prims, n_planes = a.S.n_planes;
-    __shared__ ShadeStage st;
     const ShadowQueue SQ = a.sq[1 - c];
     uint32_t* const ctr_front = &C->ext_head(1 - c);
     uint32_t* const ctr_back = &C->ext_tail(1 - c);
     uint32_t* const ctr_sh = &C->sh_head(1 - c);
-    uint32_t n_ext = 0, n_ext_bvh = 0, n_sh = 0, n_sh_bvh = 0;
+    uint32_t n_ext = 0, n_ext_bvh = 0, n_sh = 0, n_sh_bvh = 0, n_queued = 0;
     auto slot_of = [&](uint32_t i) { return i < head ? i : tail + (i - head); };
 
     // ---- work fetch (warp-uniform): static first chunk, then chunks from the cursor, reserved one ahead
@@ -522,8 +530,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, b4 = o4, tri_n = o4;   // cont: tri_n carries the stale `o` instead
     float4 o4_n = o4, d4_n = o4, b4_n = o4, tri_n_n = o4;
     uint32_t cur_slot = 0, sp_slot = 0;
-    uint32_t pend_base = 0;    // lanes 0..2: value returned by last trip's atomic for class = lane
-    unsigned prev_any = 0;     // warp-uniform: a staged trip is waiting to be flushed
+    // output segments (warp-uniform): front / back class of the other path queue, shadow queue
+    uint32_t f_base = 0, f_used = SHADE_SEG, b_base = 0, b_used = SHADE_SEG, s_base = 0, s_used = SHADE_SEG;
+    bool f_next = false, b_next = false, s_next = false;
+    uint32_t nb = 0;           // lane = class: base of the segment reserved ahead
 
     for (;;) {
         // (a) lanes without a path take their prefetched entry
@@ -533,10 +543,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
             if (!sp_nrm) {
                 const uint32_t idn = __float_as_uint(h2_n.y);
                 tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
+                if (idn != PC_NONE && idn != HIT_HOLE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
             }
             tri_n = tri_n_n;
-            cur_valid = true;
+            cur_valid = __float_as_uint(h2.y) != HIT_HOLE;
             cont = false;
             sp_valid = false;
         }
@@ -747,35 +757,31 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
             ext_push = false;
         }
         if (keep) ext_push = false;
-        // ---- compaction, one trip late (see ShadeStage)
+        // ---- queue pushes: slots from the warp's segments (see seg_alloc), written straight away
         const unsigned mf = __ballot_sync(0xffffffffu, ext_push && ext_front);
         const unsigned mb = __ballot_sync(0xffffffffu, ext_push && !ext_front);
         const unsigned ms = __ballot_sync(0xffffffffu, sh_push);
         const unsigned mp = __ballot_sync(0xffffffffu, pr_push);
-        if (prev_any) {
-            const uint32_t bf = __shfl_sync(0xffffffffu, pend_base, 0);
-            const uint32_t bb = __shfl_sync(0xffffffffu, pend_base, 1);
-            const uint32_t bs = __shfl_sync(0xffffffffu, pend_base, 2);
-            shade_flush(st, N, SQ, bf, bb, bs);
-        }
-        prev_any = mf | mb | ms | mp;
-        if (prev_any) {
-            {   // ONE atomic instruction for the three classes (lane = class; the back class grows downward: add -n).
-                // Three separate atomics into the same destination register would serialise on its scoreboard.
-                const uint32_t n = lane == 0 ? (uint32_t)__popc(mf) : (lane == 1 ? 0u - (uint32_t)__popc(mb) : (uint32_t)(__popc(ms) + __popc(mp)));
-                if (lane < 3 && n != 0u) pend_base = atomicAdd(lane == 0 ? ctr_front : (lane == 1 ? ctr_back : ctr_sh), n);
-            }
-            const uint32_t r_ext = ext_front ? __popc(mf & below) : __popc(mb & below);
-            const uint32_t r_sh = __popc(ms & below), r_pr = __popc(ms) + __popc(mp & below);
-            st.meta[threadIdx.x] = (ext_push ? 1u : 0u) | (ext_front ? 2u : 0u) | (sh_push ? 4u : 0u) | (pr_push ? 8u : 0u) |
-                                   (r_ext << 8) | (r_sh << 14) | (r_pr << 20);
+        if (mf | mb) {
+            uint32_t slot = 0;
+            if (mf) { const uint32_t v = seg_alloc<1>(f_base, f_used, f_next, nb, 0u, ctr_front, mf, lane); if (ext_front) slot = v; }
+            if (mb) { const uint32_t v = seg_alloc<-1>(b_base, b_used, b_next, nb, 1u, ctr_back, mb, lane); if (!ext_front) slot = v; }
             if (ext_push) {
-                st.eo[threadIdx.x] = eo; st.ed[threadIdx.x] = ed; st.eb[threadIdx.x] = eb; st.eh[threadIdx.x] = eh;
-                if (__float_as_uint(eo.w) & PC_STALE_O) st.ev[threadIdx.x] = ev;
+                N.o[slot] = eo;
+                N.d[slot] = ed;
+                N.beta[slot] = eb;
+                N.hit[slot] = eh;
+                if (__float_as_uint(eo.w) & PC_STALE_O) N.ov[slot] = ev;
+                ++n_queued;
             }
-            if (sh_push || pr_push) st.so[threadIdx.x] = so;
-            if (sh_push) { st.sd[threadIdx.x] = sd; st.sc[threadIdx.x] = sc; }
-            if (pr_push) { st.pd[threadIdx.x] = pd; st.pc[threadIdx.x] = pc; }
+        }
+        if (ms) {
+            const uint32_t slot = seg_alloc<1>(s_base, s_used, s_next, nb, 2u, ctr_sh, ms, lane);
+            if (sh_push) { SQ.o[slot] = so; SQ.d[slot] = sd; SQ.c[slot] = sc; }
+        }
+        if (mp) {
+            const uint32_t slot = seg_alloc<1>(s_base, s_used, s_next, nb, 2u, ctr_sh, mp, lane);
+            if (pr_push) { SQ.o[slot] = so; SQ.d[slot] = pd; SQ.c[slot] = pc; }
         }
         // ---- next vertex of the same path, straight from registers
         cur_valid = keep;
@@ -788,16 +794,22 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
         if (sp_valid && !sp_nrm) {
             const uint32_t idn = __float_as_uint(h2_n.y);
             tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
+            if (idn == HIT_HOLE) sp_valid = false;   // unfilled slot of the producer: ask for another entry next trip
+            else if (idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
             sp_nrm = true;
         }
     }
-    // epilogue: flush the last staged trip
-    if (prev_any) {
-        const uint32_t bf = __shfl_sync(0xffffffffu, pend_base, 0);
-        const uint32_t bb = __shfl_sync(0xffffffffu, pend_base, 1);
-        const uint32_t bs = __shfl_sync(0xffffffffu, pend_base, 2);
-        shade_flush(st, N, SQ, bf, bb, bs);
+    // epilogue: mark the slots this warp reserved but did not fill
+    {
+        const float2 hole = make_float2(0.f, __uint_as_float(HIT_HOLE));
+        const float4 hole4 = make_float4(0.f, 0.f, 0.f, __uint_as_float(TLIM_HOLE));
+        for (uint32_t k = f_used + lane; k < SHADE_SEG; k += 32) N.hit[seg_slot<1>(f_base, k)] = hole;
+        for (uint32_t k = b_used + lane; k < SHADE_SEG; k += 32) N.hit[seg_slot<-1>(b_base, k)] = hole;
+        for (uint32_t k = s_used + lane; k < SHADE_SEG; k += 32) SQ.d[seg_slot<1>(s_base, k)] = hole4;
+        const uint32_t nf = __shfl_sync(0xffffffffu, nb, 0), nbk = __shfl_sync(0xffffffffu, nb, 1) - 1u, ns = __shfl_sync(0xffffffffu, nb, 2);
+        if (f_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) N.hit[seg_slot<1>(nf, k)] = hole;
+        if (b_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) N.hit[seg_slot<-1>(nbk, k)] = hole;
+        if (s_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) SQ.d[seg_slot<1>(ns, k)] = hole4;
     }
     // counters
     for (int off = 16; off; off >>= 1) {
@@ -805,8 +817,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
         n_ext_bvh += __shfl_down_sync(0xffffffffu, n_ext_bvh, off);
         n_sh += __shfl_down_sync(0xffffffffu, n_sh, off);
         n_sh_bvh += __shfl_down_sync(0xffffffffu, n_sh_bvh, off);
+        n_queued += __shfl_down_sync(0xffffffffu, n_queued, off);
     }
     if (lane == 0) {
+        if (n_queued) atomicAdd(&C->live[1 - c], n_queued);
+        if (n_sh_bvh) atomicAdd(&C->sh_live[1 - c], n_sh_bvh);
         if (n_ext) atomicAdd(&C->rays_extension, (unsigned long long)n_ext);
         if (n_ext_bvh) atomicAdd(&C->rays_bvh, (unsigned long long)n_ext_bvh);
         if (n_sh) atomicAdd(&C->rays_shadow, (unsigned long long)n_sh);
