@@ -23,6 +23,8 @@ constexpr uint32_t PC_STALE_O = 0x20000000u;
 constexpr uint32_t PC_ID_MASK = 0x1fffffffu;
 constexpr uint32_t PC_NONE = 0x1fffffffu;
 constexpr uint32_t TRI_BASE = 256u;  // == MAX_OBJECTS
+constexpr int TRI_STRIDE = 4;        // float4 per LBVH triangle record: 48 B of data padded to 64 B so that the first 32 B
+                                     // can be fetched by one 256-bit load
 
 struct DevPrim {      // 48 B, mirrors FlatPrim
     float4 a;         // plane: n.xyz, dot(pos,n)   sphere: c.xyz, r
@@ -59,7 +61,7 @@ struct DevScene {          // passed to kernels by value
     const DevPrim* prims;
     const DevMaterial* mats;
     const float4* nodes;   // 4 x float4 per node
-    const float4* tris;    // 3 x float4 per triangle, leaf order
+    const float4* tris;    // TRI_STRIDE x float4 per triangle (3 used), leaf order
     const float4* tri_nrm; // unit geometric normal | object id per triangle, leaf order (shading)
     const float* light_cdf;
     const float4* tri_orig; // 3 x float4 per triangle in GLOBAL order: a, b, c (mesh-light sampling)
@@ -67,6 +69,15 @@ struct DevScene {          // passed to kernels by value
     int32_t n_planes;      // prims[0, n_planes) are planes, prims[n_planes, n_prims) spheres
     float3 bvh_min, bvh_max;
 };
+
+// 256-bit read-only load (LDG.E.256, sm_100+; p must be 32-byte aligned).  k_traverse is bound by the L1 data pipe,
+// which spends one wavefront per 128-byte line an instruction touches — a divergent lane costs the same wavefront
+// for 16 or for 32 bytes, so fetching a 64-byte node with two loads instead of four halves that cost.
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
 
 // ---------------------------------------------------------------- float3 helpers
 __host__ __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }

@@ -70,6 +70,7 @@ struct RenderContext {
     unsigned long long* d_state = nullptr;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one iteration (4 kernels) for cur = 0 / 1 ...
     std::vector<unsigned char> graph_args;                 // ... captured for exactly these kernel arguments
+    int trav_minb = 4;   // CTAs per SM the launched k_traverse instantiation was compiled for (RTB_TRAV_MINB = 4 | 5 | 6)
     int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0, grid_shade = 0;
 
     ~RenderContext() {
@@ -330,7 +331,10 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         CU_TRY(cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CU_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         int b = 0;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false>, WF_THREADS, smem_stack));
+        if (const char* e = getenv("RTB_TRAV_MINB")) c->trav_minb = atoi(e) == 5 ? 5 : (atoi(e) == 6 ? 6 : 4);
+        if (c->trav_minb == 5) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 5>, WF_THREADS, smem_stack));
+        else if (c->trav_minb == 6) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 6>, WF_THREADS, smem_stack));
+        else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false>, WF_THREADS, smem_stack));
         c->grid_ext = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true>, WF_THREADS, smem_stack));
         c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
@@ -338,6 +342,9 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         c->grid_shade = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate, WF_THREADS, smem_tab));
         c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
+        // experiment knobs: CTAs per SM of the two persistent kernels (two concurrent renders can then share every SM)
+        if (const char* e = getenv("RTB_TRAV_CTAS")) c->grid_ext = c->grid_ext_count = std::max(1, atoi(e)) * prop.multiProcessorCount;
+        if (const char* e = getenv("RTB_SHADE_CTAS")) c->grid_shade = std::max(1, atoi(e)) * prop.multiProcessorCount;
     }
     // every k_shade warp may leave up to two unfilled SHADE_SEG segments per queue class behind in each iteration
     const uint32_t seg_room = (uint32_t)c->grid_shade * (SHADE_THREADS / 32) * 2u * SHADE_SEG;
@@ -496,7 +503,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 if (ge != cudaSuccess) break;
                 k_prepare<<<1, 1, 0, c->stream>>>(ag, k);
                 k_generate<<<c->grid_gen, WF_THREADS, smem_tab, c->stream>>>(ag, k);
-                k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
+                if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
+                else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
+                else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 if (fast_shade) k_shade<true><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
             else k_shade<false><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
                 ge = cudaStreamEndCapture(c->stream, &g);
@@ -549,6 +558,8 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         cudaEvent_t* ev = &c->ext_ev[3 * ext_iters];
         CU_TRY(cudaEventRecord(ev[0], c->stream));
         if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+        else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+        else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         CU_TRY(cudaEventRecord(ev[1], c->stream));
         if (fast_shade) k_shade<true><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);

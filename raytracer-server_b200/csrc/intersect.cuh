@@ -219,7 +219,9 @@ __device__ __forceinline__ void trav_pop(Trav& T, const int* sstack, int stride,
 template <bool COUNT>
 __device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, int* sstack, int stride, int* lstack, uint32_t* work) {
     const float4* np = S.nodes + (size_t)T.node * 4;
-    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+    float4 n0, n1, n2, n3;
+    ldg256(np, n0, n1);
+    ldg256(np + 2, n2, n3);
     if (COUNT) work[0]++;
     // n0 = c0 (lo.x hi.x lo.y hi.y)  n1 = c1 (lo.x hi.x lo.y hi.y)  n2 = (c0.lo.z c0.hi.z c1.lo.z c1.hi.z)
     float a0 = n0.x * T.idx - T.oox, a1 = n0.y * T.idx - T.oox, a2 = n0.z * T.idy - T.ooy, a3 = n0.w * T.idy - T.ooy;
@@ -265,8 +267,10 @@ __device__ __forceinline__ bool trav_leaf(const DevScene& S, Trav& T, uint32_t* 
     const uint32_t first = v >> 3, cnt = (v & 7u) + 1u;
     const uint32_t origin_id = T.origin & PC_ID_MASK;
     for (uint32_t s = first; s < first + cnt; ++s) {
-        const float4* tp = S.tris + (size_t)s * 3;
-        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+        const float4* tp = S.tris + (size_t)s * TRI_STRIDE;
+        float4 t0, t1;
+        ldg256(tp, t0, t1);
+        const float4 t2 = __ldg(tp + 2);
         if (COUNT) work[1]++;
         float3 e1 = f3(t1), e2 = f3(t2);
         float3 pvec = cross(T.d, e2);

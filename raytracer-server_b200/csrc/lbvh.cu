@@ -20,6 +20,7 @@
 //      compact the surviving nodes                                   [cub::DeviceScan]
 //   6. emit 64-byte nodes {child0 box, child1 box, child refs} and triangles in leaf order
 #include "lbvh.hpp"
+#include "device_types.cuh"
 
 #include <cub/cub.cuh>
 
@@ -226,7 +227,8 @@ __global__ void k_pack_tris(int n, const uint32_t* __restrict__ sorted, const fl
     // N = (c-a) x (b-a)  (Triangle::normal, src/geometry.rs:606-608)
     float nx = e2.y * e1.z - e2.z * e1.y, ny = e2.z * e1.x - e2.x * e1.z, nz = e2.x * e1.y - e2.y * e1.x;
     float len = sqrtf(nx * nx + ny * ny + nz * nz);
-    float4* o = out + (size_t)s * 3;
+    float4* o = out + (size_t)s * rtb::TRI_STRIDE;
+    o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
     o[0] = make_float4(a.x, a.y, a.z, len > 0.f ? 1.0f / len : 0.f);
     o[1] = make_float4(e1.x, e1.y, e1.z, __int_as_float((int)g));
     o[2] = make_float4(e2.x, e2.y, e2.z, __int_as_float(tri_obj[g]));
@@ -430,7 +432,7 @@ static bool build_sah_host(const float* d_verts, const int32_t* d_tri_obj, int n
     uint32_t* d_ord=nullptr;
     LBVH_CHECK(cudaMalloc((void**)&d_ord, (size_t)n*4));
     LBVH_CHECK(cudaMemcpyAsync(d_ord, ord.data(), (size_t)n*4, cudaMemcpyHostToDevice, stream));
-    LBVH_CHECK(cudaMalloc((void**)&out.d_tris, (size_t)n*3*sizeof(float4)));
+    LBVH_CHECK(cudaMalloc((void**)&out.d_tris, (size_t)n*rtb::TRI_STRIDE*sizeof(float4)));
     LBVH_CHECK(cudaMalloc((void**)&out.d_tri_nrm, (size_t)n*sizeof(float4)));
     k_pack_tris<<<(n+255)/256, 256, 0, stream>>>(n, d_ord, d_verts, d_tri_obj, out.d_tris, out.d_tri_nrm);
     out.n_nodes=(int)B.nodes.size()/4;
@@ -475,7 +477,7 @@ bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStrea
     LBVH_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, stream));
 
     float4* d_tris = nullptr;
-    LBVH_CHECK(cudaMalloc((void**)&d_tris, (size_t)n * 3 * sizeof(float4)));
+    LBVH_CHECK(cudaMalloc((void**)&d_tris, (size_t)n * rtb::TRI_STRIDE * sizeof(float4)));
     out.d_tris = d_tris;
     LBVH_CHECK(cudaMalloc((void**)&out.d_tri_nrm, (size_t)n * sizeof(float4)));
     const char* mode_env = getenv("RTB_BVH");

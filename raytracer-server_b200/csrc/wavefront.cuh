@@ -315,8 +315,8 @@ __device__ __forceinline__ bool warp_reserve(uint32_t* cursor, uint32_t count, u
 //   * any hit for the NEE candidates in shadow queue c                  (mutually_visible; accumulates if unoccluded)
 //   * closest hit for dead-MIS probes against a mesh light              (hit.id == light_source test)
 // Lanes refill individually from one work cursor, so the two ray kinds share warps and the tail is paid once.
-template <bool COUNT>
-__global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c) {
+template <bool COUNT, int MINB = 4>
+__global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* sstack = reinterpret_cast<int*>(smem_raw) + threadIdx.x;
     const int stride = blockDim.x;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse(RenderArgs a, int c)
                 if (T.best_id != PC_NONE) Q.hit[slot] = make_float2(T.tlimit, __uint_as_float(T.best_id));
             } else {
                 bool add;
-                if (kind == 2) add = T.best_id != PC_NONE && __float_as_int(__ldg(a.S.tris + (size_t)(T.best_id - TRI_BASE) * 3 + 2).w) == light_obj;
+                if (kind == 2) add = T.best_id != PC_NONE && __float_as_int(__ldg(a.S.tris + (size_t)(T.best_id - TRI_BASE) * TRI_STRIDE + 2).w) == light_obj;
                 else add = !occluded;
                 if (add) {
                     const float4 c4 = SQ.c[slot];
@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace_rays(DevScene S, long long
         } else if (id < TRI_BASE) {
             obj[i] = sh.prims[id].obj; tri[i] = -1; tout[i] = t;
         } else {
-            const float4* tp = S.tris + (size_t)(id - TRI_BASE) * 3;
+            const float4* tp = S.tris + (size_t)(id - TRI_BASE) * TRI_STRIDE;
             int ob = __float_as_int(__ldg(tp + 2).w);
             obj[i] = ob;
             tri[i] = __float_as_int(__ldg(tp + 1).w) - sh.mats[ob].first_tri;
