@@ -60,7 +60,9 @@ struct DevScene {          // passed to kernels by value
     const DevSceneHeader* hdr;
     const DevPrim* prims;
     const DevMaterial* mats;
-    const float4* nodes;   // 4 x float4 per node
+    const float4* nodes;   // 4 x float4 per node (fp32 boxes: build output, kept for inspection)
+    const uint4* qnodes;   // 2 x uint4 per node: the 16-bit quantised table the traversal reads (lbvh.cu)
+    float3 qmin, qstep;    // quantisation grid of qnodes
     const float4* tris;    // TRI_STRIDE x float4 per triangle (3 used), leaf order
     const float4* tri_nrm; // unit geometric normal | object id per triangle, leaf order (shading)
     const float* light_cdf;
@@ -73,6 +75,11 @@ struct DevScene {          // passed to kernels by value
 // 256-bit read-only load (LDG.E.256, sm_100+; p must be 32-byte aligned).  k_traverse is bound by the L1 data pipe,
 // which spends one wavefront per 128-byte line an instruction touches — a divergent lane costs the same wavefront
 // for 16 or for 32 bytes, so fetching a 64-byte node with two loads instead of four halves that cost.
+__device__ __forceinline__ void ldg256u(const uint4* p, uint4& a, uint4& b) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+        : "l"(p));
+}
 __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)

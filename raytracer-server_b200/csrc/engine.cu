@@ -222,6 +222,9 @@ int build_device_scene(rtb_scene* sc) {
     V.prims = reinterpret_cast<const DevPrim*>(sc->d_stage + sc->off_prims);
     V.mats = reinterpret_cast<const DevMaterial*>(sc->d_stage + sc->off_mats);
     V.nodes = sc->bvh.d_nodes;
+    V.qnodes = sc->bvh.d_qnodes;
+    V.qmin = make_float3(sc->bvh.qmin[0], sc->bvh.qmin[1], sc->bvh.qmin[2]);
+    V.qstep = make_float3(sc->bvh.qstep[0], sc->bvh.qstep[1], sc->bvh.qstep[2]);
     V.tris = sc->bvh.d_tris;
     V.tri_nrm = sc->bvh.d_tri_nrm;
     V.light_cdf = reinterpret_cast<const float*>(sc->d_stage + sc->off_cdf);

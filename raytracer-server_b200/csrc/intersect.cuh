@@ -182,7 +182,8 @@ __device__ __forceinline__ void analytic_pair(const SharedScene& sh, int n_plane
 // thread) and spills to a local array beyond that.
 struct Trav {
     float3 o, d;
-    float idx, idy, idz, oox, ooy, ooz;
+    // slab distance of the quantised plane k of axis x: fma(8388608 + k, sx, bx) = (qmin.x + k * qstep.x - o.x) / d.x
+    float sx, sy, sz, bx, by, bz;
     uint32_t origin;     // pcode of the primitive the ray starts on
     float tlimit;        // only hits with t < tlimit count (closest: current best; any-hit: |y-x| - margin)
     uint32_t best_id;    // closest mode: id of the nearest triangle found so far (PC_NONE = none)
@@ -190,16 +191,20 @@ struct Trav {
     int sp;
 };
 
-__device__ __forceinline__ void trav_begin(Trav& T, float3 o, float3 d, uint32_t origin, float tlimit, int root) {
+__device__ __forceinline__ void trav_begin(const DevScene& S, Trav& T, float3 o, float3 d, uint32_t origin, float tlimit, int root) {
     T.o = o;
     T.d = d;
-    // MUFU.RCP reciprocals (1-2 ulp); the node boxes are padded by 1e-6 relative at build time to stay conservative
-    T.idx = __fdividef(1.0f, fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
-    T.idy = __fdividef(1.0f, fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
-    T.idz = __fdividef(1.0f, fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
-    T.oox = o.x * T.idx;
-    T.ooy = o.y * T.idy;
-    T.ooz = o.z * T.idz;
+    // MUFU.RCP reciprocals (1-2 ulp).  The node boxes are quantised with QPAD = 2 grid steps of slack (lbvh.cu): the
+    // constant term below carries 8388608 * s, so its rounding and the FMA's each move a plane by at most half a step.
+    const float idx = __fdividef(1.0f, fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    const float idy = __fdividef(1.0f, fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    const float idz = __fdividef(1.0f, fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    T.sx = S.qstep.x * idx;
+    T.sy = S.qstep.y * idy;
+    T.sz = S.qstep.z * idz;
+    T.bx = fmaf(-8388608.0f, T.sx, (S.qmin.x - o.x) * idx);
+    T.by = fmaf(-8388608.0f, T.sy, (S.qmin.y - o.y) * idy);
+    T.bz = fmaf(-8388608.0f, T.sz, (S.qmin.z - o.z) * idz);
     T.origin = origin;
     T.tlimit = tlimit;
     T.best_id = PC_NONE;
@@ -218,22 +223,24 @@ __device__ __forceinline__ void trav_pop(Trav& T, const int* sstack, int stride,
 // one inner node: test both child boxes, descend into the nearer hit child, push the other
 template <bool COUNT>
 __device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, int* sstack, int stride, int* lstack, uint32_t* work) {
-    const float4* np = S.nodes + (size_t)T.node * 4;
-    float4 n0, n1, n2, n3;
-    ldg256(np, n0, n1);
-    ldg256(np + 2, n2, n3);
+    uint4 q0, q1;
+    ldg256u(S.qnodes + (size_t)T.node * 2, q0, q1);
     if (COUNT) work[0]++;
-    // n0 = c0 (lo.x hi.x lo.y hi.y)  n1 = c1 (lo.x hi.x lo.y hi.y)  n2 = (c0.lo.z c0.hi.z c1.lo.z c1.hi.z)
-    float a0 = n0.x * T.idx - T.oox, a1 = n0.y * T.idx - T.oox, a2 = n0.z * T.idy - T.ooy, a3 = n0.w * T.idy - T.ooy;
-    float a4 = n2.x * T.idz - T.ooz, a5 = n2.y * T.idz - T.ooz;
-    float b0 = n1.x * T.idx - T.oox, b1 = n1.y * T.idx - T.oox, b2 = n1.z * T.idy - T.ooy, b3 = n1.w * T.idy - T.ooy;
-    float b4 = n2.z * T.idz - T.ooz, b5 = n2.w * T.idz - T.ooz;
+    // 16-bit plane index k -> the float 8388608 + k with one PRMT (bytes k.lo, k.hi, 0x00, 0x4B), then one FMA per plane
+    auto lo16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)); };
+    auto hi16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)); };
+    float a0 = fmaf(lo16(q0.x), T.sx, T.bx), a1 = fmaf(hi16(q0.x), T.sx, T.bx);
+    float a2 = fmaf(lo16(q0.y), T.sy, T.by), a3 = fmaf(hi16(q0.y), T.sy, T.by);
+    float a4 = fmaf(lo16(q0.z), T.sz, T.bz), a5 = fmaf(hi16(q0.z), T.sz, T.bz);
+    float b0 = fmaf(lo16(q0.w), T.sx, T.bx), b1 = fmaf(hi16(q0.w), T.sx, T.bx);
+    float b2 = fmaf(lo16(q1.x), T.sy, T.by), b3 = fmaf(hi16(q1.x), T.sy, T.by);
+    float b4 = fmaf(lo16(q1.y), T.sz, T.bz), b5 = fmaf(hi16(q1.y), T.sz, T.bz);
     float tmin0 = fmaxf(fmaxf(fminf(a0, a1), fminf(a2, a3)), fmaxf(fminf(a4, a5), 0.0f));
     float tmax0 = fminf(fminf(fmaxf(a0, a1), fmaxf(a2, a3)), fminf(fmaxf(a4, a5), T.tlimit));
     float tmin1 = fmaxf(fmaxf(fminf(b0, b1), fminf(b2, b3)), fmaxf(fminf(b4, b5), 0.0f));
     float tmax1 = fminf(fminf(fmaxf(b0, b1), fmaxf(b2, b3)), fminf(fmaxf(b4, b5), T.tlimit));
     const bool h0 = tmin0 <= tmax0, h1 = tmin1 <= tmax1;
-    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    const int c0 = (int)q1.z, c1 = (int)q1.w;
     // Select-based step (no three-way branch): the lane always peeks at its stack top; "both hit" pushes the
     // farther child, "none hit" pops.  Only the (rare) spill beyond STACK_SMEM levels branches.
     const bool both = h0 && h1, none = !h0 && !h1;
@@ -308,7 +315,7 @@ __device__ __forceinline__ bool bvh_traverse(const DevScene& S, const SharedScen
     const int stride = blockDim.x;
     int lstack[STACK_LOCAL];
     Trav T;
-    trav_begin(T, o, d, origin, ANY_HIT ? dist - SHADOW_MARGIN : best_t, S.root);
+    trav_begin(S, T, o, d, origin, ANY_HIT ? dist - SHADOW_MARGIN : best_t, S.root);
     while (T.node != NODE_SENTINEL) {
         while (T.node >= 0) trav_inner<COUNT>(S, T, sstack, stride, lstack, work);
         if (T.node != NODE_SENTINEL) {

@@ -10,6 +10,9 @@ namespace rtb {
 
 struct LbvhResult {
     float4* d_nodes = nullptr;  // 4 x float4 per node: c0 (lo.x hi.x lo.y hi.y), c1 (same), (c0.lo.z c0.hi.z c1.lo.z c1.hi.z), refs
+    uint4* d_qnodes = nullptr;  // the node table the traversal reads: 2 x uint4 (32 B) per node, child boxes quantised to 16 bits
+                                // on the grid qmin + k * qstep (conservative), see quantise_nodes in lbvh.cu
+    float qmin[3] = {0, 0, 0}, qstep[3] = {1, 1, 1};
     float4* d_tris = nullptr;   // TRI_STRIDE (4) x float4 per triangle in leaf order: (a | 1/|N|), (b-a | global tri id), (c-a | object id), pad
     float4* d_tri_nrm = nullptr; // 1 x float4 per triangle in leaf order: Triangle::normal (unit) | object id
     int root = 0;               // encoded reference: >= 0 node index, < 0 leaf ~((first << 3) | (count - 1))

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
                             slot = my;
                             kind = 0;
                             const float4 o4 = Q.o[my], d4 = Q.d[my];
-                            trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), h2.x, a.S.root);
+                            trav_begin(a.S, T, f3(o4), f3(d4), __float_as_uint(o4.w), h2.x, a.S.root);
                         }
                     } else {
                         const float4 d4 = SQ.d[my - n_ext];
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
                             const float4 o4 = SQ.o[slot];
                             kind = (__float_as_uint(SQ.c[slot].w) & SHADOW_PROBE) ? 2 : 1;
                             occluded = false;
-                            trav_begin(T, f3(o4), f3(d4), __float_as_uint(o4.w), d4.w, a.S.root);
+                            trav_begin(a.S, T, f3(o4), f3(d4), __float_as_uint(o4.w), d4.w, a.S.root);
                         }
                     }
                 }
