@@ -184,6 +184,8 @@ struct Trav {
     float3 o, d;
     // slab distance of the quantised plane k of axis x: fma(8388608 + k, sx, bx) = (qmin.x + k * qstep.x - o.x) / d.x
     float sx, sy, sz, bx, by, bz;
+    // PRMT selectors picking the NEAR / FAR plane of an axis out of a (lo | hi << 16) word: lo is nearer iff d > 0
+    uint32_t nsx, nsy, nsz, fsx, fsy, fsz;
     uint32_t origin;     // pcode of the primitive the ray starts on
     float tlimit;        // only hits with t < tlimit count (closest: current best; any-hit: |y-x| - margin)
     uint32_t best_id;    // closest mode: id of the nearest triangle found so far (PC_NONE = none)
@@ -205,6 +207,12 @@ __device__ __forceinline__ void trav_begin(const DevScene& S, Trav& T, float3 o,
     T.bx = fmaf(-8388608.0f, T.sx, (S.qmin.x - o.x) * idx);
     T.by = fmaf(-8388608.0f, T.sy, (S.qmin.y - o.y) * idy);
     T.bz = fmaf(-8388608.0f, T.sz, (S.qmin.z - o.z) * idz);
+    T.nsx = T.sx >= 0.f ? 0x7410u : 0x7432u;
+    T.nsy = T.sy >= 0.f ? 0x7410u : 0x7432u;
+    T.nsz = T.sz >= 0.f ? 0x7410u : 0x7432u;
+    T.fsx = T.nsx ^ 0x0022u;
+    T.fsy = T.nsy ^ 0x0022u;
+    T.fsz = T.nsz ^ 0x0022u;
     T.origin = origin;
     T.tlimit = tlimit;
     T.best_id = PC_NONE;
@@ -212,33 +220,42 @@ __device__ __forceinline__ void trav_begin(const DevScene& S, Trav& T, float3 o,
     T.sp = 0;
 }
 
-__device__ __forceinline__ void trav_pop(Trav& T, const int* sstack, int stride, const int* lstack) {
+// The shared-memory half of the stack is addressed with 32-bit shared-window addresses (ld/st.shared): `sbase` is
+// the address of this thread's level-0 slot, `sstride` the byte distance between levels (blockDim.x * 4).
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_i32(uint32_t addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v)); }
+
+__device__ __forceinline__ void trav_pop(Trav& T, uint32_t sbase, uint32_t sstride, const int* lstack) {
     if (T.sp == 0) T.node = NODE_SENTINEL;
     else {
         --T.sp;
-        T.node = T.sp < STACK_SMEM ? sstack[T.sp * stride] : lstack[T.sp - STACK_SMEM];
+        T.node = T.sp < STACK_SMEM ? lds_i32(sbase + (uint32_t)T.sp * sstride) : lstack[T.sp - STACK_SMEM];
     }
 }
 
 // one inner node: test both child boxes, descend into the nearer hit child, push the other
 template <bool COUNT>
-__device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, int* sstack, int stride, int* lstack, uint32_t* work) {
+__device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, uint32_t sbase, uint32_t sstride, int* lstack, uint32_t* work) {
     uint4 q0, q1;
     ldg256u(S.qnodes + (size_t)T.node * 2, q0, q1);
     if (COUNT) work[0]++;
-    // 16-bit plane index k -> the float 8388608 + k with one PRMT (bytes k.lo, k.hi, 0x00, 0x4B), then one FMA per plane
-    auto lo16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)); };
-    auto hi16 = [](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)); };
-    float a0 = fmaf(lo16(q0.x), T.sx, T.bx), a1 = fmaf(hi16(q0.x), T.sx, T.bx);
-    float a2 = fmaf(lo16(q0.y), T.sy, T.by), a3 = fmaf(hi16(q0.y), T.sy, T.by);
-    float a4 = fmaf(lo16(q0.z), T.sz, T.bz), a5 = fmaf(hi16(q0.z), T.sz, T.bz);
-    float b0 = fmaf(lo16(q0.w), T.sx, T.bx), b1 = fmaf(hi16(q0.w), T.sx, T.bx);
-    float b2 = fmaf(lo16(q1.x), T.sy, T.by), b3 = fmaf(hi16(q1.x), T.sy, T.by);
-    float b4 = fmaf(lo16(q1.y), T.sz, T.bz), b5 = fmaf(hi16(q1.y), T.sz, T.bz);
-    float tmin0 = fmaxf(fmaxf(fminf(a0, a1), fminf(a2, a3)), fmaxf(fminf(a4, a5), 0.0f));
-    float tmax0 = fminf(fminf(fmaxf(a0, a1), fmaxf(a2, a3)), fminf(fmaxf(a4, a5), T.tlimit));
-    float tmin1 = fmaxf(fmaxf(fminf(b0, b1), fminf(b2, b3)), fmaxf(fminf(b4, b5), 0.0f));
-    float tmax1 = fminf(fminf(fmaxf(b0, b1), fmaxf(b2, b3)), fminf(fmaxf(b4, b5), T.tlimit));
+    // 16-bit plane index k -> the float 8388608 + k with one PRMT (bytes k.lo, k.hi, 0x00, 0x4B), then one FMA per plane.
+    // The selector already picks the plane the ray enters / leaves through (sign of d), so no per-axis min / max.
+    auto pl = [](uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); };
+    const float n0x = fmaf(pl(q0.x, T.nsx), T.sx, T.bx), f0x = fmaf(pl(q0.x, T.fsx), T.sx, T.bx);
+    const float n0y = fmaf(pl(q0.y, T.nsy), T.sy, T.by), f0y = fmaf(pl(q0.y, T.fsy), T.sy, T.by);
+    const float n0z = fmaf(pl(q0.z, T.nsz), T.sz, T.bz), f0z = fmaf(pl(q0.z, T.fsz), T.sz, T.bz);
+    const float n1x = fmaf(pl(q0.w, T.nsx), T.sx, T.bx), f1x = fmaf(pl(q0.w, T.fsx), T.sx, T.bx);
+    const float n1y = fmaf(pl(q1.x, T.nsy), T.sy, T.by), f1y = fmaf(pl(q1.x, T.fsy), T.sy, T.by);
+    const float n1z = fmaf(pl(q1.y, T.nsz), T.sz, T.bz), f1z = fmaf(pl(q1.y, T.fsz), T.sz, T.bz);
+    const float tmin0 = fmaxf(fmaxf(n0x, n0y), fmaxf(n0z, 0.0f));
+    const float tmax0 = fminf(fminf(f0x, f0y), fminf(f0z, T.tlimit));
+    const float tmin1 = fmaxf(fmaxf(n1x, n1y), fmaxf(n1z, 0.0f));
+    const float tmax1 = fminf(fminf(f1x, f1y), fminf(f1z, T.tlimit));
     const bool h0 = tmin0 <= tmax0, h1 = tmin1 <= tmax1;
     const int c0 = (int)q1.z, c1 = (int)q1.w;
     // Select-based step (no three-way branch): the lane always peeks at its stack top; "both hit" pushes the
@@ -248,9 +265,9 @@ __device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, int* ssta
     const int nearc = both ? (swap ? c1 : c0) : (h0 ? c0 : c1);
     const int farc = swap ? c0 : c1;
     if (T.sp < STACK_SMEM) {
-        int* slot = sstack + max(T.sp - (none ? 1 : 0), 0) * stride;   // push target, or the top entry when popping
-        const int top = *slot;
-        if (both) *slot = farc;
+        const uint32_t slot = sbase + (uint32_t)max(T.sp - (none ? 1 : 0), 0) * sstride;   // push target, or the top entry when popping
+        const int top = lds_i32(slot);
+        if (both) sts_i32(slot, farc);
         T.node = none ? (T.sp == 0 ? NODE_SENTINEL : top) : nearc;
         T.sp += both ? 1 : (none && T.sp > 0 ? -1 : 0);
     } else {  // spill levels (local memory); T.sp == STACK_SMEM pops from shared memory via trav_pop
@@ -259,7 +276,7 @@ __device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, int* ssta
             ++T.sp;
             T.node = nearc;
         } else if (none) {
-            trav_pop(T, sstack, stride, lstack);
+            trav_pop(T, sbase, sstride, lstack);
         } else {
             T.node = nearc;
         }
@@ -311,16 +328,15 @@ __device__ __forceinline__ bool bvh_traverse(const DevScene& S, const SharedScen
                                              float& best_t, uint32_t& best_id, float dist, uint32_t* work) {
     // ANY_HIT: returns true as soon as some triangle has t + SHADOW_MARGIN < dist.
     // else   : updates (best_t, best_id) with the nearest triangle hit below best_t.
-    int* sstack = sh.stack + threadIdx.x;
-    const int stride = blockDim.x;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sh.stack + threadIdx.x), sstride = blockDim.x * 4u;
     int lstack[STACK_LOCAL];
     Trav T;
     trav_begin(S, T, o, d, origin, ANY_HIT ? dist - SHADOW_MARGIN : best_t, S.root);
     while (T.node != NODE_SENTINEL) {
-        while (T.node >= 0) trav_inner<COUNT>(S, T, sstack, stride, lstack, work);
+        while (T.node >= 0) trav_inner<COUNT>(S, T, sbase, sstride, lstack, work);
         if (T.node != NODE_SENTINEL) {
             if (trav_leaf<ANY_HIT, COUNT>(S, T, work)) return true;
-            trav_pop(T, sstack, stride, lstack);
+            trav_pop(T, sbase, sstride, lstack);
         }
     }
     if (!ANY_HIT && T.best_id != PC_NONE) {

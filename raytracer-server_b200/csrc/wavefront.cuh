@@ -318,8 +318,7 @@ __device__ __forceinline__ bool warp_reserve(uint32_t* cursor, uint32_t count, u
 template <bool COUNT, int MINB = 4>
 __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int* sstack = reinterpret_cast<int*>(smem_raw) + threadIdx.x;
-    const int stride = blockDim.x;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<int*>(smem_raw) + threadIdx.x), sstride = blockDim.x * 4u;
     int lstack[STACK_LOCAL];
     DevCtrl* C = a.ctrl;
     const uint32_t n_ext = C->ext_head(c);   // only the BVH class of the path queue needs a traversal
@@ -404,7 +403,7 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
         // `steps` inner nodes per round, so lanes whose ray ended are not left idle behind one long descent.
         for (;;) {
             int trips = 0;
-            for (int k = 0; k < steps && T.node >= 0; ++k) { trav_inner<COUNT>(a.S, T, sstack, stride, lstack, work); ++trips; }
+            for (int k = 0; k < steps && T.node >= 0; ++k) { trav_inner<COUNT>(a.S, T, sbase, sstride, lstack, work); ++trips; }
             if (COUNT) {
                 int mx = trips;
                 for (int off = 16; off; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
@@ -412,16 +411,14 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
                 if (lane == 0) { dbg[0] += 1; dbg[1] += 32ull * mx; dbg[2] += lm ? 1 : 0; dbg[3] += __popc(lm); }
             }
             if (T.node < 0 && T.node != NODE_SENTINEL) {
-                if (kind == 1) {
-                    if (trav_leaf<true, COUNT>(a.S, T, work)) {
-                        occluded = true;
-                        T.node = NODE_SENTINEL;
-                    } else {
-                        trav_pop(T, sstack, stride, lstack);
-                    }
+                // one instance of the leaf code for all ray kinds (shadow rays share warps with extension rays): an
+                // any-hit query is a closest-hit query that stops after the first leaf with a hit below its limit
+                trav_leaf<false, COUNT>(a.S, T, work);
+                if (kind == 1 && T.best_id != PC_NONE) {
+                    occluded = true;
+                    T.node = NODE_SENTINEL;
                 } else {
-                    trav_leaf<false, COUNT>(a.S, T, work);
-                    trav_pop(T, sstack, stride, lstack);
+                    trav_pop(T, sbase, sstride, lstack);
                 }
             }
             const unsigned act = __ballot_sync(0xffffffffu, T.node != NODE_SENTINEL);
