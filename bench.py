@@ -39,8 +39,9 @@ SCENE = "flying_unicorn"
 METRIC = "samples/sec (Mrays/sec alongside) on flying_unicorn"
 UNIT = "samples/s"
 # algorithmic HBM bytes of the two hot kernels per unit (DESIGN.md "Kernels and rooflines"):
-#   k_shade    per path vertex read  : hit 8 + origin/direction/throughput 3 x 16        = 56 B
-#              per extension ray written: origin/direction/throughput/hit                = 56 B
+#   k_shade    per path-queue entry read (camera rays + re-queued paths; a path stays in registers from vertex
+#              to vertex while its next hit is analytic): hit 8 + origin/direction/throughput 3 x 16 = 56 B
+#              per path-queue entry written: origin/direction/throughput/hit             = 56 B
 #              per queued shadow ray written: origin/direction/contribution              = 48 B
 #              per NEE contribution added directly: one 16-byte RED                       = 16 B
 #   k_traverse per BVH extension ray: origin/direction 32 + hit read 8 + hit write 8     = 48 B
@@ -218,7 +219,7 @@ def main():
         scene.render_device(p, shard.data_ptr())
         st = scene.stats()
         for k in ("samples", "rays_primary", "rays_extension", "rays_shadow", "kernel_launches", "iterations", "rays_bvh",
-                  "shadow_bvh"):
+                  "shadow_bvh", "paths_queued"):
             totals[k] = totals.get(k, 0) + st[k]
         for k in ("render_ms", "extend_ms", "shade_ms", "resolve_ms"):
             totals[k] = totals.get(k, 0.0) + st[k]
@@ -281,7 +282,8 @@ def main():
         n_launch = max(1.0, totals["iterations"])
         vertices = totals["rays_primary"] + totals["rays_extension"]      # path vertices shaded == closest-hit rays
         shadow_direct = totals["rays_shadow"] - totals["shadow_bvh"]       # upper bound of the REDs issued by k_shade
-        shade_bytes = (vertices * SHADE_B_VERTEX + totals["rays_extension"] * SHADE_B_EXT + totals["shadow_bvh"] * SHADE_B_SHQ
+        entries_read = totals["rays_primary"] + totals["paths_queued"]     # what k_shade pulls out of the path queue
+        shade_bytes = (entries_read * SHADE_B_VERTEX + totals["paths_queued"] * SHADE_B_EXT + totals["shadow_bvh"] * SHADE_B_SHQ
                        + shadow_direct * SHADE_B_RED)
         trav_bytes = totals["rays_bvh"] * TRAV_B_EXT + totals["shadow_bvh"] * TRAV_B_SH
         peaks = {}

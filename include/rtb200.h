@@ -117,6 +117,7 @@ typedef struct rtb_stats {
     double shade_ms;         /* k_shade */
     uint64_t rays_bvh;       /* primary + extension rays that needed the LBVH (the rest end at an analytic primitive) */
     uint64_t shadow_bvh;     /* shadow rays that needed the LBVH */
+    uint64_t paths_queued;   /* path-queue entries k_shade wrote (a path stays in registers while its next hit is analytic) */
 } rtb_stats;
 
 /* ---- scene: Scene::from_toml + SceneSpec::to_scene (src/scene.rs:143-150, 357-441) ---------

@@ -46,7 +46,7 @@ class Stats(C.Structure):
                 ("bvh_node_visits", C.c_uint64), ("bvh_tri_tests", C.c_uint64), ("render_ms", C.c_double),
                 ("extend_ms", C.c_double), ("shadow_ms", C.c_double), ("generate_ms", C.c_double),
                 ("resolve_ms", C.c_double), ("shade_ms", C.c_double), ("rays_bvh", C.c_uint64),
-                ("shadow_bvh", C.c_uint64)]
+                ("shadow_bvh", C.c_uint64), ("paths_queued", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -620,6 +620,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     st.shadow_ms += shadow_ms;
     st.rays_bvh += h.rays_bvh;
     st.shadow_bvh += h.shadow_bvh;
+    st.paths_queued += h.paths_queued;
     return RTB_OK;
 }
 

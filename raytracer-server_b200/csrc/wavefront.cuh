@@ -29,7 +29,7 @@ constexpr int TILE = 32;  // multi-GPU shard unit: 32x32 pixels, interleaved ove
 constexpr uint32_t SHADOW_PROBE = 0x80000000u;  // shadow entry = dead-MIS probe resolved by a CLOSEST-hit query (mesh lights)
 constexpr uint32_t MAX_DEPTH_FIELD = 4095u;
 constexpr uint32_t FETCH_CHUNK = 32;     // ray indices a warp reserves per atomic
-constexpr int REFILL_BELOW = 22;         // default: refill a warp when fewer than this many lanes are still traversing
+constexpr int REFILL_BELOW = 28;         // default: refill a warp when fewer than this many lanes are still traversing
 constexpr uint32_t SHADE_CHUNK = 32;     // queue entries a k_shade warp reserves per atomic
 constexpr uint32_t SHADE_SEG = 128;      // OUTPUT slots a k_shade warp reserves per atomic in each queue class
 constexpr uint32_t HIT_HOLE = 0xffffffffu;       // path-queue slot reserved by a k_shade warp but never filled (hit.y)
@@ -63,6 +63,7 @@ struct DevCtrl {
     unsigned long long gen_base, work_next, work_total;
     unsigned long long samples, rays_primary, rays_extension, rays_shadow, iterations;
     unsigned long long rays_bvh, shadow_bvh;   // of those, how many needed a BVH traversal
+    unsigned long long paths_queued;           // path-queue entries written by k_shade
     unsigned long long node_visits, tri_tests;
     // counting build only: SIMD-slot accounting of k_traverse (lane-slots offered vs used)
     unsigned long long dbg[8];   // 0 rounds, 1 inner slot-steps offered (32 x trips), 2 leaf phases, 3 leaf lanes, 4 refills, 5 refilled lanes, 6 rays, 7 -
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
         n_queued += __shfl_down_sync(0xffffffffu, n_queued, off);
     }
     if (lane == 0) {
-        if (n_queued) atomicAdd(&C->live[1 - c], n_queued);
+        if (n_queued) { atomicAdd(&C->live[1 - c], n_queued); atomicAdd(&C->paths_queued, (unsigned long long)n_queued); }
         if (n_sh_bvh) atomicAdd(&C->sh_live[1 - c], n_sh_bvh);
         if (n_ext) atomicAdd(&C->rays_extension, (unsigned long long)n_ext);
         if (n_ext_bvh) atomicAdd(&C->rays_bvh, (unsigned long long)n_ext_bvh);
