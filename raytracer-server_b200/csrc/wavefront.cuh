@@ -31,6 +31,7 @@ constexpr uint32_t MAX_DEPTH_FIELD = 4095u;
 constexpr uint32_t FETCH_CHUNK = 32;     // ray indices a warp reserves per atomic
 constexpr int REFILL_BELOW = 28;         // default: refill a warp when fewer than this many lanes are still traversing
 constexpr uint32_t SHADE_CHUNK = 32;     // queue entries a k_shade warp reserves per atomic
+constexpr int SHADE_PARK_BELOW = 12;      // k_shade tail: park the paths of a warp with fewer live lanes than this once the queue is drained
 constexpr uint32_t SHADE_SEG = 128;      // OUTPUT slots a k_shade warp reserves per atomic in each queue class
 constexpr uint32_t HIT_HOLE = 0xffffffffu;       // path-queue slot reserved by a k_shade warp but never filled (hit.y)
 constexpr uint32_t TLIM_HOLE = 0xff800000u;      // same for the shadow queue (d.w = -inf)
@@ -519,6 +520,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     const uint32_t gwarp = (blockIdx.x * SHADE_THREADS + threadIdx.x) >> 5;
     uint32_t wnext = min(gwarp * SHADE_CHUNK, count), wend = min(gwarp * SHADE_CHUNK + SHADE_CHUNK, count);
     bool exhausted = count <= a.shade_warps * SHADE_CHUNK;   // no dynamic chunks in a small launch: no atomics at all
+    const bool big_launch = count > a.shade_warps * SHADE_CHUNK * 8u;
     uint32_t nbase = 0;                                      // lane 0: base of the chunk reserved ahead
     if (!exhausted && lane == 0) nbase = atomicAdd(&C->cursor_shade, SHADE_CHUNK);
 
@@ -575,13 +577,21 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
             }
         }
         // (c) done when no lane holds a path or a prefetched entry and the queue is drained
-        if (__ballot_sync(0xffffffffu, cur_valid || sp_valid) == 0 && wnext >= wend && exhausted) break;
+        const unsigned have_work = __ballot_sync(0xffffffffu, cur_valid || sp_valid);
+        const bool drained = wnext >= wend && exhausted;
+        if (have_work == 0 && drained) break;
+        // Tail of a large launch: the queue is drained and only a few lanes still follow a path.  Those paths are
+        // parked in the back class after this vertex instead of keeping a mostly idle warp (and the whole launch)
+        // alive for the rest of their length; the next iteration packs them densely again.
+        const bool park = drained && big_launch && __popc(have_work) < SHADE_PARK_BELOW;
 
         bool ext_push = false, ext_front = false, sh_push = false, pr_push = false;
-        float4 eo = make_float4(0, 0, 0, 0), ed = eo, eb = eo, ev = eo;
-        float2 eh = make_float2(0.f, __uint_as_float(PC_NONE));
-        float4 so = eo, sd = eo, sc = eo;
-        float4 pd = eo, pc = eo;  // probe entry shares `so`
+        // outputs of this vertex; each is written before it is read under the same flag (no zero-fill: 40 registers)
+        float4 eo, ed, eb, ev = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 eh;
+        float4 so, sd, sc;
+        float4 pd, pc;  // probe entry shares `so`
+        eo.w = 0.f;     // flags word: tested (PC_STALE_O) whenever ext_push is set
 
         if (cur_valid) {
             const uint32_t id = __float_as_uint(h2.y);
@@ -749,7 +759,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
             }
         }
         // ---- where does the path go?  In registers if its next hit is final and it queued no shadow ray.
-        bool keep = ext_push && !ext_front && !sh_push && !pr_push;
+        bool keep = ext_push && !ext_front && !sh_push && !pr_push && !park;
         if (ext_push && !ext_front && __float_as_uint(eh.y) == PC_NONE) {   // left the scene: nothing to shade
             keep = false;
             ext_push = false;
