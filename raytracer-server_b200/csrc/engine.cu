@@ -602,6 +602,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[3 * k + 1], c->ext_ev[3 * k + 2]));
         shade_ms += m;
     }
+    if (h.overflow) return fail(RTB_ECUDA, "internal error: " + std::to_string(h.overflow) + " queue slots beyond the physical capacity were refused (frame is incomplete)");
     st.samples += h.samples;
     st.rays_primary += h.rays_primary;
     st.rays_extension += h.rays_extension;

@@ -65,6 +65,7 @@ struct DevCtrl {
     unsigned long long samples, rays_primary, rays_extension, rays_shadow, iterations;
     unsigned long long rays_bvh, shadow_bvh;   // of those, how many needed a BVH traversal
     unsigned long long paths_queued;           // path-queue entries written by k_shade
+    uint32_t overflow;                         // queue slots refused because they lay beyond the physical capacity (must stay 0)
     unsigned long long node_visits, tri_tests;
     // counting build only: SIMD-slot accounting of k_traverse (lane-slots offered vs used)
     unsigned long long dbg[8];   // 0 rounds, 1 inner slot-steps offered (32 x trips), 2 leaf phases, 3 leaf lanes, 4 refills, 5 refilled lanes, 6 rays, 7 -
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
             }
         }
         PushSlots ps = push_all(&C->ext_head(c), &C->ext_tail(c), &C->sh_head(c), valid, front, false, false);
+        if (valid && ps.ext >= a.Pcap) { atomicAdd(&C->overflow, 1u); valid = false; }
         if (valid) {
             a.q[c].o[ps.ext] = o4;
             a.q[c].d[ps.ext] = d4;
@@ -774,6 +776,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
             uint32_t slot = 0;
             if (mf) { const uint32_t v = seg_alloc<1>(f_base, f_used, f_next, nb, 0u, ctr_front, mf, lane); if (ext_front) slot = v; }
             if (mb) { const uint32_t v = seg_alloc<-1>(b_base, b_used, b_next, nb, 1u, ctr_back, mb, lane); if (!ext_front) slot = v; }
+            if (ext_push && slot >= a.Pcap) { atomicAdd(&C->overflow, 1u); ext_push = false; }
             if (ext_push) {
                 N.o[slot] = eo;
                 N.d[slot] = ed;
@@ -785,10 +788,12 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
         }
         if (ms) {
             const uint32_t slot = seg_alloc<1>(s_base, s_used, s_next, nb, 2u, ctr_sh, ms, lane);
+            if (sh_push && slot >= a.SPcap) { atomicAdd(&C->overflow, 1u); sh_push = false; }
             if (sh_push) { SQ.o[slot] = so; SQ.d[slot] = sd; SQ.c[slot] = sc; }
         }
         if (mp) {
             const uint32_t slot = seg_alloc<1>(s_base, s_used, s_next, nb, 2u, ctr_sh, mp, lane);
+            if (pr_push && slot >= a.SPcap) { atomicAdd(&C->overflow, 1u); pr_push = false; }
             if (pr_push) { SQ.o[slot] = so; SQ.d[slot] = pd; SQ.c[slot] = pc; }
         }
         // ---- next vertex of the same path, straight from registers
@@ -811,13 +816,15 @@ __global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(Re
     {
         const float2 hole = make_float2(0.f, __uint_as_float(HIT_HOLE));
         const float4 hole4 = make_float4(0.f, 0.f, 0.f, __uint_as_float(TLIM_HOLE));
-        for (uint32_t k = f_used + lane; k < SHADE_SEG; k += 32) N.hit[seg_slot<1>(f_base, k)] = hole;
-        for (uint32_t k = b_used + lane; k < SHADE_SEG; k += 32) N.hit[seg_slot<-1>(b_base, k)] = hole;
-        for (uint32_t k = s_used + lane; k < SHADE_SEG; k += 32) SQ.d[seg_slot<1>(s_base, k)] = hole4;
+        auto mark_path = [&](uint32_t slot) { if (slot < a.Pcap) N.hit[slot] = hole; else atomicAdd(&C->overflow, 1u); };
+        auto mark_sh = [&](uint32_t slot) { if (slot < a.SPcap) SQ.d[slot] = hole4; else atomicAdd(&C->overflow, 1u); };
+        for (uint32_t k = f_used + lane; k < SHADE_SEG; k += 32) mark_path(seg_slot<1>(f_base, k));
+        for (uint32_t k = b_used + lane; k < SHADE_SEG; k += 32) mark_path(seg_slot<-1>(b_base, k));
+        for (uint32_t k = s_used + lane; k < SHADE_SEG; k += 32) mark_sh(seg_slot<1>(s_base, k));
         const uint32_t nf = __shfl_sync(0xffffffffu, nb, 0), nbk = __shfl_sync(0xffffffffu, nb, 1) - 1u, ns = __shfl_sync(0xffffffffu, nb, 2);
-        if (f_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) N.hit[seg_slot<1>(nf, k)] = hole;
-        if (b_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) N.hit[seg_slot<-1>(nbk, k)] = hole;
-        if (s_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) SQ.d[seg_slot<1>(ns, k)] = hole4;
+        if (f_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) mark_path(seg_slot<1>(nf, k));
+        if (b_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) mark_path(seg_slot<-1>(nbk, k));
+        if (s_next) for (uint32_t k = lane; k < SHADE_SEG; k += 32) mark_sh(seg_slot<1>(ns, k));
     }
     // counters
     for (int off = 16; off; off >>= 1) {

@@ -50,6 +50,39 @@ def test_seed_changes_noise_not_mean(gpu_scene):
     assert np.abs(a - c).max() <= 1            # same seed: identical up to fp32 atomic ordering
 
 
+@pytest.mark.parametrize("use_mis", [False, True])
+def test_frame_independent_of_the_path_pool(gpu_scene, use_mis):
+    # The wavefront machinery (pool size, regeneration rounds, per-warp queue segments and their holes, paths kept
+    # in registers vs parked in the queue) must not leak into the image: RNG counters are per (pixel, sample, depth),
+    # so any pool gives the same frame up to the order of the fp32 atomic adds.
+    g = gpu_scene("flying_unicorn")
+    W, H, spp = 160, 120, 32
+    ref = g.render(W, H, spp, seed=11, use_mis=use_mis).astype(int)
+    st_ref = g.stats()
+    for pool in (1024, 6000, 1 << 16):
+        f = g.render(W, H, spp, seed=11, use_mis=use_mis, pool_paths=pool).astype(int)
+        st = g.stats()
+        assert np.abs(f - ref).max() <= 1, pool
+        for k in ("samples", "rays_primary", "rays_extension", "rays_shadow", "rays_bvh", "shadow_bvh"):
+            assert st[k] == st_ref[k], (pool, k)       # the same rays are traced, only their schedule differs
+        assert st["iterations"] >= st_ref["iterations"]
+
+
+def test_paths_stay_in_registers(gpu_scene):
+    # cornell_box has no mesh: no ray ever needs k_traverse, so k_shade follows every path from the camera ray to its
+    # end without queueing it again (one queue entry per sample, written by k_generate)
+    g = gpu_scene("cornell_box")
+    g.render(320, 240, 16, seed=4)
+    st = g.stats()
+    assert st["rays_bvh"] == 0 and st["shadow_bvh"] == 0
+    assert st["paths_queued"] <= st["samples"] // 20     # only the paths parked at the tail of a large launch (< 12 per warp)
+    g2 = gpu_scene("flying_unicorn")
+    g2.render(320, 240, 16, seed=4)
+    st2 = g2.stats()
+    # a path is queued when its next ray can reach the mesh box (or its shadow ray could): far fewer than one entry per vertex
+    assert st2["rays_bvh"] - st2["rays_primary"] <= st2["paths_queued"] < 0.35 * st2["rays_extension"]
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_tile_shards_reassemble_the_frame(gpu_scene, rtb, world):
     # per-pixel RNG counters are independent of the sharding, so the union of the ranks' tiles is the
