@@ -14,6 +14,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "--use_fast_math=false"] if False else ["-O3", "-lineinfo", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Xcompiler",
                                                   "-fPIC"]
+EXTRA = os.environ.get("RTB_NVCC_EXTRA", "").split()   # experiment knobs, e.g. -DRTB_SHADE_THREADS=160 -DRTB_SHADE_MINB=4
 SOURCES = ["engine.cu", "lbvh.cu", "scene_host.cpp"]
 
 
@@ -31,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         newest = max(os.path.getmtime(d) for d in _deps(src))
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
-            cmd = [NVCC, *ARCH, *COMMON, "-c", os.path.join(CSRC, src), "-o", obj]
+            cmd = [NVCC, *ARCH, *COMMON, *EXTRA, "-c", os.path.join(CSRC, src), "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

@@ -147,7 +147,13 @@ __device__ __forceinline__ PushSlots push_all(uint32_t* ext_head, uint32_t* ext_
 // Block-aggregated variant for k_shade: the 8 warps of a CTA pool their counts in shared memory and
 // three threads issue ONE atomic per counter per CTA iteration (fewer same-address atomics at L2).
 // Every thread of the CTA must call it (two __syncthreads inside).
-constexpr int SHADE_THREADS = 256;   // CTA size of k_shade
+#ifndef RTB_SHADE_THREADS
+#define RTB_SHADE_THREADS 256
+#endif
+#ifndef RTB_SHADE_MINB
+#define RTB_SHADE_MINB (512 / RTB_SHADE_THREADS)
+#endif
+constexpr int SHADE_THREADS = RTB_SHADE_THREADS;   // CTA size of k_shade (warps are independent: only occupancy depends on it)
 struct BlockPushSmem {
     uint32_t cnt[SHADE_THREADS / 32][4];
     uint32_t base[SHADE_THREADS / 32][4];
@@ -494,7 +500,7 @@ __device__ __forceinline__ uint32_t seg_slot(uint32_t base, uint32_t k) { return
 // only, sphere light, no probe items.  The general instantiation keeps every branch (dead-MIS estimator, Phong,
 // mesh lights, rtb_sample_radiance probes).
 template <bool FAST>
-__global__ void __launch_bounds__(SHADE_THREADS, 512 / SHADE_THREADS) k_shade(RenderArgs a, int c) {
+__global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevCtrl* C = a.ctrl;
     const DevSceneHeader* hdr = a.S.hdr;
