@@ -43,7 +43,7 @@ namespace {
         }                                                                              \
     } while (0)
 
-constexpr int LEAF_MAX = 4;
+constexpr int LEAF_MAX = 2;
 
 __device__ __forceinline__ int float_to_ordered(float f) {
     int i = __float_as_int(f);
@@ -178,10 +178,10 @@ __global__ void k_refit(int n, const uint32_t* __restrict__ sorted, const float4
     }
 }
 
-__global__ void k_mark_used(int n_internal, const int* __restrict__ rfirst, const int* __restrict__ rlast, int* __restrict__ used) {
+__global__ void k_mark_used(int n_internal, int leaf_max, const int* __restrict__ rfirst, const int* __restrict__ rlast, int* __restrict__ used) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_internal) return;
-    used[i] = (rlast[i] - rfirst[i] + 1) > LEAF_MAX ? 1 : 0;
+    used[i] = (rlast[i] - rfirst[i] + 1) > leaf_max ? 1 : 0;
 }
 
 __device__ __forceinline__ int encode_leaf(int first, int count) { return ~((first << 3) | (count - 1)); }
@@ -257,13 +257,13 @@ __global__ void k_ploc_init(int n, const uint32_t* __restrict__ sorted, const fl
     csize[s] = 1;
 }
 
-__global__ void k_ploc_nn(int m, const float4* __restrict__ clo, const float4* __restrict__ chi, int* __restrict__ nn) {
+__global__ void k_ploc_nn(int m, int radius, const float4* __restrict__ clo, const float4* __restrict__ chi, int* __restrict__ nn) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const float4 lo = clo[i], hi = chi[i];
     float best = FLT_MAX;
     int bj = -1;
-    const int j0 = max(0, i - PLOC_RADIUS), j1 = min(m - 1, i + PLOC_RADIUS);
+    const int j0 = max(0, i - radius), j1 = min(m - 1, i + radius);
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
         const float4 l2 = clo[j], h2 = chi[j];
@@ -533,6 +533,8 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
     const bool karras = mode_env && std::string(mode_env) == "lbvh";   // default: PLOC on the same Morton order
 
     Bounds6 hb;
+    int leaf_max = LEAF_MAX;
+    if (const char* e = getenv("RTB_LEAF_MAX")) leaf_max = std::min(8, std::max(1, atoi(e)));
     if (n <= LEAF_MAX) {  // the whole mesh is one leaf
         k_pack_tris<<<nb, T, 0, stream>>>(n, vals2.p, d_verts, d_tri_obj, d_tris, out.d_tri_nrm);
         out.root = ~((0 << 3) | (n - 1));
@@ -545,7 +547,7 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
         const int nbi = (ni + T - 1) / T;
         k_hierarchy<<<nbi, T, 0, stream>>>(keys2.p, n, left.p, right.p, pint.p, pleaf.p, rfirst.p, rlast.p);
         k_refit<<<nb, T, 0, stream>>>(n, vals2.p, tlo.p, thi.p, left.p, right.p, pint.p, pleaf.p, arrive.p, nlo.p, nhi.p);
-        k_mark_used<<<nbi, T, 0, stream>>>(ni, rfirst.p, rlast.p, used.p);
+        k_mark_used<<<nbi, T, 0, stream>>>(ni, leaf_max, rfirst.p, rlast.p, used.p);
         LBVH_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, used.p, newidx.p, ni, stream));
         int last_used = 0, last_idx = 0;
         LBVH_CHECK(cudaMemcpyAsync(&last_used, used.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -567,10 +569,12 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
         LBVH_CHECK(nnb.alloc(n)); LBVH_CHECK(valid.alloc(n)); LBVH_CHECK(merge.alloc(n)); LBVH_CHECK(pv.alloc(n + 1)); LBVH_CHECK(pm.alloc(n + 1));
         LBVH_CHECK(nsize.alloc(n)); LBVH_CHECK(leafpos.alloc(n)); LBVH_CHECK(ir_int.alloc(n)); LBVH_CHECK(ir_leaf.alloc(n)); LBVH_CHECK(order.alloc(n));
         k_ploc_init<<<nb, T, 0, stream>>>(n, vals2.p, tlo.p, thi.p, cn[0].p, cl[0].p, ch[0].p, cs[0].p);
+        int ploc_radius = PLOC_RADIUS;
+        if (const char* e = getenv("RTB_PLOC_RADIUS")) ploc_radius = std::max(1, atoi(e));
         int m = n, node_base = 0, cur = 0, rounds = 0;
         while (m > 1) {
             const int mb = (m + T - 1) / T;
-            k_ploc_nn<<<mb, T, 0, stream>>>(m, cl[cur].p, ch[cur].p, nnb.p);
+            k_ploc_nn<<<mb, T, 0, stream>>>(m, ploc_radius, cl[cur].p, ch[cur].p, nnb.p);
             k_ploc_flags<<<mb, T, 0, stream>>>(m, nnb.p, valid.p, merge.p);
             LBVH_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, valid.p, pv.p, m, stream));
             LBVH_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, merge.p, pm.p, m, stream));
@@ -598,7 +602,7 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
         k_ploc_order<<<nb, T, 0, stream>>>(n, vals2.p, leafpos.p, order.p);
         k_pack_tris<<<nb, T, 0, stream>>>(n, order.p, d_verts, d_tri_obj, d_tris, out.d_tri_nrm);
         const int nbi = (ni + T - 1) / T;
-        k_mark_used<<<nbi, T, 0, stream>>>(ni, rfirst.p, rlast.p, used.p);
+        k_mark_used<<<nbi, T, 0, stream>>>(ni, leaf_max, rfirst.p, rlast.p, used.p);
         LBVH_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, used.p, newidx.p, ni, stream));
         int last_used = 0, last_idx = 0, root_new = 0;
         LBVH_CHECK(cudaMemcpyAsync(&last_used, used.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));

@@ -30,7 +30,7 @@ def test_struct_layouts_match_header(rtb):
     assert C.sizeof(_abi.Params) == 4 * 4 + 8 + 3 * 4 + 5 * 4 + 0 or C.sizeof(_abi.Params) == 56
     assert C.sizeof(_abi.Params) == 56
     assert C.sizeof(_abi.SceneInfo) == 12 * 4 + 12 * 4 + 8
-    assert C.sizeof(_abi.Stats) == 8 * 8 + 6 * 8 + 2 * 8
+    assert C.sizeof(_abi.Stats) == 8 * 8 + 6 * 8 + 3 * 8
     assert C.sizeof(_abi.ObjectInfo) == 4 * 4 + 8 * (3 * 6 + 1 + 3 * 2 + 1)
 
 
