@@ -330,8 +330,9 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         // The attribute is per kernel, not per scene: always opt in to the largest table set
         // (MAX_OBJECTS primitives + materials), never to this scene's own (smaller) size.
         const int smem_max = (int)shared_tables_bytes(MAX_OBJECTS, MAX_OBJECTS);
-        CU_TRY(cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        CU_TRY(cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_shade<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_shade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_shade<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CU_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         int b = 0;
         if (const char* e = getenv("RTB_TRAV_MINB")) c->trav_minb = atoi(e) == 5 ? 5 : (atoi(e) == 6 ? 6 : 4);
@@ -341,7 +342,7 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         c->grid_ext = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true>, WF_THREADS, smem_stack));
         c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<false>, SHADE_THREADS, smem_tab));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<0>, SHADE_THREADS, smem_tab));
         c->grid_shade = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate, WF_THREADS, smem_tab));
         c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
@@ -487,8 +488,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     // Small frames are launch-bound (four tiny kernels per iteration): replay one captured CUDA graph per
     // iteration and let k_prepare publish the live-path count to mapped host memory instead of copying it back.
     // compile-time specialisation of k_shade for the common case (see its definition)
-    bool fast_shade = a.estimator == 0 && !a.probe_px && sc->fs.light_geom == GEOM_SPHERE && !getenv("RTB_NO_FAST_SHADE");
+    bool fast_shade = !a.probe_px && sc->fs.light_geom == GEOM_SPHERE && !getenv("RTB_NO_FAST_SHADE");
     for (const FlatMaterial& m : sc->fs.materials) fast_shade = fast_shade && m.brdf != BRDF_PHONG;
+    const int shade_mode = !fast_shade ? 0 : (a.estimator == 0 ? 1 : 2);
     const bool use_graph = !count_work && a.P <= (1u << 21) && !getenv("RTB_NO_GRAPH");
     if (use_graph && !done) {
         RenderArgs ag = a;
@@ -509,8 +511,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
-                if (fast_shade) k_shade<true><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
-            else k_shade<false><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
+                if (shade_mode == 1) k_shade<1><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
+                else if (shade_mode == 2) k_shade<2><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
+                else k_shade<0><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
                 ge = cudaStreamEndCapture(c->stream, &g);
                 if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->graph_exec[k], g, 0);
                 if (g) cudaGraphDestroy(g);
@@ -565,8 +568,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         CU_TRY(cudaEventRecord(ev[1], c->stream));
-        if (fast_shade) k_shade<true><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
-        else k_shade<false><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
+        if (shade_mode == 1) k_shade<1><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
+        else if (shade_mode == 2) k_shade<2><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
+        else k_shade<0><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
         CU_TRY(cudaEventRecord(ev[2], c->stream));
         ++ext_iters;
         launches += 4;

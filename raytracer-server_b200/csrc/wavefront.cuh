@@ -496,11 +496,12 @@ __device__ __forceinline__ uint32_t seg_slot(uint32_t base, uint32_t k) { return
 // New paths come from the current queue: a warp owns one static chunk of SHADE_CHUNK entries and then reserves
 // further chunks from a work cursor one chunk ahead; every lane holds one PREFETCHED entry, so the (streaming)
 // queue loads of a new path are issued a whole trip before they are needed.
-// FAST = the reference scenes' case, resolved at compile time: live NEE estimator, Diffuse / Specular materials
-// only, sphere light, no probe items.  The general instantiation keeps every branch (dead-MIS estimator, Phong,
-// mesh lights, rtb_sample_radiance probes).
-template <bool FAST>
+// MODE 1 / 2 (FAST) = the reference scenes' case, resolved at compile time: Diffuse / Specular materials only, sphere
+// light, no probe items; 1 = live NEE estimator, 2 = the dead "MIS" branch.  MODE 0, the general instantiation, keeps
+// every branch at run time (both estimators, Phong, mesh lights, rtb_sample_radiance probes).
+template <int MODE>
 __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderArgs a, int c) {
+    constexpr bool FAST = MODE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevCtrl* C = a.ctrl;
     const DevSceneHeader* hdr = a.S.hdr;
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
     const PathQueue Q = a.q[c], N = a.q[1 - c];
     const int light_obj = hdr->light_obj;
     const bool light_is_mesh = FAST ? false : hdr->light_geom == 2;
-    const bool mis = FAST ? false : a.estimator != 0;
+    const bool mis = MODE == 1 ? false : (MODE == 2 ? true : a.estimator != 0);
     const bool probe_mode = FAST ? false : a.probe_px != nullptr;
     const float3 Le = f3(sh.mats[light_obj].emitted);
     const int n_prims = a.S.n_prims, n_planes = a.S.n_planes;
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
                             float pdf_light = pdf_a * (r2 / dot(ny, -inc));
                             float3 itmp;
                             float pdf_fresh;
-                            brdf_sample(mat, hg.n, inc, rng_block(rng_pixel, sample, depth, 2u, a.k0, a.k1), itmp, pdf_fresh);
+                            brdf_sample<FAST>(mat, hg.n, inc, rng_block(rng_pixel, sample, depth, 2u, a.k0, a.k1), itmp, pdf_fresh);
                             contrib = beta * Le * f * (dot(hg.n, inc) / (pdf_light + pdf_fresh));
                         }
                         if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
@@ -684,14 +685,14 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
                         if (mis) {  // src/scene.rs:203-214: own BRDF sample; counts only if it reaches the light
                             float3 i2;
                             float pdf2;
-                            brdf_sample(mat, hg.n, ovec, rng_block(rng_pixel, sample, depth, 4u, a.k0, a.k1), i2, pdf2);
+                            brdf_sample<FAST>(mat, hg.n, ovec, rng_block(rng_pixel, sample, depth, 4u, a.k0, a.k1), i2, pdf2);
                             if (i2.x != 0.f || i2.y != 0.f || i2.z != 0.f) {
                                 float3 y2, ny2;
                                 float pdf_a2;
-                                light_sample(a.S, sh.prims, hdr, rng_block(rng_pixel, sample, depth, 3u, a.k0, a.k1), y2, ny2, pdf_a2);
+                                light_sample<FAST>(a.S, sh.prims, hdr, rng_block(rng_pixel, sample, depth, 3u, a.k0, a.k1), y2, ny2, pdf_a2);
                                 float3 dv2 = y2 - hg.pos;
                                 float pdf_light2 = pdf_a2 * (dot(dv2, dv2) / dot(ny2, -i2));
-                                float3 c2 = beta * Le * brdf_eval(mat, hg.n, ovec, i2) * (dot(hg.n, i2) / (pdf2 + pdf_light2));
+                                float3 c2 = beta * Le * brdf_eval<FAST>(mat, hg.n, ovec, i2) * (dot(hg.n, i2) / (pdf2 + pdf_light2));
                                 if (c2.x != 0.f || c2.y != 0.f || c2.z != 0.f) {
                                     // trace_ray(x, i2) and test hit.id == light_source
                                     ++n_sh;
