@@ -22,6 +22,11 @@ namespace rtb {
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr float INV_PI_F = 0.318309886183790671538f;
 
+// single-instruction SFU forms (MUFU.SQRT / MUFU.RCP, ~1 ulp, denormals flushed) for the sampling arithmetic: IEEE sqrtf /
+// division are 8-10 instruction sequences with a slow-path call each
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
@@ -127,8 +132,8 @@ __device__ __forceinline__ float3 brdf_eval(const DevMaterial& m, float3 n, floa
 template <bool FAST = false>
 __device__ __forceinline__ void brdf_sample(const DevMaterial& m, float3 n, float3 o, float4 xi, float3& i, float& pdf) {
     if (FAST || m.brdf == 0) {   // FAST callers only sample diffuse surfaces
-        float z = sqrtf(xi.x);
-        float r = sqrtf(1.0f - z * z);
+        float z = fast_sqrt(xi.x);
+        float r = fast_sqrt(1.0f - xi.x);   // sqrt(1 - z*z)
         float s, c;
         sincos_2pi(xi.y, s, c);
         float3 u, v;
@@ -166,14 +171,14 @@ __device__ __forceinline__ void light_sample(const DevScene& S, const DevPrim* p
     if (FAST || hdr->light_geom == 0) {  // sphere: uniform over the whole surface
         const DevPrim& L = prims[hdr->light_prim];
         float z = 2.0f * xi.x - 1.0f;
-        float r = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+        float r = fast_sqrt(fmaxf(1.0f - z * z, 0.0f));
         float s, c;
         sincos_2pi(xi.y, s, c);
         float3 n = normalize(f3(r * c, r * s, z));
         float rad = L.a.w;
         y = f3(L.a) + n * rad;
         ny = n;
-        pdf = 1.0f / (4.0f * PI_F * rad * rad);
+        pdf = fast_rcp(4.0f * PI_F * rad * rad);
         return;
     }
     // mesh: triangle by area (WeightedIndex: partition_point(w <= chosen)), then Triangle::sample.

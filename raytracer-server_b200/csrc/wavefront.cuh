@@ -624,10 +624,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
                 } else if (origin & PC_SPEC_PENDING) {
                     if (emits) accum_add(a.accum, acc, beta * emitted);
                     const DevMaterial& pm = sh.mats[object_of(a.S, sh, origin & PC_ID_MASK)];
-                    const float pp = (depth - 1u) <= 5u ? 1.0f : 0.9f;
-                    beta = beta * f3(pm.k) * (1.0f / pp);
+                    const float inv_pp = (depth - 1u) <= 5u ? 1.0f : (1.0f / 0.9f);   // 1 / survival probability of the specular vertex
+                    beta = beta * f3(pm.k) * inv_pp;
                 }
                 const float p = depth <= 5u ? 1.0f : 0.9f;  // MAX_BOUNCES / SURVIVAL_PROBABILITY (src/scene.rs:109-110,164-168)
+                const float inv_p = depth <= 5u ? 1.0f : (1.0f / 0.9f);
                 const uint32_t rng_pixel = probe_mode ? (uint32_t)(a.probe_py[acc] * a.width + a.probe_px[acc]) : acc >> 2;
                 const bool dead_surface = mat.brdf == 0 && mat.k.x == 0.f && mat.k.y == 0.f && mat.k.z == 0.f;
                 const bool dead_path = beta.x == 0.f && beta.y == 0.f && beta.z == 0.f;
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
                             brdf_sample<FAST>(mat, hg.n, ovec, rb, next_dir, pdf1);
                             if (next_dir.x != 0.f || next_dir.y != 0.f || next_dir.z != 0.f) {
                                 float3 nb;
-                                if (FAST || mat.brdf == 0) nb = beta * f3(mat.k) * (1.0f / p);  // f (n.i) / pdf == kd exactly
+                                if (FAST || mat.brdf == 0) nb = beta * f3(mat.k) * inv_p;  // f (n.i) / pdf == kd exactly
                                 else nb = beta * brdf_eval(mat, hg.n, ovec, next_dir) * (dot(hg.n, next_dir) / (pdf1 * p));
                                 ext_push = true;
                                 eo = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
