@@ -103,6 +103,15 @@ __device__ __forceinline__ float3 normalize(float3 a) {
     float inv = rsqrtf(dot(a, a));
     return a * inv;
 }
+// single-instruction SFU forms (MUFU.SQRT / MUFU.RCP, ~1 ulp, denormals flushed) for the sampling arithmetic: IEEE sqrtf /
+// division are 8-10 instruction sequences with a slow-path call each
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// packed FP32x2 helpers (FFMA2 / FMUL2, sm_100): the kernels are bound by instruction issue, and two rays that meet the
+// same primitive do the same arithmetic — one issue slot for both.  bc() = a scalar both halves use (SASS takes it as
+// a broadcast .F32 operand, no extra register)
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
 // Vec3::flip_across (src/geometry.rs:99-101)
 __device__ __forceinline__ float3 flip_across(float3 s, float3 axis) { return (2.0f * dot(s, axis)) * axis - s; }
 

@@ -96,7 +96,7 @@ __device__ __forceinline__ int origin_group_of(const SharedScene& sh, uint32_t o
 // plane k: distance along d (or a negative number / NaN-free "no hit" encoded by ok = false)
 __device__ __forceinline__ float plane_t(const float4 a, float num, float3 d, bool& ok) {
     const float dn = d.x * a.x + d.y * a.y + d.z * a.z;
-    const float t = __fdividef(num, dn);
+    const float t = num * fast_rcp(dn);
     ok = fabsf(dn) >= DN_EPS && t >= 0.0f;      // |d.n| < 1e-4 -> miss; t >= 0 (no epsilon), src/geometry.rs:551-568
     return t;
 }
@@ -145,10 +145,47 @@ __device__ __forceinline__ void analytic_closest(const SharedScene& sh, int n_pl
     }
 }
 
+// packed forms of plane_t / sphere_t for TWO directions (d1 | d2) = (dx, dy, dz): the same operations in the same order
+// per component (FFMA2 rounds each half like fmaf), so a ray gets the same t as from the scalar functions
+__device__ __forceinline__ float2 plane_t2(const float4 a, float num, float2 dx, float2 dy, float2 dz, bool& ok1, bool& ok2) {
+    float2 dn = __fmul2_rn(dx, bc(a.x));
+    dn = __ffma2_rn(dy, bc(a.y), dn);
+    dn = __ffma2_rn(dz, bc(a.z), dn);
+    const float2 t = __fmul2_rn(bc(num), f2(fast_rcp(dn.x), fast_rcp(dn.y)));
+    ok1 = fabsf(dn.x) >= DN_EPS && t.x >= 0.0f;
+    ok2 = fabsf(dn.y) >= DN_EPS && t.y >= 0.0f;
+    return t;
+}
+__device__ __forceinline__ float2 sphere_t2(float3 op, float r2, float2 dx, float2 dy, float2 dz, bool self, bool& ok1, bool& ok2) {
+    float2 b = __fmul2_rn(bc(op.x), dx);
+    b = __ffma2_rn(bc(op.y), dy, b);
+    b = __ffma2_rn(bc(op.z), dz, b);
+    const float2 nb = __fmul2_rn(b, bc(-1.0f));
+    const float2 lx = __ffma2_rn(nb, dx, bc(op.x)), ly = __ffma2_rn(nb, dy, bc(op.y)), lz = __ffma2_rn(nb, dz, bc(op.z));
+    float2 m = __fmul2_rn(lx, lx);
+    m = __ffma2_rn(ly, ly, m);
+    m = __ffma2_rn(lz, lz, m);
+    const float2 det = __ffma2_rn(m, bc(-1.0f), bc(r2));
+    float2 s = __fmul2_rn(det, f2(rsqrtf(det.x), rsqrtf(det.y)));
+    s.x = det.x > 0.0f ? s.x : 0.0f;
+    s.y = det.y > 0.0f ? s.y : 0.0f;
+    const float2 tn = __ffma2_rn(s, bc(-1.0f), b), tf = __fadd2_rn(b, s);
+    float2 t = f2(tn.x > T_EPS ? tn.x : tf.x, tn.y > T_EPS ? tn.y : tf.y);
+    ok1 = det.x >= 0.0f && t.x > T_EPS;
+    ok2 = det.y >= 0.0f && t.y > T_EPS;
+    if (self) {
+        t = __fadd2_rn(b, b);
+        ok1 = t.x > T_EPS;
+        ok2 = t.y > T_EPS;
+    }
+    return t;
+}
+
 // Two rays leaving the same point `o` on primitive `origin` in one pass over the table:
 //   d1: nearest analytic hit (t1, id1)                                  -> the extension ray
 //   d2: is anything analytic in front of tlim2 ?                        -> the shadow ray (mutually_visible)
-// The per-primitive set-up ((pos - o).n, c - o, the self-intersection class) is shared by both.
+// The per-primitive set-up ((pos - o).n, c - o, the self-intersection class) is shared by both, and the two rays'
+// arithmetic is issued as packed FP32x2 instructions.
 __device__ __forceinline__ void analytic_pair(const SharedScene& sh, int n_planes, int n_prims, float3 o, uint32_t origin,
                                               float3 d1, float& t1, uint32_t& id1, float3 d2, float tlim2, bool& occ2) {
     t1 = INFINITY;
@@ -156,24 +193,23 @@ __device__ __forceinline__ void analytic_pair(const SharedScene& sh, int n_plane
     occ2 = false;
     const int og = origin_group_of(sh, origin);
     const uint32_t oid = origin & PC_ID_MASK;
+    const float2 dx = f2(d1.x, d2.x), dy = f2(d1.y, d2.y), dz = f2(d1.z, d2.z);
     for (int k = 0; k < n_planes; ++k) {
         const DevPrim& P = sh.prims[k];
         const float num = plane_num(P, o, og, origin);
         bool ok1, ok2;
-        const float ta = plane_t(P.a, num, d1, ok1);
-        const float tb = plane_t(P.a, num, d2, ok2);
-        if (ok1 && ta < t1) { t1 = ta; id1 = (uint32_t)k; }
-        occ2 |= ok2 && tb < tlim2;
+        const float2 t = plane_t2(P.a, num, dx, dy, dz, ok1, ok2);
+        if (ok1 && t.x < t1) { t1 = t.x; id1 = (uint32_t)k; }
+        occ2 |= ok2 && t.y < tlim2;
     }
     for (int k = n_planes; k < n_prims; ++k) {
         const DevPrim& P = sh.prims[k];
         const float3 op = f3(P.a) - o;
         const bool self = (uint32_t)k == oid;
         bool ok1, ok2;
-        const float ta = sphere_t(op, P.b.x, d1, self, ok1);
-        const float tb = sphere_t(op, P.b.x, d2, self, ok2);
-        if (ok1 && ta < t1) { t1 = ta; id1 = (uint32_t)k; }
-        occ2 |= ok2 && tb < tlim2;
+        const float2 t = sphere_t2(op, P.b.x, dx, dy, dz, self, ok1, ok2);
+        if (ok1 && t.x < t1) { t1 = t.x; id1 = (uint32_t)k; }
+        occ2 |= ok2 && t.y < tlim2;
     }
 }
 

@@ -22,11 +22,6 @@ namespace rtb {
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr float INV_PI_F = 0.318309886183790671538f;
 
-// single-instruction SFU forms (MUFU.SQRT / MUFU.RCP, ~1 ulp, denormals flushed) for the sampling arithmetic: IEEE sqrtf /
-// division are 8-10 instruction sequences with a slow-path call each
-__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
