@@ -428,8 +428,7 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     a.spp = p->spp;
     a.num_samples = p->spp / 4;
     a.ks_done = (uint32_t)(p->spp / 4) * 4u;
-    a.k0 = (uint32_t)p->seed;
-    a.k1 = (uint32_t)(p->seed >> 32);
+    a.keys = philox_keys((uint32_t)p->seed, (uint32_t)(p->seed >> 32));
     a.estimator = p->estimator;
     a.tune_refill = p->reserved[1];
     a.tune_steps = p->reserved[2];

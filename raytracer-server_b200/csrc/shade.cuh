@@ -22,30 +22,41 @@ namespace rtb {
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr float INV_PI_F = 0.318309886183790671538f;
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+// The ten round keys (k + i * Weyl constant) are computed once on the host and live in the kernel parameters: after
+// unrolling they are constant-bank operands of the XORs, not ten pairs of additions per block.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+__host__ __device__ inline PhiloxKeys philox_keys(uint32_t k0, uint32_t k1) {
+    PhiloxKeys K;
+    for (int i = 0; i < 10; ++i) {
+        K.k0[i] = k0 + (uint32_t)i * 0x9E3779B9u;
+        K.k1[i] = k1 + (uint32_t)i * 0xBB67AE85u;
+    }
+    return K;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        uint32_t n0 = hi1 ^ c1 ^ K.k0[i], n2 = hi0 ^ c3 ^ K.k1[i];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
 }
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 __device__ __forceinline__ float u24(uint32_t v) { return ((float)v + 0.5f) * (1.0f / 16777216.0f); }
-__device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t block, uint32_t k0, uint32_t k1) {
-    uint4 r = philox4x32_10(pixel, sample, depth, block, k0, k1);
+__device__ __forceinline__ float4 rng_block(uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t block, const PhiloxKeys& K) {
+    uint4 r = philox4x32_10(pixel, sample, depth, block, K);
     return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
 }
 // the five uniforms of a live vertex from ONE Philox block (see the contract above)
 struct VertexRng {
     float light_u1, light_u2, rr, brdf_u1, brdf_u2;
 };
-__device__ __forceinline__ VertexRng rng_vertex(uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t k0, uint32_t k1) {
-    uint4 r = philox4x32_10(pixel, sample, depth, 0u, k0, k1);
+__device__ __forceinline__ VertexRng rng_vertex(uint32_t pixel, uint32_t sample, uint32_t depth, const PhiloxKeys& K) {
+    uint4 r = philox4x32_10(pixel, sample, depth, 0u, K);
     VertexRng v;
     v.light_u1 = u24(r.x >> 8);
     v.light_u2 = u24(r.y >> 8);

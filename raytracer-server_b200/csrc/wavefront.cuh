@@ -81,7 +81,7 @@ struct RenderArgs {
     Camera cam;
     int width, height, spp, num_samples;
     uint32_t ks_done;    // samples resolved so far, in (k*4 + sub-pixel) units; 4*num_samples for a finished frame
-    uint32_t k0, k1;
+    PhiloxKeys keys;     // round keys of the frame's seed
     int estimator;
     int rank, world, tiles_x, tiles_y, n_local_tiles;
     uint32_t P, SP;          // most paths / shadow rays alive at once
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
             }
             if (valid) {
                 int sub = sample / a.num_samples;
-                float4 r = rng_block(rng_pixel, (uint32_t)sample, 0u, 0u, a.k0, a.k1);
+                float4 r = rng_block(rng_pixel, (uint32_t)sample, 0u, 0u, a.keys);
                 float3 dir = camera_dir(a.cam, x, a.height - y - 1, sub & 1, sub >> 1, tent(r.x), tent(r.y), w, h);
                 float ta;
                 uint32_t ida;
@@ -633,11 +633,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
                 const bool dead_surface = mat.brdf == 0 && mat.k.x == 0.f && mat.k.y == 0.f && mat.k.z == 0.f;
                 const bool dead_path = beta.x == 0.f && beta.y == 0.f && beta.z == 0.f;
                 if (!dead_surface && !dead_path && depth < MAX_DEPTH_FIELD) {
-                    const VertexRng vr = rng_vertex(rng_pixel, sample, depth, a.k0, a.k1);
+                    const VertexRng vr = rng_vertex(rng_pixel, sample, depth, a.keys);
                     // lobe / light-triangle selectors live in block 1 and are only drawn by Phong surfaces / mesh lights
                     float lobe_u = 0.f, select_u = 0.f;
                     if (!FAST && (mat.brdf == 2 || light_is_mesh)) {
-                        const float4 r1 = rng_block(rng_pixel, sample, depth, 1u, a.k0, a.k1);
+                        const float4 r1 = rng_block(rng_pixel, sample, depth, 1u, a.keys);
                         lobe_u = r1.x;
                         select_u = r1.y;
                     }
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
                             float pdf_light = pdf_a * (r2 / dot(ny, -inc));
                             float3 itmp;
                             float pdf_fresh;
-                            brdf_sample<FAST>(mat, hg.n, inc, rng_block(rng_pixel, sample, depth, 2u, a.k0, a.k1), itmp, pdf_fresh);
+                            brdf_sample<FAST>(mat, hg.n, inc, rng_block(rng_pixel, sample, depth, 2u, a.keys), itmp, pdf_fresh);
                             contrib = beta * Le * f * (dot(hg.n, inc) / (pdf_light + pdf_fresh));
                         }
                         if (contrib.x != 0.f || contrib.y != 0.f || contrib.z != 0.f) {
@@ -686,11 +686,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
                         if (mis) {  // src/scene.rs:203-214: own BRDF sample; counts only if it reaches the light
                             float3 i2;
                             float pdf2;
-                            brdf_sample<FAST>(mat, hg.n, ovec, rng_block(rng_pixel, sample, depth, 4u, a.k0, a.k1), i2, pdf2);
+                            brdf_sample<FAST>(mat, hg.n, ovec, rng_block(rng_pixel, sample, depth, 4u, a.keys), i2, pdf2);
                             if (i2.x != 0.f || i2.y != 0.f || i2.z != 0.f) {
                                 float3 y2, ny2;
                                 float pdf_a2;
-                                light_sample<FAST>(a.S, sh.prims, hdr, rng_block(rng_pixel, sample, depth, 3u, a.k0, a.k1), y2, ny2, pdf_a2);
+                                light_sample<FAST>(a.S, sh.prims, hdr, rng_block(rng_pixel, sample, depth, 3u, a.keys), y2, ny2, pdf_a2);
                                 float3 dv2 = y2 - hg.pos;
                                 float pdf_light2 = pdf_a2 * (dot(dv2, dv2) / dot(ny2, -i2));
                                 float3 c2 = beta * Le * brdf_eval<FAST>(mat, hg.n, ovec, i2) * (dot(hg.n, i2) / (pdf2 + pdf_light2));
