@@ -223,6 +223,10 @@ int build_device_scene(rtb_scene* sc) {
     V.mats = reinterpret_cast<const DevMaterial*>(sc->d_stage + sc->off_mats);
     V.nodes = sc->bvh.d_nodes;
     V.qnodes = sc->bvh.d_qnodes;
+    V.qnodes4 = sc->bvh.d_qnodes4;
+    V.root4 = sc->bvh.root4;
+    V.wide = 0;   // measured: the 4-wide table halves the memory stalls but costs 36 % more instructions — a wash
+    if (const char* e = getenv("RTB_BVH_WIDE")) V.wide = atoi(e) != 0;
     V.qmin = make_float3(sc->bvh.qmin[0], sc->bvh.qmin[1], sc->bvh.qmin[2]);
     V.qstep = make_float3(sc->bvh.qstep[0], sc->bvh.qstep[1], sc->bvh.qstep[2]);
     V.tris = sc->bvh.d_tris;
@@ -338,9 +342,11 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         if (const char* e = getenv("RTB_TRAV_MINB")) c->trav_minb = atoi(e) == 5 ? 5 : (atoi(e) == 6 ? 6 : 4);
         if (c->trav_minb == 5) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 5>, WF_THREADS, smem_stack));
         else if (c->trav_minb == 6) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 6>, WF_THREADS, smem_stack));
+        else if (sc->view.wide) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 4, true>, WF_THREADS, smem_stack));
         else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false>, WF_THREADS, smem_stack));
         c->grid_ext = std::max(1, b) * prop.multiProcessorCount;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true>, WF_THREADS, smem_stack));
+        if (sc->view.wide) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true, 4, true>, WF_THREADS, smem_stack));
+        else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true>, WF_THREADS, smem_stack));
         c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<0>, SHADE_THREADS, smem_tab));
         c->grid_shade = std::max(1, b) * prop.multiProcessorCount;
@@ -507,7 +513,8 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 if (ge != cudaSuccess) break;
                 k_prepare<<<1, 1, 0, c->stream>>>(ag, k);
                 k_generate<<<c->grid_gen, WF_THREADS, smem_tab, c->stream>>>(ag, k);
-                if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
+                if (ag.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
+                else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 if (shade_mode == 1) k_shade<1><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
@@ -562,7 +569,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         }
         cudaEvent_t* ev = &c->ext_ev[3 * ext_iters];
         CU_TRY(cudaEventRecord(ev[0], c->stream));
-        if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+        if (count_work && a.S.wide) k_traverse<true, 4, true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+        else if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+        else if (a.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);

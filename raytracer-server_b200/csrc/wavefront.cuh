@@ -325,7 +325,7 @@ __device__ __forceinline__ bool warp_reserve(uint32_t* cursor, uint32_t count, u
 //   * any hit for the NEE candidates in shadow queue c                  (mutually_visible; accumulates if unoccluded)
 //   * closest hit for dead-MIS probes against a mesh light              (hit.id == light_source test)
 // Lanes refill individually from one work cursor, so the two ray kinds share warps and the tail is paid once.
-template <bool COUNT, int MINB = 4>
+template <bool COUNT, int MINB = 4, bool WIDE = false>
 __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<int*>(smem_raw) + threadIdx.x), sstride = blockDim.x * 4u;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
     const ShadowQueue SQ = a.sq[c];
     const int light_obj = a.S.hdr->light_obj;
     const int refill_below = a.tune_refill > 0 ? a.tune_refill : REFILL_BELOW;
-    const int steps = a.tune_steps > 0 ? a.tune_steps : INNER_STEPS;
+    const int steps = a.tune_steps > 0 ? a.tune_steps : (WIDE ? INNER_STEPS / 2 : INNER_STEPS);
     uint32_t work[2] = {0, 0};
     unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // first chunk: static (warp w owns [w*32, w*32+32)), later chunks from the atomic cursor, which k_prepare
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
                             slot = my;
                             kind = 0;
                             const float4 o4 = Q.o[my], d4 = Q.d[my];
-                            trav_begin(a.S, T, f3(o4), f3(d4), __float_as_uint(o4.w), h2.x, a.S.root);
+                            trav_begin(a.S, T, f3(o4), f3(d4), __float_as_uint(o4.w), h2.x, WIDE ? a.S.root4 : a.S.root);
                         }
                     } else {
                         const float4 d4 = SQ.d[my - n_ext];
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
                             const float4 o4 = SQ.o[slot];
                             kind = (__float_as_uint(SQ.c[slot].w) & SHADOW_PROBE) ? 2 : 1;
                             occluded = false;
-                            trav_begin(a.S, T, f3(o4), f3(d4), __float_as_uint(o4.w), d4.w, a.S.root);
+                            trav_begin(a.S, T, f3(o4), f3(d4), __float_as_uint(o4.w), d4.w, WIDE ? a.S.root4 : a.S.root);
                         }
                     }
                 }
@@ -413,7 +413,11 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
         // `steps` inner nodes per round, so lanes whose ray ended are not left idle behind one long descent.
         for (;;) {
             int trips = 0;
-            for (int k = 0; k < steps && T.node >= 0; ++k) { trav_inner<COUNT>(a.S, T, sbase, sstride, lstack, work); ++trips; }
+            for (int k = 0; k < steps && T.node >= 0; ++k) {
+                if (WIDE) trav_inner4<COUNT>(a.S, T, sbase, sstride, lstack, work);
+                else trav_inner<COUNT>(a.S, T, sbase, sstride, lstack, work);
+                ++trips;
+            }
             if (COUNT) {
                 int mx = trips;
                 for (int off = 16; off; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
@@ -935,7 +939,10 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace_rays(DevScene S, long long
         float t;
         uint32_t id;
         analytic_closest(sh, S.n_planes, S.n_prims, o, d, PC_NONE, t, id);
-        if (ray_hits_bvh_box(S, o, d, t)) bvh_traverse<false, COUNT>(S, sh, o, d, PC_NONE, t, id, 0.0f, work);
+        if (ray_hits_bvh_box(S, o, d, t)) {
+            if (S.wide) bvh_traverse<false, COUNT, true>(S, sh, o, d, PC_NONE, t, id, 0.0f, work);
+            else bvh_traverse<false, COUNT, false>(S, sh, o, d, PC_NONE, t, id, 0.0f, work);
+        }
         if (id == PC_NONE) {
             obj[i] = -1; tri[i] = -1; tout[i] = INFINITY;
         } else if (id < TRI_BASE) {
