@@ -537,11 +537,14 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
     uint32_t nbase = 0;                                      // lane 0: base of the chunk reserved ahead
     if (!exhausted && lane == 0) nbase = atomicAdd(&C->cursor_shade, SHADE_CHUNK);
 
-    // ---- lane state: the path being shaded + one prefetched queue entry
+    // ---- lane state: the path being shaded (registers) + one prefetched queue entry (shared memory, filled by per-thread
+    // asynchronous copies issued a trip before the entry is needed: it costs no registers while it waits)
+    __shared__ __align__(16) float4 spare[5][SHADE_THREADS];   // o | d | beta | triangle normal | hit (8 bytes used)
+    const uint32_t sp_o = (uint32_t)__cvta_generic_to_shared(&spare[0][threadIdx.x]);
+    constexpr uint32_t SP_D = SHADE_THREADS * 16u, SP_B = 2u * SP_D, SP_N = 3u * SP_D, SP_H = 4u * SP_D;
     bool cur_valid = false, cont = false, sp_valid = false, sp_nrm = false;
-    float2 h2 = make_float2(0.f, __uint_as_float(PC_NONE)), h2_n = h2;
+    float2 h2 = make_float2(0.f, __uint_as_float(PC_NONE));
     float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, b4 = o4, tri_n = o4;   // cont: tri_n carries the stale `o` instead
-    float4 o4_n = o4, d4_n = o4, b4_n = o4, tri_n_n = o4;
     uint32_t cur_slot = 0, sp_slot = 0;
     // output segments (warp-uniform): front / back class of the other path queue, shadow queue
     uint32_t f_base = 0, f_used = SHADE_SEG, b_base = 0, b_used = SHADE_SEG, s_base = 0, s_used = SHADE_SEG;
@@ -551,29 +554,31 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
     for (;;) {
         // (a) lanes without a path take their prefetched entry
         if (!cur_valid && sp_valid) {
-            h2 = h2_n; o4 = o4_n; d4 = d4_n; b4 = b4_n;
+            cp_async_wait_all();
+            h2 = lds_f2(sp_o + SP_H);
+            o4 = lds_f4(sp_o);
+            d4 = lds_f4(sp_o + SP_D);
+            b4 = lds_f4(sp_o + SP_B);
             cur_slot = sp_slot;
-            if (!sp_nrm) {
-                const uint32_t idn = __float_as_uint(h2_n.y);
-                tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idn != PC_NONE && idn != HIT_HOLE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
-            }
-            tri_n = tri_n_n;
-            cur_valid = __float_as_uint(h2.y) != HIT_HOLE;
+            const uint32_t idn = __float_as_uint(h2.y);
+            if (idn != PC_NONE && idn != HIT_HOLE && idn >= TRI_BASE)
+                tri_n = sp_nrm ? lds_f4(sp_o + SP_N) : __ldg(a.S.tri_nrm + (idn - TRI_BASE));
+            cur_valid = idn != HIT_HOLE;
             cont = false;
             sp_valid = false;
         }
-        // (b) refill the prefetch registers from the warp's chunk
+        // (b) refill the prefetch slot from the warp's chunk
         {
             const unsigned need = __ballot_sync(0xffffffffu, !sp_valid);
             if (need && wnext < wend) {
                 const uint32_t my = wnext + __popc(need & below);
                 if (!sp_valid && my < wend) {
                     sp_slot = slot_of(my);
-                    h2_n = Q.hit[sp_slot];
-                    o4_n = Q.o[sp_slot];
-                    d4_n = Q.d[sp_slot];
-                    b4_n = Q.beta[sp_slot];
+                    cp_async8(sp_o + SP_H, Q.hit + sp_slot);
+                    cp_async16(sp_o, Q.o + sp_slot);
+                    cp_async16(sp_o + SP_D, Q.d + sp_slot);
+                    cp_async16(sp_o + SP_B, Q.beta + sp_slot);
+                    cp_async_commit();
                     sp_valid = true;
                     sp_nrm = false;
                 }
@@ -817,10 +822,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
         }
         // ---- the prefetched entry's hit id has arrived by now -> start the dependent triangle-normal fetch
         if (sp_valid && !sp_nrm) {
-            const uint32_t idn = __float_as_uint(h2_n.y);
-            tri_n_n = make_float4(0.f, 0.f, 0.f, 0.f);
+            cp_async_wait_all();
+            const uint32_t idn = __float_as_uint(lds_f2(sp_o + SP_H).y);
             if (idn == HIT_HOLE) sp_valid = false;   // unfilled slot of the producer: ask for another entry next trip
-            else if (idn != PC_NONE && idn >= TRI_BASE) tri_n_n = __ldg(a.S.tri_nrm + (idn - TRI_BASE));
+            else if (idn != PC_NONE && idn >= TRI_BASE) {
+                cp_async16(sp_o + SP_N, a.S.tri_nrm + (idn - TRI_BASE));
+                cp_async_commit();
+            }
             sp_nrm = true;
         }
     }
