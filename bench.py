@@ -311,6 +311,10 @@ def main():
             gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                     "traffic": traffic_per_launch[kernel],
+                    # neither hot kernel is HBM bound (DESIGN.md "Rooflines"): what limits them is instruction issue, so the
+                    # ncu-measured issue utilisation and SIMD lanes per instruction of the committed profile ride along
+                    "issue_active_pct_ncu": traffic.get(kernel + "_issue_active_pct"),
+                    "lanes_per_instruction_ncu": traffic.get(kernel + "_lanes_per_instruction"),
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
                     "algorithmic_bytes_per_launch": nbytes / n_launch, "avg_launch_ms": ms / n_launch,
                     "share_of_step": ms / max(totals["render_ms"], 1e-9)}
@@ -344,7 +348,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "reference scene fixtures (tests/golden/scenes), Philox seeds per step",
             "config": {"workload": wl["name"], "width": W, "height": H, "spp": SPP, "samples_per_step": samples_per_step_total,
                        "parallelism": f"tiles32x32 interleaved x{world}" if world > 1 else "single GPU",
-                       "l2": "every iteration streams the path / shadow queues (several GB: 32 Mi path slots x 240 B at this frame size) and the 127 MiB accumulator buffer through HBM, far more than the 126 MB L2; no flush needed"},
+                       "l2": "no flush needed: every step re-traces the whole frame, streaming ~270 GB through HBM (path / shadow queue entries of the paths that leave registers + the 127 MiB accumulator buffer, cleared per step), far more than the 126 MB L2; only the 4 MB scene + LBVH is meant to stay cache-resident"},
             "mrays_per_s": rays / elapsed / 1e6,
             "rays_per_sample": rays / max(1.0, job["samples"]),
             "device_ms_per_step": totals["render_ms"] / max(1, args.steps),
