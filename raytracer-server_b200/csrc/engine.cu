@@ -463,8 +463,28 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     }
     a.accum = c->accum;
     a.ctrl = c->ctrl;
+    if (sc->fs.prims.size() <= 8)
+        for (size_t k = 0; k < sc->fs.prims.size(); ++k) {
+            const FlatPrim& P = sc->fs.prims[k];
+            a.ss.a[k] = make_float4(P.a[0], P.a[1], P.a[2], P.a[3]);
+            a.ss.r2[k] = P.b[0];
+            a.ss.group[k] = P.group;
+        }
     a.trav_warps = (uint32_t)c->grid_ext * (WF_THREADS / 32);
     a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
+}
+
+// k_shade instantiations: general | reference-scene fast paths | fast paths with the analytic table in the kernel
+// parameters, unrolled for 5 planes + 1..3 spheres (cubes, flying_unicorn, cornell_box)
+static void launch_shade(int mode, int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur) {
+#define RTB_SHADE(M, P, S) k_shade<M, P, S><<<grid, SHADE_THREADS, smem, st>>>(a, cur)
+    const bool small = mode != 0 && n_planes == 5 && n_spheres >= 1 && n_spheres <= 3 && !getenv("RTB_NO_SMALL_TABLE");
+    if (mode == 1 && small) { if (n_spheres == 1) RTB_SHADE(1, 5, 1); else if (n_spheres == 2) RTB_SHADE(1, 5, 2); else RTB_SHADE(1, 5, 3); }
+    else if (mode == 2 && small) { if (n_spheres == 1) RTB_SHADE(2, 5, 1); else if (n_spheres == 2) RTB_SHADE(2, 5, 2); else RTB_SHADE(2, 5, 3); }
+    else if (mode == 1) RTB_SHADE(1, 0, 0);
+    else if (mode == 2) RTB_SHADE(2, 0, 0);
+    else RTB_SHADE(0, 0, 0);
+#undef RTB_SHADE
 }
 
 // The wavefront loop: runs samples [ks_begin, ks_end) (ks = k*4 + sub-pixel) of every local pixel,
@@ -517,9 +537,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
-                if (shade_mode == 1) k_shade<1><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
-                else if (shade_mode == 2) k_shade<2><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
-                else k_shade<0><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(ag, k);
+                launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_shade, smem_tab, c->stream, ag, k);
                 ge = cudaStreamEndCapture(c->stream, &g);
                 if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->graph_exec[k], g, 0);
                 if (g) cudaGraphDestroy(g);
@@ -576,9 +594,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
         CU_TRY(cudaEventRecord(ev[1], c->stream));
-        if (shade_mode == 1) k_shade<1><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
-        else if (shade_mode == 2) k_shade<2><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
-        else k_shade<0><<<c->grid_shade, SHADE_THREADS, smem_tab, c->stream>>>(a, cur);
+        launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_shade, smem_tab, c->stream, a, cur);
         CU_TRY(cudaEventRecord(ev[2], c->stream));
         ++ext_iters;
         launches += 4;

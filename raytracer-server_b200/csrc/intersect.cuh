@@ -213,6 +213,43 @@ __device__ __forceinline__ void analytic_pair(const SharedScene& sh, int n_plane
     }
 }
 
+// The analytic table of a scene with at most 8 primitives, carried in the KERNEL PARAMETERS: with the loops unrolled
+// for a known (planes, spheres) count every coefficient is a constant-bank operand — no shared-memory loads, no loop
+// counters, and the chains of different primitives interleave freely.
+struct SmallScene {
+    float4 a[8];        // plane: n.xyz, dot(pos, n)   sphere: centre.xyz, r
+    float r2[8];
+    int32_t group[8];
+};
+template <int NP, int NS>
+__device__ __forceinline__ void analytic_pair_small(const SmallScene& ss, int og, float3 o, uint32_t origin, float3 d1, float& t1,
+                                                    uint32_t& id1, float3 d2, float tlim2, bool& occ2) {
+    t1 = INFINITY;
+    id1 = PC_NONE;
+    occ2 = false;
+    const uint32_t oid = origin & PC_ID_MASK;
+    const float2 dx = f2(d1.x, d2.x), dy = f2(d1.y, d2.y), dz = f2(d1.z, d2.z);
+    const float self_num = (origin & PC_FLIPPED) ? SURF_OFFSET : -SURF_OFFSET;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const float4 A = ss.a[k];
+        const float num = ss.group[k] == og ? self_num : A.w - (o.x * A.x + o.y * A.y + o.z * A.z);   // plane_num
+        bool ok1, ok2;
+        const float2 t = plane_t2(A, num, dx, dy, dz, ok1, ok2);
+        if (ok1 && t.x < t1) { t1 = t.x; id1 = (uint32_t)k; }
+        occ2 |= ok2 && t.y < tlim2;
+    }
+#pragma unroll
+    for (int k = NP; k < NP + NS; ++k) {
+        const float4 A = ss.a[k];
+        const float3 op = f3(A) - o;
+        bool ok1, ok2;
+        const float2 t = sphere_t2(op, ss.r2[k], dx, dy, dz, (uint32_t)k == oid, ok1, ok2);
+        if (ok1 && t.x < t1) { t1 = t.x; id1 = (uint32_t)k; }
+        occ2 |= ok2 && t.y < tlim2;
+    }
+}
+
 // ---- LBVH traversal ------------------------------------------------------------------------
 // Per-lane traversal state.  The stack lives in shared memory (first STACK_SMEM levels, one column per
 // thread) and spills to a local array beyond that.

@@ -82,6 +82,7 @@ struct RenderArgs {
     int width, height, spp, num_samples;
     uint32_t ks_done;    // samples resolved so far, in (k*4 + sub-pixel) units; 4*num_samples for a finished frame
     PhiloxKeys keys;     // round keys of the frame's seed
+    SmallScene ss;       // analytic table of small scenes (k_shade<MODE, NP, NS> with NP > 0)
     int estimator;
     int rank, world, tiles_x, tiles_y, n_local_tiles;
     uint32_t P, SP;          // most paths / shadow rays alive at once
@@ -500,11 +501,12 @@ __device__ __forceinline__ uint32_t seg_slot(uint32_t base, uint32_t k) { return
 // New paths come from the current queue: a warp owns one static chunk of SHADE_CHUNK entries and then reserves
 // further chunks from a work cursor one chunk ahead; every lane holds one PREFETCHED entry, so the (streaming)
 // queue loads of a new path are issued a whole trip before they are needed.
+// NP > 0: the scene has exactly NP planes + NS spheres (<= 8) and its table rides in the kernel parameters (SmallScene).
 // MODE 1 / 2 (FAST) = the reference scenes' case, resolved at compile time: Diffuse / Specular materials only, sphere
 // light, no probe items; 1 = live NEE estimator, 2 = the dead "MIS" branch.  MODE 0, the general instantiation, keeps
 // every branch at run time (both estimators, Phong, mesh lights, rtb_sample_radiance probes).
-template <int MODE>
-__global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderArgs a, int c) {
+template <int MODE, int NP = 0, int NS = 0>
+__global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const __grid_constant__ RenderArgs a, int c) {
     constexpr bool FAST = MODE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevCtrl* C = a.ctrl;
@@ -754,7 +756,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(RenderA
                         float ta;
                         uint32_t ida;
                         bool occ;
-                        analytic_pair(sh, n_planes, n_prims, hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
+                        if (NP > 0) analytic_pair_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
+                        else analytic_pair(sh, n_planes, n_prims, hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
                         if (want_sh && !occ) {
                             if (ray_hits_bvh_box(a.S, hg.pos, sh_dir, sh_tlim)) {
                                 sh_push = true;
