@@ -337,7 +337,7 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         CU_TRY(cudaFuncSetAttribute(k_shade<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CU_TRY(cudaFuncSetAttribute(k_shade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CU_TRY(cudaFuncSetAttribute(k_shade<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        CU_TRY(cudaFuncSetAttribute(k_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaFuncSetAttribute(k_generate<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         int b = 0;
         if (const char* e = getenv("RTB_TRAV_MINB")) c->trav_minb = atoi(e) == 5 ? 5 : (atoi(e) == 6 ? 6 : 4);
         if (c->trav_minb == 5) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 5>, WF_THREADS, smem_stack));
@@ -350,7 +350,7 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<0>, SHADE_THREADS, smem_tab));
         c->grid_shade = std::max(1, b) * prop.multiProcessorCount;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate, WF_THREADS, smem_tab));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate<0, 0>, WF_THREADS, smem_tab));
         c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
         // experiment knobs: CTAs per SM of the two persistent kernels (two concurrent renders can then share every SM)
         if (const char* e = getenv("RTB_TRAV_CTAS")) c->grid_ext = c->grid_ext_count = std::max(1, atoi(e)) * prop.multiProcessorCount;
@@ -474,6 +474,13 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
 }
 
+static void launch_generate(int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur) {
+    const bool small = n_planes == 5 && n_spheres >= 1 && n_spheres <= 3 && !getenv("RTB_NO_SMALL_TABLE");
+    if (!small) k_generate<0, 0><<<grid, WF_THREADS, smem, st>>>(a, cur);
+    else if (n_spheres == 1) k_generate<5, 1><<<grid, WF_THREADS, smem, st>>>(a, cur);
+    else if (n_spheres == 2) k_generate<5, 2><<<grid, WF_THREADS, smem, st>>>(a, cur);
+    else k_generate<5, 3><<<grid, WF_THREADS, smem, st>>>(a, cur);
+}
 // k_shade instantiations: general | reference-scene fast paths | fast paths with the analytic table in the kernel
 // parameters, unrolled for 5 planes + 1..3 spheres (cubes, flying_unicorn, cornell_box)
 static void launch_shade(int mode, int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur) {
@@ -532,7 +539,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 ge = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
                 if (ge != cudaSuccess) break;
                 k_prepare<<<1, 1, 0, c->stream>>>(ag, k);
-                k_generate<<<c->grid_gen, WF_THREADS, smem_tab, c->stream>>>(ag, k);
+                launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, ag, k);
                 if (ag.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
                 else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
@@ -579,7 +586,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     while (!done) {
         if (cancel && *cancel) { cancelled = true; break; }
         k_prepare<<<1, 1, 0, c->stream>>>(a, cur);
-        k_generate<<<c->grid_gen, WF_THREADS, smem_tab, c->stream>>>(a, cur);
+        launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, a, cur);
         while (c->ext_ev.size() < 3 * (ext_iters + 1)) {
             cudaEvent_t e0;
             CU_TRY(cudaEventCreate(&e0));

@@ -250,6 +250,30 @@ __device__ __forceinline__ void analytic_pair_small(const SmallScene& ss, int og
     }
 }
 
+template <int NP, int NS>
+__device__ __forceinline__ void analytic_closest_small(const SmallScene& ss, int og, float3 o, float3 d, uint32_t origin, float& best_t,
+                                                       uint32_t& best_id) {
+    best_t = INFINITY;
+    best_id = PC_NONE;
+    const uint32_t oid = origin & PC_ID_MASK;
+    const float self_num = (origin & PC_FLIPPED) ? SURF_OFFSET : -SURF_OFFSET;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const float4 A = ss.a[k];
+        const float num = ss.group[k] == og ? self_num : A.w - (o.x * A.x + o.y * A.y + o.z * A.z);
+        bool ok;
+        const float t = plane_t(A, num, d, ok);
+        if (ok && t < best_t) { best_t = t; best_id = (uint32_t)k; }
+    }
+#pragma unroll
+    for (int k = NP; k < NP + NS; ++k) {
+        const float4 A = ss.a[k];
+        bool ok;
+        const float t = sphere_t(f3(A) - o, ss.r2[k], d, (uint32_t)k == oid, ok);
+        if (ok && t < best_t) { best_t = t; best_id = (uint32_t)k; }
+    }
+}
+
 // ---- LBVH traversal ------------------------------------------------------------------------
 // Per-lane traversal state.  The stack lives in shared memory (first STACK_SMEM levels, one column per
 // thread) and spills to a local array beyond that.

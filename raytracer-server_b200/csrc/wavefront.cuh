@@ -232,7 +232,8 @@ __global__ void k_prepare(RenderArgs a, int c) {
 }
 
 // ---------------------------------------------------------------- k_generate
-__global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
+template <int NP = 0, int NS = 0>
+__global__ void __launch_bounds__(WF_THREADS) k_generate(const __grid_constant__ RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevCtrl* C = a.ctrl;
     const uint32_t n = C->gen_count;
@@ -277,7 +278,8 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(RenderArgs a, int c) {
                 float3 dir = camera_dir(a.cam, x, a.height - y - 1, sub & 1, sub >> 1, tent(r.x), tent(r.y), w, h);
                 float ta;
                 uint32_t ida;
-                analytic_closest(sh, a.S.n_planes, a.S.n_prims, a.cam.pos, dir, PC_NONE, ta, ida);
+                if (NP > 0) analytic_closest_small<NP, NS>(a.ss, -1, a.cam.pos, dir, PC_NONE, ta, ida);
+                else analytic_closest(sh, a.S.n_planes, a.S.n_prims, a.cam.pos, dir, PC_NONE, ta, ida);
                 front = ray_hits_bvh_box(a.S, a.cam.pos, dir, ta);
                 o4 = make_float4(a.cam.pos.x, a.cam.pos.y, a.cam.pos.z, __uint_as_float(PC_NONE));
                 d4 = make_float4(dir.x, dir.y, dir.z, __uint_as_float(acc));
@@ -710,7 +712,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                                     ++n_sh;
                                     float ta;
                                     uint32_t ida;
-                                    analytic_closest(sh, n_planes, n_prims, hg.pos, i2, hg.pcode, ta, ida);
+                                    if (NP > 0) analytic_closest_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, i2, hg.pcode, ta, ida);
+                                    else analytic_closest(sh, n_planes, n_prims, hg.pos, i2, hg.pcode, ta, ida);
                                     const bool needs_bvh = ray_hits_bvh_box(a.S, hg.pos, i2, ta);
                                     if (!light_is_mesh) {
                                         // the light is analytic: it must be the nearest analytic hit and no triangle may lie in front of it
