@@ -131,6 +131,14 @@ __device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
     return v;
 }
+// atomicAdd as ONE instruction.  nvcc rewrites atomicAdd(uniform address) into a warp-aggregated sequence (VOTE / POPC /
+// ATOMG by the leader / SHFL of the result), and the SHFL waits for the atomic's round trip on the spot — which defeats a
+// reservation that is issued ahead precisely so that nobody waits for it.  Called by one lane; the result is read later.
+__device__ __forceinline__ uint32_t atomic_add_lane(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
 // Vec3::flip_across (src/geometry.rs:99-101)
 __device__ __forceinline__ float3 flip_across(float3 s, float3 axis) { return (2.0f * dot(s, axis)) * axis - s; }
 

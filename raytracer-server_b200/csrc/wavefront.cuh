@@ -470,7 +470,7 @@ __device__ __forceinline__ uint32_t seg_alloc(uint32_t& base, uint32_t& used, bo
     const uint32_t step = (uint32_t)(DIR * (int)SHADE_SEG);
     uint32_t slot;
     if (used + n > SHADE_SEG) {   // runs over into the next segment
-        if (!has_next && lane == cls) nb = atomicAdd(ctr, step);
+        if (!has_next && lane == cls) nb = atomic_add_lane(ctr, step);
         uint32_t nbase = __shfl_sync(0xffffffffu, nb, cls);
         if (DIR < 0) nbase -= 1u;   // element 0 of a downward segment sits just below the old tail
         slot = r < SHADE_SEG ? base + (uint32_t)(DIR * (int)r) : nbase + (uint32_t)(DIR * (int)(r - SHADE_SEG));
@@ -482,7 +482,7 @@ __device__ __forceinline__ uint32_t seg_alloc(uint32_t& base, uint32_t& used, bo
         used += n;
     }
     if (!has_next && used + 64u > SHADE_SEG) {
-        if (lane == cls) nb = atomicAdd(ctr, step);
+        if (lane == cls) nb = atomic_add_lane(ctr, step);
         has_next = true;
     }
     return slot;
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
     bool exhausted = count <= a.shade_warps * SHADE_CHUNK;   // no dynamic chunks in a small launch: no atomics at all
     const bool big_launch = count > a.shade_warps * SHADE_CHUNK * 8u;
     uint32_t nbase = 0;                                      // lane 0: base of the chunk reserved ahead
-    if (!exhausted && lane == 0) nbase = atomicAdd(&C->cursor_shade, SHADE_CHUNK);
+    if (!exhausted && lane == 0) nbase = atomic_add_lane(&C->cursor_shade, SHADE_CHUNK);
 
     // ---- lane state: the path being shaded (registers) + one prefetched queue entry (shared memory, filled by per-thread
     // asynchronous copies issued a trip before the entry is needed: it costs no registers while it waits)
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                 else {
                     wnext = b;
                     wend = min(b + SHADE_CHUNK, count);
-                    if (lane == 0) nbase = atomicAdd(&C->cursor_shade, SHADE_CHUNK);
+                    if (lane == 0) nbase = atomic_add_lane(&C->cursor_shade, SHADE_CHUNK);
                 }
             }
         }
