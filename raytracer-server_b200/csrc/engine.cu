@@ -463,6 +463,11 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     }
     a.accum = c->accum;
     a.ctrl = c->ctrl;
+    for (const FlatPrim& P : sc->fs.prims)
+        if (P.obj == sc->fs.light_obj && sc->fs.light_geom == GEOM_SPHERE) {
+            a.light_sphere = make_float4(P.a[0], P.a[1], P.a[2], P.a[3]);
+            a.light_pdf = 1.0f / (4.0f * 3.14159265358979323846f * P.a[3] * P.a[3]);
+        }
     if (sc->fs.prims.size() <= 8)
         for (size_t k = 0; k < sc->fs.prims.size(); ++k) {
             const FlatPrim& P = sc->fs.prims[k];
@@ -474,6 +479,14 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
 }
 
+static RenderArgs with_cur(const RenderArgs& a, int cur) {
+    RenderArgs r = a;
+    r.qin = a.q[cur];
+    r.qout = a.q[1 - cur];
+    r.sqin = a.sq[cur];
+    r.sqout = a.sq[1 - cur];
+    return r;
+}
 static void launch_generate(int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur) {
     const bool small = n_planes == 5 && n_spheres >= 1 && n_spheres <= 3 && !getenv("RTB_NO_SMALL_TABLE");
     if (!small) k_generate<0, 0><<<grid, WF_THREADS, smem, st>>>(a, cur);
@@ -539,12 +552,13 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 ge = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
                 if (ge != cudaSuccess) break;
                 k_prepare<<<1, 1, 0, c->stream>>>(ag, k);
-                launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, ag, k);
-                if (ag.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
-                else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
-                else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
-                else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ag, k);
-                launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_shade, smem_tab, c->stream, ag, k);
+                const RenderArgs agk = with_cur(ag, k);   // queue pointers of this parity, resolved here
+                launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, agk, k);
+                if (ag.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
+                else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
+                else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
+                else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
+                launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_shade, smem_tab, c->stream, agk, k);
                 ge = cudaStreamEndCapture(c->stream, &g);
                 if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->graph_exec[k], g, 0);
                 if (g) cudaGraphDestroy(g);
@@ -586,7 +600,8 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     while (!done) {
         if (cancel && *cancel) { cancelled = true; break; }
         k_prepare<<<1, 1, 0, c->stream>>>(a, cur);
-        launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, a, cur);
+        const RenderArgs ac = with_cur(a, cur);
+        launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, ac, cur);
         while (c->ext_ev.size() < 3 * (ext_iters + 1)) {
             cudaEvent_t e0;
             CU_TRY(cudaEventCreate(&e0));
@@ -594,14 +609,14 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         }
         cudaEvent_t* ev = &c->ext_ev[3 * ext_iters];
         CU_TRY(cudaEventRecord(ev[0], c->stream));
-        if (count_work && a.S.wide) k_traverse<true, 4, true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
-        else if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
-        else if (a.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
-        else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
-        else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
-        else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+        if (count_work && a.S.wide) k_traverse<true, 4, true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
+        else if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
+        else if (a.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
+        else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
+        else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
+        else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
         CU_TRY(cudaEventRecord(ev[1], c->stream));
-        launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_shade, smem_tab, c->stream, a, cur);
+        launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_shade, smem_tab, c->stream, ac, cur);
         CU_TRY(cudaEventRecord(ev[2], c->stream));
         ++ext_iters;
         launches += 4;

@@ -170,6 +170,19 @@ __device__ __forceinline__ void brdf_sample(const DevMaterial& m, float3 n, floa
     }
 }
 
+// sphere light with its constants in the kernel parameters (the FAST instantiations): same arithmetic as the sphere
+// branch of light_sample below
+__device__ __forceinline__ void light_sample_sphere(const float4 L, float pdf_const, float4 xi, float3& y, float3& ny, float& pdf) {
+    float z = 2.0f * xi.x - 1.0f;
+    float r = fast_sqrt(fmaxf(1.0f - z * z, 0.0f));
+    float s, c;
+    sincos_2pi(xi.y, s, c);
+    float3 n = normalize(f3(r * c, r * s, z));
+    y = f3(L) + n * L.w;
+    ny = n;
+    pdf = pdf_const;
+}
+
 // ---- Geometry::sample for the light (src/geometry.rs:573-595); xi = {u1, u2, -, select} --------
 template <bool FAST = false>
 __device__ __forceinline__ void light_sample(const DevScene& S, const DevPrim* prims, const DevSceneHeader* hdr, float4 xi,

@@ -88,6 +88,12 @@ struct RenderArgs {
     uint32_t P, SP;          // most paths / shadow rays alive at once
     uint32_t Pcap, SPcap;    // physical slots per queue: P, SP + room for the unfilled tails of k_shade's per-warp segments
     PathQueue q[2];
+    // the queues of THIS launch, resolved on the host (q[c], q[1 - c], sq[c], sq[1 - c]): plain constant-bank pointers
+    // instead of parameter arrays indexed by a run-time `c`
+    PathQueue qin, qout;
+    ShadowQueue sqin, sqout;
+    float4 light_sphere;     // centre | radius of a sphere light
+    float light_pdf;         // 1 / (4 pi r^2)
     ShadowQueue sq[2];   // sq[c] is read by k_traverse(c) and was written by k_shade(1-c)
     float4* accum;       // [pixel*4 + sub] -> (r, g, b, -) sums
     DevCtrl* ctrl;
@@ -290,10 +296,10 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(const __grid_constant__
         PushSlots ps = push_all(&C->ext_head(c), &C->ext_tail(c), &C->sh_head(c), valid, front, false, false);
         if (valid && ps.ext >= a.Pcap) { atomicAdd(&C->overflow, 1u); valid = false; }
         if (valid) {
-            a.q[c].o[ps.ext] = o4;
-            a.q[c].d[ps.ext] = d4;
-            a.q[c].beta[ps.ext] = b4;
-            a.q[c].hit[ps.ext] = h2;
+            a.qin.o[ps.ext] = o4;
+            a.qin.d[ps.ext] = d4;
+            a.qin.beta[ps.ext] = b4;
+            a.qin.hit[ps.ext] = h2;
             ++made;
             made_bvh += front ? 1u : 0u;
         }
@@ -329,7 +335,7 @@ __device__ __forceinline__ bool warp_reserve(uint32_t* cursor, uint32_t count, u
 //   * closest hit for dead-MIS probes against a mesh light              (hit.id == light_source test)
 // Lanes refill individually from one work cursor, so the two ray kinds share warps and the tail is paid once.
 template <bool COUNT, int MINB = 4, bool WIDE = false>
-__global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int c) {
+__global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_constant__ RenderArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<int*>(smem_raw) + threadIdx.x), sstride = blockDim.x * 4u;
     int lstack[STACK_LOCAL];
@@ -337,8 +343,8 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(RenderArgs a, int
     const uint32_t n_ext = C->ext_head(c);   // only the BVH class of the path queue needs a traversal
     const uint32_t count = n_ext + C->sh_head(c);
     const unsigned lane = threadIdx.x & 31;
-    const PathQueue Q = a.q[c];
-    const ShadowQueue SQ = a.sq[c];
+    const PathQueue& Q = a.qin;
+    const ShadowQueue& SQ = a.sqin;
     const int light_obj = a.S.hdr->light_obj;
     const int refill_below = a.tune_refill > 0 ? a.tune_refill : REFILL_BELOW;
     const int steps = a.tune_steps > 0 ? a.tune_steps : (WIDE ? INNER_STEPS / 2 : INNER_STEPS);
@@ -519,14 +525,14 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
     const SharedScene sh = stage_scene(a.S, smem_raw, false);
     const unsigned lane = threadIdx.x & 31;
     const unsigned below = (1u << lane) - 1u;
-    const PathQueue Q = a.q[c], N = a.q[1 - c];
+    const PathQueue &Q = a.qin, &N = a.qout;
     const int light_obj = hdr->light_obj;
     const bool light_is_mesh = FAST ? false : hdr->light_geom == 2;
     const bool mis = MODE == 1 ? false : (MODE == 2 ? true : a.estimator != 0);
     const bool probe_mode = FAST ? false : a.probe_px != nullptr;
     const float3 Le = f3(sh.mats[light_obj].emitted);
     const int n_prims = a.S.n_prims, n_planes = a.S.n_planes;
-    const ShadowQueue SQ = a.sq[1 - c];
+    const ShadowQueue& SQ = a.sqout;
     uint32_t* const ctr_front = &C->ext_head(1 - c);
     uint32_t* const ctr_back = &C->ext_tail(1 - c);
     uint32_t* const ctr_sh = &C->sh_head(1 - c);
@@ -671,7 +677,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                         // ---- direct light
                         float3 y, ny;
                         float pdf_a;
-                        light_sample<FAST>(a.S, sh.prims, hdr, r0, y, ny, pdf_a);
+                        if (FAST) light_sample_sphere(a.light_sphere, a.light_pdf, r0, y, ny, pdf_a);
+                        else light_sample<FAST>(a.S, sh.prims, hdr, r0, y, ny, pdf_a);
                         float3 dv = y - hg.pos;
                         float r2 = dot(dv, dv);
                         float inv_dist = rsqrtf(r2);
@@ -703,7 +710,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                             if (i2.x != 0.f || i2.y != 0.f || i2.z != 0.f) {
                                 float3 y2, ny2;
                                 float pdf_a2;
-                                light_sample<FAST>(a.S, sh.prims, hdr, rng_block(rng_pixel, sample, depth, 3u, a.keys), y2, ny2, pdf_a2);
+                                if (FAST) light_sample_sphere(a.light_sphere, a.light_pdf, rng_block(rng_pixel, sample, depth, 3u, a.keys), y2, ny2, pdf_a2);
+                                else light_sample<FAST>(a.S, sh.prims, hdr, rng_block(rng_pixel, sample, depth, 3u, a.keys), y2, ny2, pdf_a2);
                                 float3 dv2 = y2 - hg.pos;
                                 float pdf_light2 = pdf_a2 * (dot(dv2, dv2) / dot(ny2, -i2));
                                 float3 c2 = beta * Le * brdf_eval<FAST>(mat, hg.n, ovec, i2) * (dot(hg.n, i2) / (pdf2 + pdf_light2));
