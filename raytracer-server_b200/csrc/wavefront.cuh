@@ -422,10 +422,18 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_cons
         // `steps` inner nodes per round, so lanes whose ray ended are not left idle behind one long descent.
         for (;;) {
             int trips = 0;
-            for (int k = 0; k < steps && T.node >= 0; ++k) {
-                if (WIDE) trav_inner4<COUNT>(a.S, T, sbase, sstride, lstack, work);
-                else trav_inner<COUNT>(a.S, T, sbase, sstride, lstack, work);
-                ++trips;
+            if (!COUNT && !WIDE && steps == INNER_STEPS) {   // default knob: unrolled, no loop counter
+#pragma unroll
+                for (int k = 0; k < INNER_STEPS; ++k) {
+                    if (T.node < 0) break;
+                    trav_inner<COUNT>(a.S, T, sbase, sstride, lstack, work);
+                }
+            } else {
+                for (int k = 0; k < steps && T.node >= 0; ++k) {
+                    if (WIDE) trav_inner4<COUNT>(a.S, T, sbase, sstride, lstack, work);
+                    else trav_inner<COUNT>(a.S, T, sbase, sstride, lstack, work);
+                    ++trips;
+                }
             }
             if (COUNT) {
                 int mx = trips;
