@@ -498,9 +498,11 @@ static void launch_generate(int n_planes, int n_spheres, int grid, size_t smem, 
 // parameters, unrolled for 5 planes + 1..3 spheres (cubes, flying_unicorn, cornell_box)
 static void launch_shade(int mode, int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur) {
 #define RTB_SHADE(M, P, S) k_shade<M, P, S><<<grid, SHADE_THREADS, smem, st>>>(a, cur)
-    const bool small = mode != 0 && n_planes == 5 && n_spheres >= 1 && n_spheres <= 3 && !getenv("RTB_NO_SMALL_TABLE");
+    const bool small = mode != 0 && n_planes == 5 && n_spheres >= 1 && n_spheres <= 3 && !getenv("RTB_NO_SMALL_TABLE") && !getenv("RTB_GENERIC_TABLE");
     if (mode == 1 && small) { if (n_spheres == 1) RTB_SHADE(1, 5, 1); else if (n_spheres == 2) RTB_SHADE(1, 5, 2); else RTB_SHADE(1, 5, 3); }
     else if (mode == 2 && small) { if (n_spheres == 1) RTB_SHADE(2, 5, 1); else if (n_spheres == 2) RTB_SHADE(2, 5, 2); else RTB_SHADE(2, 5, 3); }
+    else if (mode == 1 && n_planes + n_spheres <= 8 && !getenv("RTB_NO_SMALL_TABLE")) RTB_SHADE(1, 8, 0);   // any small scene: generic unrolled table
+    else if (mode == 2 && n_planes + n_spheres <= 8 && !getenv("RTB_NO_SMALL_TABLE")) RTB_SHADE(2, 8, 0);
     else if (mode == 1) RTB_SHADE(1, 0, 0);
     else if (mode == 2) RTB_SHADE(2, 0, 0);
     else RTB_SHADE(0, 0, 0);

@@ -250,6 +250,32 @@ __device__ __forceinline__ void analytic_pair_small(const SmallScene& ss, int og
     }
 }
 
+// Any scene with at most 8 analytic primitives: unrolled over the 8 slots, each slot guarded by warp-uniform tests of
+// the run-time counts (planes first, then spheres) — still constant-bank operands, no shared-memory loads, no loop counter.
+__device__ __forceinline__ void analytic_pair_small8(const SmallScene& ss, int n_planes, int n_prims, int og, float3 o, uint32_t origin,
+                                                     float3 d1, float& t1, uint32_t& id1, float3 d2, float tlim2, bool& occ2) {
+    t1 = INFINITY;
+    id1 = PC_NONE;
+    occ2 = false;
+    const uint32_t oid = origin & PC_ID_MASK;
+    const float2 dx = f2(d1.x, d2.x), dy = f2(d1.y, d2.y), dz = f2(d1.z, d2.z);
+    const float self_num = (origin & PC_FLIPPED) ? SURF_OFFSET : -SURF_OFFSET;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 A = ss.a[k];
+        bool ok1 = false, ok2 = false;
+        float2 t = f2(0.f, 0.f);
+        if (k < n_planes) {
+            const float num = ss.group[k] == og ? self_num : A.w - (o.x * A.x + o.y * A.y + o.z * A.z);
+            t = plane_t2(A, num, dx, dy, dz, ok1, ok2);
+        } else if (k < n_prims) {
+            t = sphere_t2(f3(A) - o, ss.r2[k], dx, dy, dz, (uint32_t)k == oid, ok1, ok2);
+        }
+        if (ok1 && t.x < t1) { t1 = t.x; id1 = (uint32_t)k; }
+        occ2 |= ok2 && t.y < tlim2;
+    }
+}
+
 template <int NP, int NS>
 __device__ __forceinline__ void analytic_closest_small(const SmallScene& ss, int og, float3 o, float3 d, uint32_t origin, float& best_t,
                                                        uint32_t& best_id) {

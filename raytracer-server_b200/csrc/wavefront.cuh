@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                                     ++n_sh;
                                     float ta;
                                     uint32_t ida;
-                                    if (NP > 0) analytic_closest_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, i2, hg.pcode, ta, ida);
+                                    if (NP > 0 && NP < 8) analytic_closest_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, i2, hg.pcode, ta, ida);
                                     else analytic_closest(sh, n_planes, n_prims, hg.pos, i2, hg.pcode, ta, ida);
                                     const bool needs_bvh = ray_hits_bvh_box(a.S, hg.pos, i2, ta);
                                     if (!light_is_mesh) {
@@ -775,7 +775,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                         float ta;
                         uint32_t ida;
                         bool occ;
-                        if (NP > 0) analytic_pair_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
+                        if (NP == 8) analytic_pair_small8(a.ss, n_planes, n_prims, origin_group_of(sh, hg.pcode), hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
+                        else if (NP > 0) analytic_pair_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
                         else analytic_pair(sh, n_planes, n_prims, hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
                         if (want_sh && !occ) {
                             if (ray_hits_bvh_box(a.S, hg.pos, sh_dir, sh_tlim)) {
