@@ -83,6 +83,25 @@ __device__ __forceinline__ bool ray_hits_bvh_box(const DevScene& S, float3 o, fl
     return tmin <= tfar * 1.000002f + 1e-6f;
 }
 
+// the same test for TWO rays leaving one point (extension ray | shadow ray of a vertex): the box-minus-origin terms are
+// shared, the slab products are packed FP32x2, and the two chains interleave instead of sitting in separate branches
+__device__ __forceinline__ void ray_pair_hits_bvh_box(const DevScene& S, float3 o, float3 d1, float tmax1, float3 d2, float tmax2,
+                                                      bool& hit1, bool& hit2) {
+    hit1 = hit2 = false;
+    if (S.n_tris == 0) return;
+    auto inv = [](float d) { return fast_rcp(fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); };
+    const float2 ix = f2(inv(d1.x), inv(d2.x)), iy = f2(inv(d1.y), inv(d2.y)), iz = f2(inv(d1.z), inv(d2.z));
+    const float2 x0 = __fmul2_rn(bc(S.bvh_min.x - o.x), ix), x1 = __fmul2_rn(bc(S.bvh_max.x - o.x), ix);
+    const float2 y0 = __fmul2_rn(bc(S.bvh_min.y - o.y), iy), y1 = __fmul2_rn(bc(S.bvh_max.y - o.y), iy);
+    const float2 z0 = __fmul2_rn(bc(S.bvh_min.z - o.z), iz), z1 = __fmul2_rn(bc(S.bvh_max.z - o.z), iz);
+    const float tmin1 = fmaxf(fmaxf(fminf(x0.x, x1.x), fminf(y0.x, y1.x)), fmaxf(fminf(z0.x, z1.x), 0.0f));
+    const float tfar1 = fminf(fminf(fmaxf(x0.x, x1.x), fmaxf(y0.x, y1.x)), fminf(fmaxf(z0.x, z1.x), tmax1));
+    const float tmin2 = fmaxf(fmaxf(fminf(x0.y, x1.y), fminf(y0.y, y1.y)), fmaxf(fminf(z0.y, z1.y), 0.0f));
+    const float tfar2 = fminf(fminf(fmaxf(x0.y, x1.y), fmaxf(y0.y, y1.y)), fminf(fmaxf(z0.y, z1.y), tmax2));
+    hit1 = tmin1 <= tfar1 * 1.000002f + 1e-6f;
+    hit2 = tmin2 <= tfar2 * 1.000002f + 1e-6f;
+}
+
 // ---- analytic primitives -------------------------------------------------------------------
 // prims[0, n_planes) are planes, the rest spheres; every lane walks the same table (no divergence) and the
 // tests are written as selects.  `origin` = pcode of the primitive the ray starts on (PC_NONE id for camera /

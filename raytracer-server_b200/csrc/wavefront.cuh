@@ -778,8 +778,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                         if (NP == 8) analytic_pair_small8(a.ss, n_planes, n_prims, origin_group_of(sh, hg.pcode), hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
                         else if (NP > 0) analytic_pair_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
                         else analytic_pair(sh, n_planes, n_prims, hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
+                        bool ext_box, sh_box;   // can the two rays still reach the mesh box?  (both at once: shared terms, packed products)
+                        ray_pair_hits_bvh_box(a.S, hg.pos, next_dir, ta, sh_dir, sh_tlim, ext_box, sh_box);
                         if (want_sh && !occ) {
-                            if (ray_hits_bvh_box(a.S, hg.pos, sh_dir, sh_tlim)) {
+                            if (sh_box) {
                                 sh_push = true;
                                 ++n_sh_bvh;
                                 so = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
@@ -790,7 +792,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                             }
                         }
                         if (ext_push) {
-                            ext_front = ray_hits_bvh_box(a.S, hg.pos, next_dir, ta);
+                            ext_front = ext_box;
                             ed = make_float4(next_dir.x, next_dir.y, next_dir.z, __uint_as_float(acc));
                             eh = make_float2(ta, __uint_as_float(ida));
                             ++n_ext;
