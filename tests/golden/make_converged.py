@@ -19,7 +19,7 @@ from oracle import oracle as O  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "converged")
 W, H, SPP, SEED = 600, 450, 4096, 7     # the reference server's frame size (src/server.rs:29-30)
-JOBS = [("cornell_box", 0), ("cubes", 0), ("cubes", 1), ("flying_unicorn", 0), ("cornell_box", 1)]
+JOBS = [("cornell_box", 0), ("cubes", 0), ("cubes", 1), ("flying_unicorn", 0), ("cornell_box", 1), ("flying_unicorn", 1)]
 
 if __name__ == "__main__":
     threads = int(sys.argv[1]) if len(sys.argv) > 1 else (os.cpu_count() or 1)
