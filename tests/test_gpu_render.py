@@ -83,6 +83,25 @@ def test_paths_stay_in_registers(gpu_scene):
     assert st2["rays_bvh"] - st2["rays_primary"] <= st2["paths_queued"] < 0.35 * st2["rays_extension"]
 
 
+@pytest.mark.parametrize("use_mis", [False, True])
+def test_analytic_table_variants_agree(gpu_scene, monkeypatch, use_mis):
+    # k_shade reads the plane / sphere table (a) from the kernel parameters with loops unrolled for the exact counts of the
+    # reference scenes, (b) from the kernel parameters through a generic 8-slot form, (c) from shared memory in a loop.
+    # Same arithmetic in the same order per ray -> the same frame (up to the order of the fp32 atomic adds).
+    for name in ("cornell_box", "flying_unicorn"):
+        g = gpu_scene(name)
+        ref = g.render(200, 150, 16, seed=21, use_mis=use_mis).astype(int)
+        st_ref = g.stats()
+        for var in ("RTB_GENERIC_TABLE", "RTB_NO_SMALL_TABLE"):
+            monkeypatch.setenv(var, "1")
+            f = g.render(200, 150, 16, seed=21, use_mis=use_mis).astype(int)
+            st = g.stats()
+            monkeypatch.delenv(var)
+            assert np.abs(f - ref).max() <= 1, (name, var)
+            for k in ("rays_extension", "rays_shadow", "rays_bvh", "shadow_bvh"):
+                assert st[k] == st_ref[k], (name, var, k)
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_tile_shards_reassemble_the_frame(gpu_scene, rtb, world):
     # per-pixel RNG counters are independent of the sharding, so the union of the ranks' tiles is the
