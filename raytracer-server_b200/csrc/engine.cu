@@ -498,6 +498,12 @@ static void launch_generate(int n_planes, int n_spheres, int grid, size_t smem, 
 // parameters, unrolled for 5 planes + 1..3 spheres (cubes, flying_unicorn, cornell_box)
 static void launch_shade(int mode, int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur) {
 #define RTB_SHADE(M, P, S) k_shade<M, P, S><<<grid, SHADE_THREADS, smem, st>>>(a, cur)
+    if (a.S.n_tris == 0 && mode != 0 && n_planes == 5 && n_spheres == 3 && !getenv("RTB_NO_SMALL_TABLE") && !getenv("RTB_GENERIC_TABLE")) {
+        // cornell_box: analytic primitives only
+        if (mode == 1) k_shade<1, 5, 3, false><<<grid, SHADE_THREADS, smem, st>>>(a, cur);
+        else k_shade<2, 5, 3, false><<<grid, SHADE_THREADS, smem, st>>>(a, cur);
+        return;
+    }
     const bool small = mode != 0 && n_planes == 5 && n_spheres >= 1 && n_spheres <= 3 && !getenv("RTB_NO_SMALL_TABLE") && !getenv("RTB_GENERIC_TABLE");
     if (mode == 1 && small) { if (n_spheres == 1) RTB_SHADE(1, 5, 1); else if (n_spheres == 2) RTB_SHADE(1, 5, 2); else RTB_SHADE(1, 5, 3); }
     else if (mode == 2 && small) { if (n_spheres == 1) RTB_SHADE(2, 5, 1); else if (n_spheres == 2) RTB_SHADE(2, 5, 2); else RTB_SHADE(2, 5, 3); }

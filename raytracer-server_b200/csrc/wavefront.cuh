@@ -517,11 +517,12 @@ __device__ __forceinline__ uint32_t seg_slot(uint32_t base, uint32_t k) { return
 // New paths come from the current queue: a warp owns one static chunk of SHADE_CHUNK entries and then reserves
 // further chunks from a work cursor one chunk ahead; every lane holds one PREFETCHED entry, so the (streaming)
 // queue loads of a new path are issued a whole trip before they are needed.
+// MESH = false: the scene has no triangles — the box tests and the front / shadow queue code vanish at compile time.
 // NP > 0: the scene has exactly NP planes + NS spheres (<= 8) and its table rides in the kernel parameters (SmallScene).
 // MODE 1 / 2 (FAST) = the reference scenes' case, resolved at compile time: Diffuse / Specular materials only, sphere
 // light, no probe items; 1 = live NEE estimator, 2 = the dead "MIS" branch.  MODE 0, the general instantiation, keeps
 // every branch at run time (both estimators, Phong, mesh lights, rtb_sample_radiance probes).
-template <int MODE, int NP = 0, int NS = 0>
+template <int MODE, int NP = 0, int NS = 0, bool MESH = true>
 __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const __grid_constant__ RenderArgs a, int c) {
     constexpr bool FAST = MODE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                                     uint32_t ida;
                                     if (NP > 0 && NP < 8) analytic_closest_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, i2, hg.pcode, ta, ida);
                                     else analytic_closest(sh, n_planes, n_prims, hg.pos, i2, hg.pcode, ta, ida);
-                                    const bool needs_bvh = ray_hits_bvh_box(a.S, hg.pos, i2, ta);
+                                    const bool needs_bvh = MESH ? ray_hits_bvh_box(a.S, hg.pos, i2, ta) : false;
                                     if (!light_is_mesh) {
                                         // the light is analytic: it must be the nearest analytic hit and no triangle may lie in front of it
                                         if (ida != PC_NONE && sh.prims[ida].obj == light_obj) {
@@ -779,7 +780,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
                         else if (NP > 0) analytic_pair_small<NP, NS>(a.ss, origin_group_of(sh, hg.pcode), hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
                         else analytic_pair(sh, n_planes, n_prims, hg.pos, hg.pcode, next_dir, ta, ida, sh_dir, sh_tlim, occ);
                         bool ext_box, sh_box;   // can the two rays still reach the mesh box?  (both at once: shared terms, packed products)
-                        ray_pair_hits_bvh_box(a.S, hg.pos, next_dir, ta, sh_dir, sh_tlim, ext_box, sh_box);
+                        if (MESH) ray_pair_hits_bvh_box(a.S, hg.pos, next_dir, ta, sh_dir, sh_tlim, ext_box, sh_box);
+                        else ext_box = sh_box = false;   // no triangles in the scene: no ray ever leaves this kernel for k_traverse
                         if (want_sh && !occ) {
                             if (sh_box) {
                                 sh_push = true;
