@@ -70,6 +70,7 @@ struct RenderContext {
     unsigned long long* d_state = nullptr;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one iteration (4 kernels) for cur = 0 / 1 ...
     std::vector<unsigned char> graph_args;                 // ... captured for exactly these kernel arguments
+    int grid_shade_nomesh = 0;   // grid of the mesh-less k_shade instantiation (160-thread CTAs)
     int trav_minb = 4;   // CTAs per SM the launched k_traverse instantiation was compiled for (RTB_TRAV_MINB = 4 | 5 | 6)
     int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0, grid_shade = 0;
 
@@ -350,6 +351,8 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<0>, SHADE_THREADS, smem_tab));
         c->grid_shade = std::max(1, b) * prop.multiProcessorCount;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<1, 5, 3, false, SHADE_THREADS_NOMESH>, SHADE_THREADS_NOMESH, smem_tab));
+        c->grid_shade_nomesh = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate<0, 0>, WF_THREADS, smem_tab));
         c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
         // experiment knobs: CTAs per SM of the two persistent kernels (two concurrent renders can then share every SM)
@@ -357,7 +360,7 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         if (const char* e = getenv("RTB_SHADE_CTAS")) c->grid_shade = std::max(1, atoi(e)) * prop.multiProcessorCount;
     }
     // every k_shade warp may leave up to two unfilled SHADE_SEG segments per queue class behind in each iteration
-    const uint32_t seg_room = (uint32_t)c->grid_shade * (SHADE_THREADS / 32) * 2u * SHADE_SEG;
+    const uint32_t seg_room = (uint32_t)std::max(c->grid_shade * (SHADE_THREADS / 32), c->grid_shade_nomesh * (SHADE_THREADS_NOMESH / 32)) * 2u * SHADE_SEG;
     if (c->P != P) {
         cudaFree(c->qbuf);
         c->qbuf = nullptr;
@@ -496,12 +499,16 @@ static void launch_generate(int n_planes, int n_spheres, int grid, size_t smem, 
 }
 // k_shade instantiations: general | reference-scene fast paths | fast paths with the analytic table in the kernel
 // parameters, unrolled for 5 planes + 1..3 spheres (cubes, flying_unicorn, cornell_box)
+static bool shade_is_nomesh(int mode, const RenderArgs& a) {
+    return a.S.n_tris == 0 && mode != 0 && a.S.n_planes == 5 && a.S.n_prims - a.S.n_planes == 3 && !getenv("RTB_NO_SMALL_TABLE") &&
+           !getenv("RTB_GENERIC_TABLE");
+}
 static void launch_shade(int mode, int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur) {
 #define RTB_SHADE(M, P, S) k_shade<M, P, S><<<grid, SHADE_THREADS, smem, st>>>(a, cur)
-    if (a.S.n_tris == 0 && mode != 0 && n_planes == 5 && n_spheres == 3 && !getenv("RTB_NO_SMALL_TABLE") && !getenv("RTB_GENERIC_TABLE")) {
+    if (shade_is_nomesh(mode, a)) {
         // cornell_box: analytic primitives only
-        if (mode == 1) k_shade<1, 5, 3, false><<<grid, SHADE_THREADS, smem, st>>>(a, cur);
-        else k_shade<2, 5, 3, false><<<grid, SHADE_THREADS, smem, st>>>(a, cur);
+        if (mode == 1) k_shade<1, 5, 3, false, SHADE_THREADS_NOMESH><<<grid, SHADE_THREADS_NOMESH, smem, st>>>(a, cur);
+        else k_shade<2, 5, 3, false, SHADE_THREADS_NOMESH><<<grid, SHADE_THREADS_NOMESH, smem, st>>>(a, cur);
         return;
     }
     const bool small = mode != 0 && n_planes == 5 && n_spheres >= 1 && n_spheres <= 3 && !getenv("RTB_NO_SMALL_TABLE") && !getenv("RTB_GENERIC_TABLE");
@@ -544,6 +551,10 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     bool fast_shade = !a.probe_px && sc->fs.light_geom == GEOM_SPHERE && !getenv("RTB_NO_FAST_SHADE");
     for (const FlatMaterial& m : sc->fs.materials) fast_shade = fast_shade && m.brdf != BRDF_PHONG;
     const int shade_mode = !fast_shade ? 0 : (a.estimator == 0 ? 1 : 2);
+    // the mesh-less instantiation runs 160-thread CTAs: its grid and warp count (static first chunks, k_prepare) differ
+    const bool nomesh = shade_is_nomesh(shade_mode, a);
+    const int grid_shade = nomesh ? c->grid_shade_nomesh : c->grid_shade;
+    a.shade_warps = (uint32_t)grid_shade * (uint32_t)((nomesh ? SHADE_THREADS_NOMESH : SHADE_THREADS) / 32);
     const bool use_graph = !count_work && a.P <= (1u << 21) && !getenv("RTB_NO_GRAPH");
     if (use_graph && !done) {
         RenderArgs ag = a;
@@ -566,7 +577,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
                 else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
                 else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
-                launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_shade, smem_tab, c->stream, agk, k);
+                launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, agk, k);
                 ge = cudaStreamEndCapture(c->stream, &g);
                 if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->graph_exec[k], g, 0);
                 if (g) cudaGraphDestroy(g);
@@ -624,7 +635,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
         else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
         CU_TRY(cudaEventRecord(ev[1], c->stream));
-        launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_shade, smem_tab, c->stream, ac, cur);
+        launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, ac, cur);
         CU_TRY(cudaEventRecord(ev[2], c->stream));
         ++ext_iters;
         launches += 4;

@@ -522,15 +522,16 @@ __device__ __forceinline__ uint32_t seg_slot(uint32_t base, uint32_t k) { return
 // MODE 1 / 2 (FAST) = the reference scenes' case, resolved at compile time: Diffuse / Specular materials only, sphere
 // light, no probe items; 1 = live NEE estimator, 2 = the dead "MIS" branch.  MODE 0, the general instantiation, keeps
 // every branch at run time (both estimators, Phong, mesh lights, rtb_sample_radiance probes).
-template <int MODE, int NP = 0, int NS = 0, bool MESH = true>
-__global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const __grid_constant__ RenderArgs a, int c) {
+constexpr int SHADE_THREADS_NOMESH = 160;   // the mesh-less instantiation needs 96 registers: 4 CTAs of 160 threads = 20 warps per SM
+template <int MODE, int NP = 0, int NS = 0, bool MESH = true, int THREADS = SHADE_THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_MINB : 640 / THREADS) k_shade(const __grid_constant__ RenderArgs a, int c) {
     constexpr bool FAST = MODE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevCtrl* C = a.ctrl;
     const DevSceneHeader* hdr = a.S.hdr;
     const uint32_t head = C->ext_head(c), tail = C->ext_tail(c);
     const uint32_t count = head + (a.Pcap - tail);
-    if (blockIdx.x * (SHADE_THREADS / 32) * SHADE_CHUNK >= count) return;   // CTA beyond the static region of a small launch
+    if (blockIdx.x * (THREADS / 32) * SHADE_CHUNK >= count) return;   // CTA beyond the static region of a small launch
     const SharedScene sh = stage_scene(a.S, smem_raw, false);
     const unsigned lane = threadIdx.x & 31;
     const unsigned below = (1u << lane) - 1u;
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
     auto slot_of = [&](uint32_t i) { return i < head ? i : tail + (i - head); };
 
     // ---- work fetch (warp-uniform): static first chunk, then chunks from the cursor, reserved one ahead
-    const uint32_t gwarp = (blockIdx.x * SHADE_THREADS + threadIdx.x) >> 5;
+    const uint32_t gwarp = (blockIdx.x * THREADS + threadIdx.x) >> 5;
     uint32_t wnext = min(gwarp * SHADE_CHUNK, count), wend = min(gwarp * SHADE_CHUNK + SHADE_CHUNK, count);
     bool exhausted = count <= a.shade_warps * SHADE_CHUNK;   // no dynamic chunks in a small launch: no atomics at all
     const bool big_launch = count > a.shade_warps * SHADE_CHUNK * 8u;
@@ -558,9 +559,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, RTB_SHADE_MINB) k_shade(const _
 
     // ---- lane state: the path being shaded (registers) + one prefetched queue entry (shared memory, filled by per-thread
     // asynchronous copies issued a trip before the entry is needed: it costs no registers while it waits)
-    __shared__ __align__(16) float4 spare[5][SHADE_THREADS];   // o | d | beta | triangle normal | hit (8 bytes used)
+    __shared__ __align__(16) float4 spare[5][THREADS];   // o | d | beta | triangle normal | hit (8 bytes used)
     const uint32_t sp_o = (uint32_t)__cvta_generic_to_shared(&spare[0][threadIdx.x]);
-    constexpr uint32_t SP_D = SHADE_THREADS * 16u, SP_B = 2u * SP_D, SP_N = 3u * SP_D, SP_H = 4u * SP_D;
+    constexpr uint32_t SP_D = THREADS * 16u, SP_B = 2u * SP_D, SP_N = 3u * SP_D, SP_H = 4u * SP_D;
     bool cur_valid = false, cont = false, sp_valid = false, sp_nrm = false;
     float2 h2 = make_float2(0.f, __uint_as_float(PC_NONE));
     float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, b4 = o4, tri_n = o4;   // cont: tri_n carries the stale `o` instead
