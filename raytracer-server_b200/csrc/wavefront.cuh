@@ -515,10 +515,11 @@ __device__ __forceinline__ uint32_t seg_slot(uint32_t base, uint32_t k) { return
 //     (at most ONE shadow entry and ONE path entry per input path and iteration: the queue capacities hold)
 //   * path ends (roulette, dead surface, miss)  -> lane takes a new path
 // New paths come from the current queue: a warp owns one static chunk of SHADE_CHUNK entries and then reserves
-// further chunks from a work cursor one chunk ahead; every lane holds one PREFETCHED entry, so the (streaming)
-// queue loads of a new path are issued a whole trip before they are needed.
+// further chunks from a work cursor one chunk ahead; every lane holds one PREFETCHED entry (in shared memory, filled by
+// per-thread cp.async copies), so the (streaming) queue loads of a new path are issued a whole trip before they are needed.
 // MESH = false: the scene has no triangles — the box tests and the front / shadow queue code vanish at compile time.
-// NP > 0: the scene has exactly NP planes + NS spheres (<= 8) and its table rides in the kernel parameters (SmallScene).
+// NP > 0: the scene has exactly NP planes + NS spheres (<= 8) and its table rides in the kernel parameters (SmallScene);
+// NP = 8, NS = 0: any scene with <= 8 analytic primitives (generic 8-slot form, run-time counts).
 // MODE 1 / 2 (FAST) = the reference scenes' case, resolved at compile time: Diffuse / Specular materials only, sphere
 // light, no probe items; 1 = live NEE estimator, 2 = the dead "MIS" branch.  MODE 0, the general instantiation, keeps
 // every branch at run time (both estimators, Phong, mesh lights, rtb_sample_radiance probes).
