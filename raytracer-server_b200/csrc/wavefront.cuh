@@ -30,8 +30,14 @@ constexpr uint32_t SHADOW_PROBE = 0x80000000u;  // shadow entry = dead-MIS probe
 constexpr uint32_t MAX_DEPTH_FIELD = 4095u;
 constexpr uint32_t FETCH_CHUNK = 32;     // ray indices a warp reserves per atomic
 constexpr int REFILL_BELOW = 28;         // default: refill a warp when fewer than this many lanes are still traversing
-constexpr uint32_t SHADE_CHUNK = 32;     // queue entries a k_shade warp reserves per atomic
-constexpr int SHADE_PARK_BELOW = 12;      // k_shade tail: park the paths of a warp with fewer live lanes than this once the queue is drained
+#ifndef RTB_PARK_BELOW
+#define RTB_PARK_BELOW 20
+#endif
+#ifndef RTB_SHADE_CHUNK
+#define RTB_SHADE_CHUNK 64
+#endif
+constexpr uint32_t SHADE_CHUNK = RTB_SHADE_CHUNK;     // queue entries a k_shade warp reserves per atomic
+constexpr int SHADE_PARK_BELOW = RTB_PARK_BELOW;      // k_shade tail: park the paths of a warp with fewer live lanes than this once the queue is drained
 constexpr uint32_t SHADE_SEG = 128;      // OUTPUT slots a k_shade warp reserves per atomic in each queue class
 constexpr uint32_t HIT_HOLE = 0xffffffffu;       // path-queue slot reserved by a k_shade warp but never filled (hit.y)
 constexpr uint32_t TLIM_HOLE = 0xff800000u;      // same for the shadow queue (d.w = -inf)
