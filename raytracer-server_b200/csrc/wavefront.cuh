@@ -157,9 +157,6 @@ __device__ __forceinline__ PushSlots push_all(uint32_t* ext_head, uint32_t* ext_
     return r;
 }
 
-// Block-aggregated variant for k_shade: the 8 warps of a CTA pool their counts in shared memory and
-// three threads issue ONE atomic per counter per CTA iteration (fewer same-address atomics at L2).
-// Every thread of the CTA must call it (two __syncthreads inside).
 #ifndef RTB_SHADE_THREADS
 #define RTB_SHADE_THREADS 256
 #endif
@@ -167,46 +164,6 @@ __device__ __forceinline__ PushSlots push_all(uint32_t* ext_head, uint32_t* ext_
 #define RTB_SHADE_MINB (512 / RTB_SHADE_THREADS)
 #endif
 constexpr int SHADE_THREADS = RTB_SHADE_THREADS;   // CTA size of k_shade (warps are independent: only occupancy depends on it)
-struct BlockPushSmem {
-    uint32_t cnt[SHADE_THREADS / 32][4];
-    uint32_t base[SHADE_THREADS / 32][4];
-};
-__device__ __forceinline__ PushSlots push_all_block(BlockPushSmem& sm, uint32_t* ext_head, uint32_t* ext_tail, uint32_t* sh_head,
-                                                    bool ext_push, bool ext_front, bool sh_push, bool pr_push) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned mf = __ballot_sync(0xffffffffu, ext_push && ext_front);
-    const unsigned mb = __ballot_sync(0xffffffffu, ext_push && !ext_front);
-    const unsigned ms = __ballot_sync(0xffffffffu, sh_push);
-    const unsigned mp = __ballot_sync(0xffffffffu, pr_push);
-    if (lane == 0) {
-        sm.cnt[warp][0] = __popc(mf);
-        sm.cnt[warp][1] = __popc(mb);
-        sm.cnt[warp][2] = __popc(ms) + __popc(mp);
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        const int cls = threadIdx.x;
-        uint32_t tot = 0;
-#pragma unroll
-        for (int w = 0; w < SHADE_THREADS / 32; ++w) tot += sm.cnt[w][cls];
-        uint32_t b = 0;
-        if (tot) b = cls == 0 ? atomicAdd(ext_head, tot) : (cls == 1 ? atomicSub(ext_tail, tot) : atomicAdd(sh_head, tot));
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < SHADE_THREADS / 32; ++w) {
-            sm.base[w][cls] = cls == 1 ? b - run : b + run;   // back class grows downward
-            run += sm.cnt[w][cls];
-        }
-    }
-    __syncthreads();
-    const uint32_t bf = sm.base[warp][0], bb = sm.base[warp][1], bs = sm.base[warp][2];
-    const unsigned below = (1u << lane) - 1u;
-    PushSlots r;
-    r.ext = ext_front ? bf + __popc(mf & below) : bb - 1u - __popc(mb & below);
-    r.sh = bs + __popc(ms & below);
-    r.pr = bs + __popc(ms) + __popc(mp & below);
-    return r;
-}
 
 __device__ __forceinline__ void accum_add(float4* accum, uint32_t idx, float3 v) {
     atomicAdd(&accum[idx], make_float4(v.x, v.y, v.z, 0.0f));  // one 128-bit RED (sm_90+)
