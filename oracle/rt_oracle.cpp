@@ -3,10 +3,15 @@
 // TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
 //
-// PARITY UNPINNED: the reference (Rust) cannot be compiled here (no cargo/rustc) and its
-// only unit test (`test_octants`, src/geometry.rs:1115-1131) pins octant numbering only;
-// that test is reproduced in tests/test_oracle_pins.py.  Everything numerical is pinned by
-// hand-derived known-answer tests in tests/, not by reference outputs.
+// PARITY PINS: the reference (Rust) cannot be compiled here (no cargo/rustc) and holds no golden vectors; its
+// only unit test (`test_octants`, src/geometry.rs:1115-1131) pins octant numbering and is reproduced in
+// tests/test_oracle_pins.py.  What the reference DOES ship are three images its own renderer wrote
+// (examples/cornell_box.png, examples/cubes.png, raytracer.gif); tests/test_reference_pins.py checks that this
+// oracle, in the reference's real mode (octree traversal + live NEE), reproduces them region by region on the
+// oracle-vs-oracle noise floor (50x50 tile means 0.26 % / 0.41 %, channel means 0.03 %, noise level 0.03 %,
+// clamp loss and firefly count) — fixtures in tests/golden/reference_pins.npz, generator make_reference_pins.py.
+// Still UNPINNED by any reference output: individual random sequences (the reference is OS-seeded), the dead
+// "MIS" branch (no image of it exists), Phong and mesh lights (no reference scene uses them).
 // The reference's RNG is rand 0.8.5 (Cargo.lock:556-557; ChaCha12 thread_rng, OS-seeded,
 // source not under /root/reference).  Its sequences cannot be matched, only its
 // distributions; this oracle draws from Philox4x32-10 (Salmon et al. 2011) with a

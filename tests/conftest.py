@@ -62,3 +62,48 @@ def gpu_scene(rtb):
 
 
 NCPU = os.cpu_count() or 1
+
+
+# ---- measured parity numbers: every parity test records what it measured (not only whether it passed); the session
+# writes them to gpurun_out/parity_{gpu,cpu}.json (override: $RTB_PARITY_OUT) — the GPU file is committed per round as
+# profiles/parity_rNN.json
+_parity = {}
+
+
+@pytest.fixture(scope="session")
+def parity_log():
+    def log(key, **values):
+        def conv(v):
+            import numpy as np
+
+            if isinstance(v, np.ndarray):
+                return [conv(x) for x in v.tolist()]
+            if isinstance(v, (np.floating, np.integer, np.bool_)):
+                return v.item()
+            if isinstance(v, (list, tuple)):
+                return [conv(x) for x in v]
+            return v
+
+        _parity.setdefault(key, {}).update({k: conv(v) for k, v in values.items()})
+
+    return log
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _parity:
+        return
+    import json
+
+    gpu = any(k.startswith("gpu/") for k in _parity)
+    path = os.environ.get("RTB_PARITY_OUT") or os.path.join(ROOT, "gpurun_out", "parity_gpu.json" if gpu else "parity_cpu.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        old = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                old = json.load(f)
+        old.update(_parity)
+        with open(path, "w") as f:
+            json.dump(old, f, indent=1, sort_keys=True)
+    except Exception as e:  # never fail a test run over the report
+        print(f"parity log not written: {e}")
