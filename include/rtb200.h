@@ -111,7 +111,7 @@ typedef struct rtb_stats {
     uint64_t bvh_tri_tests;
     double render_ms;        /* CUDA-event time of the whole device-side render */
     double extend_ms;        /* CUDA-event time of k_traverse (all LBVH queries: closest + any hit), summed over launches */
-    double shadow_ms;        /* reserved (shadow rays are traversed inside k_traverse) */
+    double bin_ms;           /* CUDA-event time of the coherence binning in front of k_traverse (k_bin_keys / _scan / _scatter) */
     double generate_ms;
     double resolve_ms;
     double shade_ms;         /* k_shade */

@@ -44,7 +44,7 @@ class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays_primary", C.c_uint64), ("rays_extension", C.c_uint64),
                 ("rays_shadow", C.c_uint64), ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("bvh_node_visits", C.c_uint64), ("bvh_tri_tests", C.c_uint64), ("render_ms", C.c_double),
-                ("extend_ms", C.c_double), ("shadow_ms", C.c_double), ("generate_ms", C.c_double),
+                ("extend_ms", C.c_double), ("bin_ms", C.c_double), ("generate_ms", C.c_double),
                 ("resolve_ms", C.c_double), ("shade_ms", C.c_double), ("rays_bvh", C.c_uint64),
                 ("shadow_bvh", C.c_uint64), ("paths_queued", C.c_uint64)]
 

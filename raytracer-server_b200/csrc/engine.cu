@@ -54,12 +54,15 @@ struct RenderContext {
     float4* sbuf = nullptr;      // 2 shadow queues x 3 arrays x SP
     float4* accum = nullptr;
     size_t accum_cap = 0;
+    uint32_t* bin_buf = nullptr;     // coherence binning: keys | perm (Pcap + SPcap each)
+    size_t bin_cap = 0;
+    uint32_t* bin_hist = nullptr;    // histogram | offsets (BIN_MAX + 1 each)
     DevCtrl* ctrl = nullptr;
     uint32_t* h_active = nullptr;  // pinned ring of read-backs
     static constexpr int RING = 16;
     cudaEvent_t ring_ev[RING] = {};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    std::vector<cudaEvent_t> ext_ev;  // per iteration: 3 events bracketing k_traverse | k_shade
+    std::vector<cudaEvent_t> ext_ev;  // per iteration: 4 events bracketing k_bin_* | k_traverse | k_shade
     unsigned char* d_rgb = nullptr;
     size_t rgb_cap = 0;
     unsigned char* h_rgb = nullptr;   // pinned
@@ -72,12 +75,13 @@ struct RenderContext {
     std::vector<unsigned char> graph_args;                 // ... captured for exactly these kernel arguments
     int grid_shade_nomesh = 0;   // grid of the mesh-less k_shade instantiation (160-thread CTAs)
     int trav_minb = 4;   // CTAs per SM the launched k_traverse instantiation was compiled for (RTB_TRAV_MINB = 4 | 5 | 6)
-    int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0, grid_shade = 0;
+    int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0, grid_shade = 0, grid_bin = 0;
 
     ~RenderContext() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         cudaFree(qbuf); cudaFree(sbuf); cudaFree(accum); cudaFree(ctrl); cudaFree(d_rgb); cudaFree(d_probe);
+        cudaFree(bin_buf); cudaFree(bin_hist);
         if (h_active) cudaFreeHost(h_active);
         if (h_state) cudaFreeHost((void*)h_state);
         for (auto& e : graph_exec) if (e) cudaGraphExecDestroy(e);
@@ -355,6 +359,7 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         c->grid_shade_nomesh = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generate<0, 0>, WF_THREADS, smem_tab));
         c->grid_gen = std::max(1, b) * prop.multiProcessorCount;
+        c->grid_bin = 8 * prop.multiProcessorCount;
         // experiment knobs: CTAs per SM of the two persistent kernels (two concurrent renders can then share every SM)
         if (const char* e = getenv("RTB_TRAV_CTAS")) c->grid_ext = c->grid_ext_count = std::max(1, atoi(e)) * prop.multiProcessorCount;
         if (const char* e = getenv("RTB_SHADE_CTAS")) c->grid_shade = std::max(1, atoi(e)) * prop.multiProcessorCount;
@@ -384,6 +389,20 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         c->accum = nullptr;
         CU_TRY(cudaMalloc((void**)&c->accum, accum_elems * sizeof(float4)));
         c->accum_cap = accum_elems;
+    }
+    if (sc->view.n_tris > 0) {   // coherence binning of the LBVH rays (scenes without triangles never traverse)
+        const size_t need = (size_t)c->Pcap + c->SPcap;
+        if (c->bin_cap < need) {
+            cudaFree(c->bin_buf);
+            c->bin_buf = nullptr;
+            c->bin_cap = 0;
+            CU_TRY(cudaMalloc((void**)&c->bin_buf, need * 2 * sizeof(uint32_t)));
+            c->bin_cap = need;
+        }
+        if (!c->bin_hist) {
+            CU_TRY(cudaMalloc((void**)&c->bin_hist, (size_t)(BIN_MAX + 1) * 2 * sizeof(uint32_t)));
+            CU_TRY(cudaMemsetAsync(c->bin_hist, 0, (size_t)(BIN_MAX + 1) * 2 * sizeof(uint32_t), c->stream));
+        }
     }
     return RTB_OK;
 }
@@ -426,6 +445,22 @@ uint32_t default_pool(const rtb_params* p) {
     }
     P = std::max<uint64_t>(P, 1024);
     return (uint32_t)((P + 31ull) & ~31ull);
+}
+
+// library default of the coherence binning (cell bits per axis, 0 = off); RTB_BIN_BITS overrides it
+int default_bin_bits() {
+    static const int v = [] {
+        const char* e = getenv("RTB_BIN_BITS");
+        return e ? std::min(std::max(atoi(e), 0), BIN_MAX_BITS) : 0;
+    }();
+    return v;
+}
+
+void launch_binning(RenderContext* c, const RenderArgs& a, int cur) {
+    if (a.bin_bits <= 0) return;
+    k_bin_keys<<<c->grid_bin, WF_THREADS, 0, c->stream>>>(a, cur);
+    k_bin_scan<<<1, BIN_SCAN_THREADS, 0, c->stream>>>(a);
+    k_bin_scatter<<<c->grid_bin, WF_THREADS, 0, c->stream>>>(a, cur);
 }
 
 void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, RenderArgs& a) {
@@ -480,6 +515,15 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
         }
     a.trav_warps = (uint32_t)c->grid_ext * (WF_THREADS / 32);
     a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
+    // coherence binning: rtb_params.reserved[3] = 0 library default | 1 off | 2..5 cell bits per axis; reserved[4] & 1 = octant-major keys
+    int bits = p->reserved[3] == 0 ? default_bin_bits() : (p->reserved[3] == 1 ? 0 : std::min(std::max(p->reserved[3], 2), BIN_MAX_BITS));
+    if (sc->view.n_tris == 0 || !c->bin_buf) bits = 0;
+    a.bin_bits = bits;
+    a.bin_octant_major = p->reserved[4] & 1;
+    a.bin_key = c->bin_buf;
+    a.bin_perm = c->bin_buf ? c->bin_buf + c->bin_cap : nullptr;
+    a.bin_hist = c->bin_hist;
+    a.bin_offs = c->bin_hist ? c->bin_hist + (BIN_MAX + 1) : nullptr;
 }
 
 static RenderArgs with_cur(const RenderArgs& a, int cur) {
@@ -573,6 +617,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 k_prepare<<<1, 1, 0, c->stream>>>(ag, k);
                 const RenderArgs agk = with_cur(ag, k);   // queue pointers of this parity, resolved here
                 launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, agk, k);
+                launch_binning(c, agk, k);
                 if (ag.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
                 else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
                 else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
@@ -595,7 +640,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
             if (cancel && *cancel) { cancelled = true; break; }
             ge = cudaGraphLaunch(exec[cur], c->stream);
             if (ge != cudaSuccess) break;
-            launches += 4;
+            launches += a.bin_bits > 0 ? 7 : 4;
             ++it;
             cur ^= 1;
             for (;;) {   // {iteration, live paths} as published by the newest k_prepare that has run
@@ -621,12 +666,14 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         k_prepare<<<1, 1, 0, c->stream>>>(a, cur);
         const RenderArgs ac = with_cur(a, cur);
         launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, ac, cur);
-        while (c->ext_ev.size() < 3 * (ext_iters + 1)) {
+        while (c->ext_ev.size() < 4 * (ext_iters + 1)) {
             cudaEvent_t e0;
             CU_TRY(cudaEventCreate(&e0));
             c->ext_ev.push_back(e0);
         }
-        cudaEvent_t* ev = &c->ext_ev[3 * ext_iters];
+        cudaEvent_t* ev = &c->ext_ev[4 * ext_iters];
+        CU_TRY(cudaEventRecord(ev[3], c->stream));
+        launch_binning(c, ac, cur);
         CU_TRY(cudaEventRecord(ev[0], c->stream));
         if (count_work && a.S.wide) k_traverse<true, 4, true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
         else if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
@@ -638,7 +685,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, ac, cur);
         CU_TRY(cudaEventRecord(ev[2], c->stream));
         ++ext_iters;
-        launches += 4;
+        launches += a.bin_bits > 0 ? 7 : 4;
         // lagged, non-blocking termination test: read back `active` (state after this iteration's
         // k_prepare) into a pinned ring; the host keeps launching until a completed read-back says 0.
         int slot = (int)(it % RenderContext::RING);
@@ -663,13 +710,15 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     CU_TRY(cudaGetLastError());
     float ms = 0;
     CU_TRY(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
-    double ext_ms = 0, shade_ms = 0, shadow_ms = 0;
+    double ext_ms = 0, shade_ms = 0, shadow_ms = 0;   // shadow_ms: the binning kernels (rtb_stats.bin_ms)
     for (size_t k = 0; k < ext_iters; ++k) {
         float m = 0;
-        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[3 * k], c->ext_ev[3 * k + 1]));
+        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[4 * k], c->ext_ev[4 * k + 1]));
         ext_ms += m;
-        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[3 * k + 1], c->ext_ev[3 * k + 2]));
+        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[4 * k + 1], c->ext_ev[4 * k + 2]));
         shade_ms += m;
+        CU_TRY(cudaEventElapsedTime(&m, c->ext_ev[4 * k + 3], c->ext_ev[4 * k]));
+        shadow_ms += m;
     }
     if (h.overflow) return fail(RTB_ECUDA, "internal error: " + std::to_string(h.overflow) + " queue slots beyond the physical capacity were refused (frame is incomplete)");
     st.samples += h.samples;
@@ -687,7 +736,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     st.render_ms += ms;
     st.extend_ms += ext_ms;
     st.shade_ms += shade_ms;
-    st.shadow_ms += shadow_ms;
+    st.bin_ms += shadow_ms;
     st.rays_bvh += h.rays_bvh;
     st.shadow_bvh += h.shadow_bvh;
     st.paths_queued += h.paths_queued;

@@ -114,6 +114,13 @@ struct RenderArgs {
     volatile unsigned long long* host_state;
     uint32_t trav_warps;   // warps in the k_traverse grid: each owns the static first chunk [w*32, w*32+32)
     uint32_t shade_warps;  // same for k_shade
+    // coherence binning of the LBVH rays (k_bin_*): perm[i] = queue index of the i-th ray in bin order; nullptr = queue order
+    uint32_t* bin_key;     // [Pcap + SPcap]
+    uint32_t* bin_perm;    // [Pcap + SPcap]
+    uint32_t* bin_hist;    // [BIN_MAX + 1], zero between iterations
+    uint32_t* bin_offs;    // [BIN_MAX + 1]
+    int bin_bits;          // cell bits per axis (0 = binning off); bins = 8 octants x 2^(3 bits)
+    int bin_octant_major;
 };
 
 // ---------------------------------------------------------------- tile order <-> pixels
@@ -278,6 +285,103 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(const __grid_constant__
     }
 }
 
+// ---------------------------------------------------------------- coherence binning of the LBVH rays
+// k_traverse's warps lose half their lanes to divergence when the 32 rays of a warp walk unrelated parts of the tree
+// (incoherent bounce rays in queue order).  Before each traversal the rays of the iteration — the front class of the
+// path queue and the queued shadow rays — are therefore BINNED by (cell of the point where the ray enters the mesh
+// box | direction octant) with a one-pass counting sort: keys + histogram, exclusive scan, scatter of the INDICES.
+// k_traverse fetches its rays through the permutation; nothing else moves.  All counts stay on the device.
+constexpr int BIN_MAX_BITS = 5;                                  // cell bits per axis
+constexpr uint32_t BIN_MAX = 8u << (3 * BIN_MAX_BITS);           // bins at BIN_MAX_BITS (holes go to bin index `bins`)
+constexpr int BIN_SCAN_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t spread3_5(uint32_t v) {   // bit k of a 5-bit value -> bit 3k
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
+}
+__device__ __forceinline__ uint32_t bin_key_of(const RenderArgs& a, float3 o, float3 d) {
+    // entry point into the box of all triangles (the origin itself when it lies inside)
+    auto inv = [](float v) { return fast_rcp(fabsf(v) > 1e-20f ? v : copysignf(1e-20f, v)); };
+    const float ix = inv(d.x), iy = inv(d.y), iz = inv(d.z);
+    const float x0 = (a.S.bvh_min.x - o.x) * ix, x1 = (a.S.bvh_max.x - o.x) * ix;
+    const float y0 = (a.S.bvh_min.y - o.y) * iy, y1 = (a.S.bvh_max.y - o.y) * iy;
+    const float z0 = (a.S.bvh_min.z - o.z) * iz, z1 = (a.S.bvh_max.z - o.z) * iz;
+    const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float3 p = o + tmin * d;
+    const float cells = (float)(1 << a.bin_bits);
+    const float3 e = a.S.bvh_max - a.S.bvh_min;
+    const int hi = (1 << a.bin_bits) - 1;
+    const int cx = min(max((int)((p.x - a.S.bvh_min.x) * cells * fast_rcp(fmaxf(e.x, 1e-20f))), 0), hi);
+    const int cy = min(max((int)((p.y - a.S.bvh_min.y) * cells * fast_rcp(fmaxf(e.y, 1e-20f))), 0), hi);
+    const int cz = min(max((int)((p.z - a.S.bvh_min.z) * cells * fast_rcp(fmaxf(e.z, 1e-20f))), 0), hi);
+    const uint32_t morton = spread3_5((uint32_t)cx) | (spread3_5((uint32_t)cy) << 1) | (spread3_5((uint32_t)cz) << 2);
+    const uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+    return a.bin_octant_major ? (oct << (3 * a.bin_bits)) | morton : (morton << 3) | oct;
+}
+
+__global__ void __launch_bounds__(WF_THREADS) k_bin_keys(const __grid_constant__ RenderArgs a, int c) {
+    DevCtrl* C = a.ctrl;
+    const uint32_t n_ext = C->ext_head(c);
+    const uint32_t count = n_ext + C->sh_head(c);
+    const uint32_t bins = 8u << (3 * a.bin_bits);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        float4 o4, d4;
+        bool hole;
+        if (i < n_ext) {
+            hole = __float_as_uint(a.qin.hit[i].y) == HIT_HOLE;
+            o4 = a.qin.o[i];
+            d4 = a.qin.d[i];
+        } else {
+            d4 = a.sqin.d[i - n_ext];
+            hole = __float_as_uint(d4.w) == TLIM_HOLE;
+            o4 = a.sqin.o[i - n_ext];
+        }
+        const uint32_t key = hole ? bins : bin_key_of(a, f3(o4), f3(d4));   // unfilled slots sort to the end
+        a.bin_key[i] = key;
+        atomicAdd(&a.bin_hist[key], 1u);
+    }
+}
+
+// one CTA: exclusive scan of the histogram into the scatter offsets; clears the histogram for the next iteration
+__global__ void __launch_bounds__(BIN_SCAN_THREADS) k_bin_scan(const __grid_constant__ RenderArgs a) {
+    __shared__ uint32_t warp_sum[BIN_SCAN_THREADS / 32];
+    const uint32_t n = (8u << (3 * a.bin_bits)) + 1u;
+    const uint32_t per = (n + BIN_SCAN_THREADS - 1) / BIN_SCAN_THREADS;
+    const uint32_t b0 = min(threadIdx.x * per, n), b1 = min(b0 + per, n);
+    uint32_t sum = 0;
+    for (uint32_t b = b0; b < b1; ++b) sum += a.bin_hist[b];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((int)lane >= off) incl += v;
+    }
+    if (lane == 31) warp_sum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t v = warp_sum[lane];
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, v, off);
+            if ((int)lane >= off) v += u;
+        }
+        warp_sum[lane] = v;   // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t run = incl - sum + (w ? warp_sum[w - 1] : 0u);
+    for (uint32_t b = b0; b < b1; ++b) {
+        const uint32_t h = a.bin_hist[b];
+        a.bin_offs[b] = run;
+        a.bin_hist[b] = 0u;
+        run += h;
+    }
+}
+
+__global__ void __launch_bounds__(WF_THREADS) k_bin_scatter(const __grid_constant__ RenderArgs a, int c) {
+    DevCtrl* C = a.ctrl;
+    const uint32_t count = C->ext_head(c) + C->sh_head(c);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        a.bin_perm[atomicAdd(&a.bin_offs[a.bin_key[i]], 1u)] = i;
+}
+
 // ---------------------------------------------------------------- persistent traversal kernels
 // Warp-level work fetch: a warp owns [wnext, wend) of the queue and takes a new FETCH_CHUNK with one
 // atomic when it runs dry.  Returns false once the queue is exhausted.  Warp-uniform.
@@ -309,6 +413,7 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_cons
     const PathQueue& Q = a.qin;
     const ShadowQueue& SQ = a.sqin;
     const int light_obj = a.S.hdr->light_obj;
+    const uint32_t* const perm = a.bin_bits > 0 ? a.bin_perm : nullptr;   // bin order (see k_bin_*), or queue order
     const int refill_below = a.tune_refill > 0 ? a.tune_refill : REFILL_BELOW;
     const int steps = a.tune_steps > 0 ? a.tune_steps : (WIDE ? INNER_STEPS / 2 : INNER_STEPS);
     uint32_t work[2] = {0, 0};
@@ -350,8 +455,9 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_cons
         if (idle_mask && !exhausted) {
             if (!warp_reserve(&C->cursor_trav, count, wnext, wend)) exhausted = true;
             else {
-                const uint32_t my = wnext + __popc(idle_mask & ((1u << lane) - 1u));
-                if (idle && my < wend) {
+                const uint32_t pos = wnext + __popc(idle_mask & ((1u << lane) - 1u));
+                if (idle && pos < wend) {
+                    const uint32_t my = perm ? perm[pos] : pos;
                     // slots a k_shade warp reserved but did not fill are marked as holes: the lane stays idle this round
                     if (my < n_ext) {
                         const float2 h2 = Q.hit[my];

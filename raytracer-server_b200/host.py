@@ -42,7 +42,9 @@ def _check(rc: int, load: bool = False):
 
 
 def make_params(width: int, height: int, spp: int, *, use_mis: bool = False, seed: int = 0, rank: int = 0, world: int = 1,
-                pool_paths: int = 0, count_work: bool = False, tune_refill: int = 0, tune_steps: int = 0) -> Params:
+                pool_paths: int = 0, count_work: bool = False, tune_refill: int = 0, tune_steps: int = 0,
+                bin_bits: int | None = None, bin_octant_major: bool = False) -> Params:
+    """bin_bits: coherence binning of the LBVH rays — None = library default, 0 = off, 2..5 = cell bits per axis."""
     p = Params()
     p.width, p.height, p.spp = width, height, spp
     p.estimator = EST_MIS_DEAD if use_mis else EST_NEE
@@ -51,6 +53,8 @@ def make_params(width: int, height: int, spp: int, *, use_mis: bool = False, see
     p.reserved[0] = 1 if count_work else 0
     p.reserved[1] = tune_refill
     p.reserved[2] = tune_steps
+    p.reserved[3] = 0 if bin_bits is None else (1 if bin_bits <= 0 else max(2, bin_bits))
+    p.reserved[4] = 1 if bin_octant_major else 0
     return p
 
 
@@ -164,10 +168,11 @@ class Scene:
     # ---- RenderJob::run, blocking whole-frame form ----------------------------------------------
     def render(self, width: int, height: int, spp: int, *, use_mis: bool = False, seed: int = 0, rank: int = 0,
                world: int = 1, pool_paths: int = 0, out: np.ndarray | None = None, count_work: bool = False,
-               tune_refill: int = 0, tune_steps: int = 0) -> np.ndarray:
+               tune_refill: int = 0, tune_steps: int = 0, bin_bits: int | None = None, bin_octant_major: bool = False) -> np.ndarray:
         """Returns the frame as uint8 [height, width, 3], row 0 = top (the bytes of src/server.rs:187-189)."""
         p = make_params(width, height, spp, use_mis=use_mis, seed=seed, rank=rank, world=world, pool_paths=pool_paths,
-                        count_work=count_work, tune_refill=tune_refill, tune_steps=tune_steps)
+                        count_work=count_work, tune_refill=tune_refill, tune_steps=tune_steps, bin_bits=bin_bits,
+                        bin_octant_major=bin_octant_major)
         if out is None:
             out = np.zeros((height, width, 3), dtype=np.uint8)
         assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size == width * height * 3

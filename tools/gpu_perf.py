@@ -15,9 +15,9 @@ for name, w, h, spp in cfgs:
     st = g.stats()
     rays = st["rays_primary"] + st["rays_extension"] + st["rays_shadow"]
     it = st["iterations"]
-    print(f"{name} {w}x{h}x{spp}: wall {dt*1e3:.1f} ms dev {st['render_ms']:.1f} ms | extend {st['extend_ms']:.1f} shade {st['shade_ms']:.1f} shadow {st['shadow_ms']:.1f} other {st['render_ms']-st['extend_ms']-st['shade_ms']-st['shadow_ms']:.1f} | iters {it} "
+    print(f"{name} {w}x{h}x{spp}: wall {dt*1e3:.1f} ms dev {st['render_ms']:.1f} ms | extend {st['extend_ms']:.1f} shade {st['shade_ms']:.1f} bin {st['bin_ms']:.1f} other {st['render_ms']-st['extend_ms']-st['shade_ms']-st['bin_ms']:.1f} | iters {it} "
           f"| {st['samples']/st['render_ms']/1e3:.1f} Msamples/s {rays/st['render_ms']/1e3:.0f} Mrays/s | bvh rays {st['rays_bvh']/max(1,st['rays_primary']+st['rays_extension']):.3f} shadow bvh {st['shadow_bvh']/max(1,st['rays_shadow']):.3f}"
-          f" | per iter: ext {st['extend_ms']/it*1e3:.0f} us shade {st['shade_ms']/it*1e3:.0f} us shadow {st['shadow_ms']/it*1e3:.0f} us", flush=True)
+          f" | per iter: ext {st['extend_ms']/it*1e3:.0f} us shade {st['shade_ms']/it*1e3:.0f} us bin {st['bin_ms']/it*1e3:.0f} us", flush=True)
 # small frames (launch-bound regime): BASELINE configs[0] and [1]
 for name, w, h, spp in (("cornell_box", 600, 450, 64), ("cubes", 600, 450, 256)):
     if len(sys.argv) > 1 and name not in sys.argv[1:]:
