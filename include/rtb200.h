@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 1
+#define RTB_ABI_VERSION 2
 
 /* error codes — LoadTomlError::{Io,Parse,MeshLoad} (src/scene.rs:350-355) plus the reference's
  * panics turned into codes: no emitter = unreachable!() (src/scene.rs:136); plane light =
@@ -73,7 +73,9 @@ typedef struct rtb_scene_info {
     int32_t bvh_nodes;
     int32_t bvh_leaves;
     int32_t device;
-    int32_t reserved[3];
+    int32_t bvh_depth;    /* inner-node levels on the longest root-to-leaf path; the loader refuses trees deeper than the
+                             traversal stack (96) with RTB_EUNSUPPORTED */
+    int32_t reserved[2];
     float bvh_min[3];
     float bvh_max[3];
     float camera_pos[3];
@@ -118,6 +120,8 @@ typedef struct rtb_stats {
     uint64_t rays_bvh;       /* primary + extension rays that needed the LBVH (the rest end at an analytic primitive) */
     uint64_t shadow_bvh;     /* shadow rays that needed the LBVH */
     uint64_t paths_queued;   /* path-queue entries k_shade wrote (a path stays in registers while its next hit is analytic) */
+    double first_record_ms;  /* streaming jobs: host time from rtb_job_begin until the first record could be delivered (-1: none yet) */
+    double wall_ms;          /* streaming jobs: host time from rtb_job_begin until the last worker finished (or until now) */
 } rtb_stats;
 
 /* ---- scene: Scene::from_toml + SceneSpec::to_scene (src/scene.rs:143-150, 357-441) ---------
@@ -190,15 +194,23 @@ int rtb_render_device(rtb_scene* scene, const rtb_params* params, void* d_rgb8_t
  * to shard_stride bytes) into a scan-line frame; all pointers are device pointers */
 int rtb_untile_device(const rtb_params* params, const void* d_shards, int64_t shard_stride, void* d_rgb8_frame,
                       int device);
+/* same, enqueued on the caller's stream (a cudaStream_t; NULL = legacy default stream) without any synchronisation */
+int rtb_untile_device_async(const rtb_params* params, const void* d_shards, int64_t shard_stride, void* d_rgb8_frame,
+                            int device, void* cuda_stream);
 
-/* counters of the last render on this scene handle by the calling thread's most recent call */
+/* counters of the calling thread's most recent rtb_render* / rtb_sample_* call on this scene; a thread that has not rendered on
+ * it gets the scene's most recently finished render or job (whichever thread ran it).  Jobs: rtb_job_stats. */
 int rtb_get_stats(const rtb_scene* scene, rtb_stats* stats);
 
 /* ---- streaming job: the message loop of RenderJob::run (src/server.rs:166-194) -------------
  * rtb_job_next yields records in the reference's wire shape: screen column x, screen row y
  * (top-down), n <= 60 pixels, n*3 bytes of rgb.  Returns 1 while records remain, 0 when the
- * frame is complete, RTB_ESTOPPED after rtb_job_cancel.  Progressive mode (passes > 1, not in
- * the reference) re-sends every record once per pass with the running estimate. */
+ * frame is complete, RTB_ESTOPPED after rtb_job_cancel.  Records become available WHILE the frame is
+ * still rendering: the frame is rendered in bands of tile rows, top-down, and each finished band is
+ * resolved and copied to pinned host memory on a side stream (large frames; a frame of less than ~32 M
+ * samples is one band).  Progressive mode (passes > 1, not in the reference) re-sends every record once
+ * per pass with the running estimate; pass n + 1 renders while pass n is copied and consumed.
+ * One consumer thread per job. */
 int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rtb_job** out);
 int rtb_job_next(rtb_job* job, uint16_t* x, uint16_t* y, uint8_t* n, uint8_t* rgb /* >= 180 bytes */);
 /* bulk form: up to max_records records packed exactly like the reference's binary messages,
@@ -209,6 +221,8 @@ int rtb_job_next_messages(rtb_job* job, uint8_t* buf, int64_t buf_bytes, int32_t
 /* whole-frame form (progressive display): copies the latest finished pass (height*width*3 bytes, row 0 = top)
  * and its 0-based pass index; 1 = frame copied, 0 = all passes delivered, RTB_ESTOPPED after a cancel */
 int rtb_job_next_frame(rtb_job* job, uint8_t* rgb8_out, int32_t* pass_index);
+/* counters of the job so far (finished bands / passes), incl. first_record_ms / wall_ms; callable at any time before rtb_job_end */
+int rtb_job_stats(rtb_job* job, rtb_stats* stats);
 int rtb_job_cancel(rtb_job* job);
 int rtb_job_end(rtb_job* job);
 
@@ -225,6 +239,12 @@ int rtb_trace_rays(rtb_scene* scene, int64_t n, const float* org3, const float* 
  * path-level probe matching the oracle's or_sample_radiance under the shared RNG contract */
 int rtb_sample_radiance(rtb_scene* scene, const rtb_params* params, int64_t n, const int32_t* px, const int32_t* py,
                         const int32_t* sample_idx, float* rgb3);
+
+/* sample_pixel (src/server.rs:320-364) for a list of n pixels (x, screen row y): the Vec3 the reference's function returns
+ * per pixel — all spp samples, per-sub-pixel clamp, gamma, scaled to 0..255.5, BEFORE the `as u8` of RenderJob::run —
+ * as 3 floats each.  Same random numbers as the frame render, so trunc(rgb3) equals the frame's bytes up to the
+ * order of the fp32 accumulation. */
+int rtb_sample_pixels(rtb_scene* scene, const rtb_params* params, int64_t n, const int32_t* px, const int32_t* py, float* rgb3);
 
 /* FP32 FMA-chain microbenchmark on `device`: measured non-tensor FP32 peak (TFLOP/s) */
 int rtb_fp32_peak(int device, double* tflops);

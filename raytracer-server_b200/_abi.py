@@ -35,7 +35,7 @@ class Params(C.Structure):
 class SceneInfo(C.Structure):
     _fields_ = [("n_objects", C.c_int32), ("n_planes", C.c_int32), ("n_spheres", C.c_int32), ("n_meshes", C.c_int32),
                 ("n_triangles", C.c_int32), ("light_object", C.c_int32), ("bvh_nodes", C.c_int32),
-                ("bvh_leaves", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 3),
+                ("bvh_leaves", C.c_int32), ("device", C.c_int32), ("bvh_depth", C.c_int32), ("reserved", C.c_int32 * 2),
                 ("bvh_min", C.c_float * 3), ("bvh_max", C.c_float * 3), ("camera_pos", C.c_float * 3),
                 ("camera_dir", C.c_float * 3), ("build_ms", C.c_double)]
 
@@ -46,7 +46,7 @@ class Stats(C.Structure):
                 ("bvh_node_visits", C.c_uint64), ("bvh_tri_tests", C.c_uint64), ("render_ms", C.c_double),
                 ("extend_ms", C.c_double), ("bin_ms", C.c_double), ("generate_ms", C.c_double),
                 ("resolve_ms", C.c_double), ("shade_ms", C.c_double), ("rays_bvh", C.c_uint64),
-                ("shadow_bvh", C.c_uint64), ("paths_queued", C.c_uint64)]
+                ("shadow_bvh", C.c_uint64), ("paths_queued", C.c_uint64), ("first_record_ms", C.c_double), ("wall_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -75,6 +75,7 @@ EXPORTS = [
     "rtb_scene_upload", "rtb_scene_triangles", "rtb_render", "rtb_local_pixels", "rtb_tile_map", "rtb_render_device",
     "rtb_untile_device", "rtb_get_stats", "rtb_job_begin", "rtb_job_next", "rtb_job_next_messages", "rtb_job_next_frame", "rtb_job_cancel",
     "rtb_job_end", "rtb_trace_primary", "rtb_trace_rays", "rtb_sample_radiance", "rtb_fp32_peak",
+    "rtb_untile_device_async", "rtb_job_stats", "rtb_sample_pixels",
 ]
 
 _lib = None
@@ -119,6 +120,9 @@ def lib():
     L.rtb_trace_rays.argtypes = [vp, C.c_int64, fp, fp, ip, ip, fp, C.POINTER(C.c_uint64)]
     L.rtb_sample_radiance.argtypes = [vp, C.POINTER(Params), C.c_int64, ip, ip, ip, fp]
     L.rtb_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.rtb_untile_device_async.argtypes = [C.POINTER(Params), vp, C.c_int64, vp, C.c_int, vp]
+    L.rtb_job_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.rtb_sample_pixels.argtypes = [vp, C.POINTER(Params), C.c_int64, ip, ip, fp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:

@@ -27,6 +27,9 @@ using namespace rtb;
 namespace {
 
 thread_local std::string g_last_error;
+// counters of the calling thread's most recent render call (rtb_get_stats prefers them over the scene-global copy)
+thread_local rtb_stats g_thread_stats{};
+thread_local const void* g_thread_stats_scene = nullptr;
 
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -44,12 +47,15 @@ static_assert(sizeof(FlatPrim) == sizeof(DevPrim), "FlatPrim/DevPrim layout");
 static_assert(sizeof(FlatMaterial) == sizeof(DevMaterial), "FlatMaterial/DevMaterial layout");
 static_assert(sizeof(DevPrim) == 48 && sizeof(DevMaterial) == 80, "16-byte multiples expected by stage_scene");
 static_assert(MAX_OBJECTS == (int)TRI_BASE, "primitive code space");
+static_assert(BVH_MAX_DEPTH == STACK_SMEM + STACK_LOCAL, "the loader's depth limit is the traversal stack's capacity");
 
 struct RenderContext {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    uint32_t P = 0, SP = 0;
-    uint32_t Pcap = 0, SPcap = 0;   // physical slots: P, SP + room for k_shade's unfilled segment tails
+    bool initialised = false;   // set once the whole one-time set-up below has succeeded
+    uint32_t P = 0, SP = 0;         // path / shadow slots of the CURRENT request (logical)
+    uint32_t Pcap = 0, SPcap = 0;   // slots the current request addresses: P, SP + room for k_shade's unfilled segment tails
+    uint32_t Palloc = 0, SPalloc = 0;   // slots allocated: buffers only ever grow, a smaller request uses the front part
     float4* qbuf = nullptr;      // 2 queues x (4 float4 arrays + 1 float2 array) x P
     float4* sbuf = nullptr;      // 2 shadow queues x 3 arrays x SP
     float4* accum = nullptr;
@@ -186,7 +192,8 @@ int build_device_scene(rtb_scene* sc) {
     CU_TRY(cudaEventCreate(&e1));
     CU_TRY(cudaEventRecord(e0, sc->stream));
     std::string err;
-    if (!build_lbvh(d_verts, d_triobj, n_tris, sc->stream, sc->bvh, err)) return fail(RTB_ECUDA, err);
+    if (!build_lbvh(d_verts, d_triobj, n_tris, sc->stream, sc->bvh, err))
+        return fail(err.rfind("unsupported:", 0) == 0 ? RTB_EUNSUPPORTED : RTB_ECUDA, err);
     if (n_tris) {
         CU_TRY(cudaMalloc((void**)&sc->d_tri_orig, (size_t)n_tris * 3 * sizeof(float4)));
         k_tri_orig<<<(n_tris + 255) / 256, 256, 0, sc->stream>>>(d_verts, n_tris, sc->d_tri_orig);
@@ -256,6 +263,7 @@ int build_device_scene(rtb_scene* sc) {
     I.light_object = fs.light_obj;
     I.bvh_nodes = sc->bvh.n_nodes;
     I.bvh_leaves = sc->bvh.n_leaves;
+    I.bvh_depth = sc->bvh.depth;
     I.device = sc->device;
     for (int k = 0; k < 3; ++k) {
         I.bvh_min[k] = H.bvh_min[k];
@@ -304,11 +312,19 @@ int finish_scene(rtb_scene* sc, int rc, const std::string& err, rtb_scene** out)
 }
 
 // ---------------------------------------------------------------- render contexts
-RenderContext* acquire_context(rtb_scene* sc) {
+// want_paths: path slots the caller is going to ask for — the pooled context whose queues fit best is handed out
+// (smallest that is large enough, else the largest), so that nothing is reallocated when it can be avoided
+RenderContext* acquire_context(rtb_scene* sc, uint32_t want_paths = 0) {
     std::lock_guard<std::mutex> lk(sc->mu);
     if (!sc->pool.empty()) {
-        RenderContext* c = sc->pool.back();
-        sc->pool.pop_back();
+        size_t best = 0;
+        for (size_t k = 1; k < sc->pool.size(); ++k) {
+            const uint32_t a = sc->pool[k]->Palloc, b = sc->pool[best]->Palloc;
+            const bool a_fits = a >= want_paths, b_fits = b >= want_paths;
+            if ((a_fits && (!b_fits || a < b)) || (!a_fits && !b_fits && a > b)) best = k;
+        }
+        RenderContext* c = sc->pool[best];
+        sc->pool.erase(sc->pool.begin() + (long)best);
         return c;
     }
     RenderContext* c = new RenderContext();
@@ -316,13 +332,25 @@ RenderContext* acquire_context(rtb_scene* sc) {
     return c;
 }
 void release_context(rtb_scene* sc, RenderContext* c) {
+    if (!c->initialised) {   // ensure_context failed half-way: do not hand a half-built context to the next render
+        delete c;
+        return;
+    }
     std::lock_guard<std::mutex> lk(sc->mu);
     sc->pool.push_back(c);
 }
 
-int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, size_t accum_elems) {
+int default_bin_bits();
+// cell bits per axis of the coherence binning this request asks for (0 = off):
+// rtb_params.reserved[3] = 0 library default | 1 off | 2..5 bits
+int requested_bin_bits(const rtb_scene* sc, const rtb_params* p) {
+    if (sc->view.n_tris == 0) return 0;   // scenes without triangles never traverse
+    return p->reserved[3] == 0 ? default_bin_bits() : (p->reserved[3] == 1 ? 0 : std::min(std::max(p->reserved[3], 2), BIN_MAX_BITS));
+}
+
+int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, size_t accum_elems, bool binning = false) {
     CU_TRY(cudaSetDevice(sc->device));
-    if (!c->stream) {
+    if (!c->initialised) {   // a context whose set-up failed half-way is deleted by its caller, never pooled
         CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CU_TRY(cudaMalloc((void**)&c->ctrl, sizeof(DevCtrl)));
@@ -363,24 +391,31 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         // experiment knobs: CTAs per SM of the two persistent kernels (two concurrent renders can then share every SM)
         if (const char* e = getenv("RTB_TRAV_CTAS")) c->grid_ext = c->grid_ext_count = std::max(1, atoi(e)) * prop.multiProcessorCount;
         if (const char* e = getenv("RTB_SHADE_CTAS")) c->grid_shade = std::max(1, atoi(e)) * prop.multiProcessorCount;
+        c->initialised = true;
     }
     // every k_shade warp may leave up to two unfilled SHADE_SEG segments per queue class behind in each iteration
     const uint32_t seg_room = (uint32_t)std::max(c->grid_shade * (SHADE_THREADS / 32), c->grid_shade_nomesh * (SHADE_THREADS_NOMESH / 32)) * 2u * SHADE_SEG;
-    if (c->P != P) {
-        cudaFree(c->qbuf);
-        c->qbuf = nullptr;
-        c->P = 0;
+    {
         const uint32_t cap = P + 2u * seg_room;   // front + back class
-        CU_TRY(cudaMalloc((void**)&c->qbuf, (size_t)cap * 9 * sizeof(float4)));
+        if (c->Palloc < cap) {   // (re)allocation of GBs of queue costs 100s of ms: never shrink, so a scene that serves
+            cudaFree(c->qbuf);   // whole frames and band-sized streaming jobs alternately does it once
+            c->qbuf = nullptr;
+            c->Palloc = 0;
+            CU_TRY(cudaMalloc((void**)&c->qbuf, (size_t)cap * 9 * sizeof(float4)));
+            c->Palloc = cap;
+        }
         c->P = P;
         c->Pcap = cap;
     }
-    if (c->SP != SP) {
-        cudaFree(c->sbuf);
-        c->sbuf = nullptr;
-        c->SP = 0;
+    {
         const uint32_t cap = SP + seg_room;
-        CU_TRY(cudaMalloc((void**)&c->sbuf, (size_t)cap * 6 * sizeof(float4)));
+        if (c->SPalloc < cap) {
+            cudaFree(c->sbuf);
+            c->sbuf = nullptr;
+            c->SPalloc = 0;
+            CU_TRY(cudaMalloc((void**)&c->sbuf, (size_t)cap * 6 * sizeof(float4)));
+            c->SPalloc = cap;
+        }
         c->SP = SP;
         c->SPcap = cap;
     }
@@ -390,7 +425,7 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         CU_TRY(cudaMalloc((void**)&c->accum, accum_elems * sizeof(float4)));
         c->accum_cap = accum_elems;
     }
-    if (sc->view.n_tris > 0) {   // coherence binning of the LBVH rays (scenes without triangles never traverse)
+    if (binning) {   // coherence binning of the LBVH rays: buffers exist only once a request asks for it
         const size_t need = (size_t)c->Pcap + c->SPcap;
         if (c->bin_cap < need) {
             cudaFree(c->bin_buf);
@@ -434,17 +469,19 @@ int local_tiles(const rtb_params* p) {
 // Path slots in flight.  More slots = fewer, fuller wavefront iterations (measured on flying_unicorn 1080p 256 spp:
 // 8 Mi 497, 16 Mi 528, 32 Mi 542 Msamples/s), but 240 B of queue memory each; default: one eighth of the frame's
 // samples, between 1 Mi and 32 Mi (7.7 GB).
-uint32_t default_pool(const rtb_params* p) {
+uint32_t pool_for(uint64_t samples, int pool_paths) {
     uint64_t P;
-    if (p->pool_paths > 0) P = (uint64_t)p->pool_paths;
+    if (pool_paths > 0) P = (uint64_t)pool_paths;
     else {
-        uint64_t samples = (uint64_t)local_tiles(p) * 1024ull * 4ull * (uint64_t)std::max(1, p->spp / 4);
         uint64_t want = samples / 8;
         P = 1ull << 20;
         while (P < want && P < (1ull << 25)) P <<= 1;
     }
     P = std::max<uint64_t>(P, 1024);
     return (uint32_t)((P + 31ull) & ~31ull);
+}
+uint32_t default_pool(const rtb_params* p) {
+    return pool_for((uint64_t)local_tiles(p) * 1024ull * 4ull * (uint64_t)std::max(1, p->spp / 4), p->pool_paths);
 }
 
 // library default of the coherence binning (cell bits per axis, 0 = off); RTB_BIN_BITS overrides it
@@ -516,9 +553,7 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     a.trav_warps = (uint32_t)c->grid_ext * (WF_THREADS / 32);
     a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
     // coherence binning: rtb_params.reserved[3] = 0 library default | 1 off | 2..5 cell bits per axis; reserved[4] & 1 = octant-major keys
-    int bits = p->reserved[3] == 0 ? default_bin_bits() : (p->reserved[3] == 1 ? 0 : std::min(std::max(p->reserved[3], 2), BIN_MAX_BITS));
-    if (sc->view.n_tris == 0 || !c->bin_buf) bits = 0;
-    a.bin_bits = bits;
+    a.bin_bits = c->bin_buf && c->bin_hist ? requested_bin_bits(sc, p) : 0;
     a.bin_octant_major = p->reserved[4] & 1;
     a.bin_key = c->bin_buf;
     a.bin_perm = c->bin_buf ? c->bin_buf + c->bin_cap : nullptr;
@@ -577,9 +612,12 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     h.ext_head(0) = h.ext_head(1) = 0;
     h.ext_tail(0) = h.ext_tail(1) = a.Pcap;
     h.sh_head(0) = h.sh_head(1) = 0;
-    unsigned long long npl = (unsigned long long)a.n_local_tiles * 1024ull;
-    h.work_next = a.probe_px ? 0ull : (unsigned long long)ks_begin * npl;
-    h.work_total = a.probe_px ? (unsigned long long)a.n_probe : (unsigned long long)ks_end * npl;
+    unsigned long long npl = a.pixel_list ? (unsigned long long)a.n_probe : (unsigned long long)a.n_local_tiles * 1024ull;
+    const bool explicit_items = a.probe_px && !a.pixel_list;
+    h.work_next = explicit_items ? 0ull : (unsigned long long)ks_begin * npl;
+    h.work_total = explicit_items ? (unsigned long long)a.n_probe : (unsigned long long)ks_end * npl;
+    h.tile_base = a.tile_base;
+    h.n_tiles = a.n_local_tiles;
     CU_TRY(cudaMemcpyAsync(c->ctrl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaEventRecord(c->ev_begin, c->stream));
     const size_t smem_tab = shared_tables_bytes(a.S.n_prims, a.S.n_objects);
@@ -603,6 +641,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     if (use_graph && !done) {
         RenderArgs ag = a;
         ag.host_state = c->d_state;
+        ag.tile_base = ag.n_local_tiles = 0;   // the kernels of the loop read the tile range from the control block: one graph serves every band
         c->h_state[0] = 0;
         c->h_state[1] = 1;
         cudaError_t ge = cudaSuccess;
@@ -635,7 +674,10 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
             c->graph_args.assign(reinterpret_cast<unsigned char*>(&ag), reinterpret_cast<unsigned char*>(&ag) + sizeof(RenderArgs));
         }
         cudaGraphExec_t* exec = c->graph_exec;
-        const uint64_t run_ahead = 24;
+        // graphs launched beyond the newest iteration the device has reported: enough to hide the launch latency of the
+        // short tail iterations, few enough that a finished run leaves only a handful of empty graphs behind (each costs
+        // ~8 us of device time — most of a 1-sample progressive pass when there were 24 of them)
+        const uint64_t run_ahead = 6;
         while (!done) {
             if (cancel && *cancel) { cancelled = true; break; }
             ge = cudaGraphLaunch(exec[cur], c->stream);
@@ -749,7 +791,7 @@ int render_into_context(rtb_scene* sc, const rtb_params* p, RenderContext* c, Re
     uint32_t P = default_pool(p);
     uint32_t SP = p->estimator == RTB_EST_NEE ? P : 2 * P;
     size_t accum_elems = (size_t)p->width * p->height * 4;
-    int rc = ensure_context(sc, c, P, SP, accum_elems);
+    int rc = ensure_context(sc, c, P, SP, accum_elems, requested_bin_bits(sc, p) > 0);
     if (rc != RTB_OK) return rc;
     fill_args(sc, p, c, a);
     CU_TRY(cudaMemsetAsync(c->accum, 0, accum_elems * sizeof(float4), c->stream));
@@ -777,6 +819,15 @@ int resolve_to(RenderContext* c, const RenderArgs& a, unsigned char* d_out, floa
     st.resolve_ms += ms;
     st.kernel_launches += 1;
     return RTB_OK;
+}
+
+void publish_stats(rtb_scene* sc, const rtb_stats& st, bool calling_thread = true) {
+    if (calling_thread) {
+        g_thread_stats = st;
+        g_thread_stats_scene = sc;
+    }
+    std::lock_guard<std::mutex> lk(sc->mu);
+    sc->last_stats = st;
 }
 
 int ensure_rgb(RenderContext* c, size_t bytes, bool host) {
@@ -930,6 +981,10 @@ int64_t rtb_tile_map(const rtb_params* params, int32_t* xy, int64_t cap) {
 
 int rtb_get_stats(const rtb_scene* scene, rtb_stats* stats) {
     if (!scene || !stats) return fail(RTB_EINVAL, "NULL argument");
+    if (g_thread_stats_scene == scene) {   // this thread has rendered on the scene: its own last call, whatever other threads did since
+        *stats = g_thread_stats;
+        return RTB_OK;
+    }
     rtb_scene* s = const_cast<rtb_scene*>(scene);
     std::lock_guard<std::mutex> lk(s->mu);
     *stats = s->last_stats;
@@ -940,17 +995,14 @@ int rtb_render_device(rtb_scene* scene, const rtb_params* params, void* d_rgb8_t
     if (int rc0 = need_device(scene)) return rc0;
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
-    RenderContext* c = acquire_context(scene);
+    RenderContext* c = acquire_context(scene, default_pool(params));
     RenderArgs a;
     rtb_stats st{};
     bool cancelled = false;
     rc = render_into_context(scene, params, c, a, cancel, st, cancelled);
     if (rc == RTB_OK && !cancelled && d_rgb8_tiles)
         rc = resolve_to(c, a, (unsigned char*)d_rgb8_tiles, (float4*)d_subpixel_sums, 0, st);
-    {
-        std::lock_guard<std::mutex> lk(scene->mu);
-        scene->last_stats = st;
-    }
+    publish_stats(scene, st);
     release_context(scene, c);
     if (rc != RTB_OK) return rc;
     return cancelled ? RTB_ECANCELLED : RTB_OK;
@@ -961,7 +1013,7 @@ int rtb_render(rtb_scene* scene, const rtb_params* params, uint8_t* rgb8_out, vo
     if (int rc0 = need_device(scene)) return rc0;
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
-    RenderContext* c = acquire_context(scene);
+    RenderContext* c = acquire_context(scene, default_pool(params));
     RenderArgs a;
     rtb_stats st{};
     bool cancelled = false;
@@ -980,34 +1032,41 @@ int rtb_render(rtb_scene* scene, const rtb_params* params, uint8_t* rgb8_out, vo
         if (rc == RTB_OK) {
             if (whole) std::memcpy(rgb8_out, c->h_rgb, frame);
             else {
-                for (int lp = 0; lp < a.n_local_tiles * 1024; ++lp) {
+                // tile order walks 8x4-pixel blocks: 8 consecutive slots are 8 consecutive pixels of one row
+                for (int lp = 0; lp < a.n_local_tiles * 1024; lp += 8) {
                     int x, y;
                     if (!local_to_xy(lp, a.rank, a.world, a.tiles_x, a.width, a.height, x, y)) continue;
-                    std::memcpy(rgb8_out + ((size_t)y * a.width + x) * 3, c->h_rgb + (size_t)lp * 3, 3);
+                    const int run = std::min(8, a.width - x);
+                    std::memcpy(rgb8_out + ((size_t)y * a.width + x) * 3, c->h_rgb + (size_t)lp * 3, (size_t)run * 3);
                 }
             }
         }
     }
-    {
-        std::lock_guard<std::mutex> lk(scene->mu);
-        scene->last_stats = st;
-    }
+    publish_stats(scene, st);
     release_context(scene, c);
     if (rc != RTB_OK) return rc;
     return cancelled ? RTB_ECANCELLED : RTB_OK;
 }
 
-int rtb_untile_device(const rtb_params* params, const void* d_shards, int64_t shard_stride, void* d_rgb8_frame, int device) {
+int rtb_untile_device_async(const rtb_params* params, const void* d_shards, int64_t shard_stride, void* d_rgb8_frame, int device,
+                            void* cuda_stream) {
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
     if (!d_shards || !d_rgb8_frame) return fail(RTB_EINVAL, "NULL argument");
     CU_TRY(cudaSetDevice(device));
     int tx = (params->width + TILE - 1) / TILE, ty = (params->height + TILE - 1) / TILE;
     long long total = (long long)tx * ty * 1024;
-    k_untile<<<(unsigned)((total + 255) / 256), 256>>>((const unsigned char*)d_shards, shard_stride, params->world, tx, ty,
-                                                       params->width, params->height, (unsigned char*)d_rgb8_frame);
-    CU_TRY(cudaDeviceSynchronize());
+    k_untile<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>((const unsigned char*)d_shards, shard_stride, params->world,
+                                                                                    tx, ty, params->width, params->height,
+                                                                                    (unsigned char*)d_rgb8_frame);
     CU_TRY(cudaGetLastError());
+    return RTB_OK;
+}
+
+int rtb_untile_device(const rtb_params* params, const void* d_shards, int64_t shard_stride, void* d_rgb8_frame, int device) {
+    int rc = rtb_untile_device_async(params, d_shards, shard_stride, d_rgb8_frame, device, nullptr);
+    if (rc != RTB_OK) return rc;
+    CU_TRY(cudaStreamSynchronize(nullptr));   // legacy default stream only — not the whole device
     return RTB_OK;
 }
 
@@ -1119,10 +1178,62 @@ int rtb_sample_radiance(rtb_scene* scene, const rtb_params* params, int64_t n, c
                 rgb3[3 * i] = host[i].x; rgb3[3 * i + 1] = host[i].y; rgb3[3 * i + 2] = host[i].z;
             }
     }
-    {
-        std::lock_guard<std::mutex> lk(scene->mu);
-        scene->last_stats = st;
+    publish_stats(scene, st);
+    release_context(scene, c);
+    return rc;
+}
+
+// sample_pixel (src/server.rs:320-364) for a LIST of pixels: the full sample set of every listed pixel, resolved to the Vec3
+// the reference's function returns (gamma-corrected, 0..255.5, before RenderJob::run's `as u8`).  Same RNG counters as a frame.
+int rtb_sample_pixels(rtb_scene* scene, const rtb_params* params, int64_t n, const int32_t* px, const int32_t* py, float* rgb3) {
+    if (!scene || !px || !py || !rgb3) return fail(RTB_EINVAL, "NULL argument");
+    if (int rc0 = need_device(scene)) return rc0;
+    int rc = check_params(params);
+    if (rc != RTB_OK) return rc;
+    if (n <= 0) return RTB_OK;
+    if (n > (1 << 24)) return fail(RTB_EINVAL, "at most 2^24 pixels per call");
+    for (int64_t i = 0; i < n; ++i)
+        if (px[i] < 0 || px[i] >= params->width || py[i] < 0 || py[i] >= params->height) return fail(RTB_EINVAL, "pixel out of range");
+    const int num_samples = params->spp / 4;
+    RenderContext* c = acquire_context(scene);
+    const uint64_t samples = (uint64_t)n * 4ull * (uint64_t)std::max(1, num_samples);
+    const uint32_t P = pool_for(samples, params->pool_paths);
+    const uint32_t SP = params->estimator == RTB_EST_NEE ? P : 2 * P;
+    rc = ensure_context(scene, c, P, SP, (size_t)n * 4, requested_bin_bits(scene, params) > 0);
+    RenderArgs a;
+    rtb_stats st{};
+    float* d_out = nullptr;
+    if (rc == RTB_OK && c->probe_cap < (size_t)n * 3) {
+        cudaFree(c->d_probe);
+        c->d_probe = nullptr;
+        c->probe_cap = 0;
+        if (cudaMalloc((void**)&c->d_probe, (size_t)n * 3 * sizeof(int32_t)) != cudaSuccess) rc = fail(RTB_ECUDA, "probe alloc");
+        else c->probe_cap = (size_t)n * 3;
     }
+    if (rc == RTB_OK) {
+        fill_args(scene, params, c, a);
+        a.probe_px = c->d_probe;
+        a.probe_py = c->d_probe + n;
+        a.probe_sample = nullptr;
+        a.n_probe = (int)n;
+        a.pixel_list = 1;
+        cudaError_t e = cudaMemcpyAsync(c->d_probe, px, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_probe + n, py, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->accum, 0, (size_t)n * 4 * sizeof(float4), c->stream);
+        if (e != cudaSuccess) rc = fail(RTB_ECUDA, cudaGetErrorString(e));
+    }
+    bool cancelled = false;
+    if (rc == RTB_OK && num_samples > 0) rc = run_wavefront(scene, c, a, 0u, (uint32_t)num_samples * 4u, false, nullptr, st, cancelled);
+    if (rc == RTB_OK) {
+        // the pixel list is no longer needed: the result overwrites it (n x 3 floats in the 3n-word probe buffer)
+        d_out = reinterpret_cast<float*>(c->d_probe);
+        k_resolve_list<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->accum, (int)n, num_samples, d_out);
+        cudaError_t e = cudaMemcpyAsync(rgb3, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(RTB_ECUDA, cudaGetErrorString(e));
+        st.kernel_launches += 1;
+    }
+    publish_stats(scene, st);
     release_context(scene, c);
     return rc;
 }
@@ -1159,86 +1270,271 @@ int rtb_fp32_peak(int device, double* tflops) {
 }  // extern "C"
 
 // ======================================================================================= jobs
-// RenderJob::run's message loop (src/server.rs:166-194).  A worker thread renders pass after pass
-// on the job's own context; after each pass the frame is resolved and copied to pinned host memory
-// on the context's stream; the consumer walks rows top-down in 60-pixel windows like the reference.
+// RenderJob::run's message loop (src/server.rs:166-194).  The reference sends every 60-pixel window the moment it is
+// sampled; a GPU renders a whole frame region at once, so a streaming job renders the frame in BANDS of whole tile rows,
+// top-down, and hands each band to the consumer while the next ones are still being rendered:
+//   * worker threads (two when there are enough bands, each with its own render context and stream, so that the
+//     under-filled tail iterations of one band overlap the full ones of the next) take bands from a counter, render
+//     them into their accumulators and launch resolve + cudaMemcpyAsync into the job's PINNED frame on the context's
+//     side stream; a host callback on that stream publishes the band.  The render stream never waits for the copy.
+//   * the consumer walks rows top-down in 60-pixel windows straight out of the pinned frame; it takes the job's
+//     mutex once per band (when it runs out of published rows), not per record, and nothing is copied twice.
+//   * progressive jobs (passes > 1, not in the reference) keep the whole frame as one band per pass and ping-pong
+//     between two pinned frames: pass n + 1 renders while pass n is copied and consumed.
 struct rtb_job {
     rtb_scene* scene = nullptr;
     rtb_params params{};
     int passes = 1;
-    std::thread worker;
+    std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv;
-    std::vector<uint8_t> frame;   // latest completed pass, scan-line RGB8
-    int passes_done = 0;          // produced
-    int pass_consumed = 0;        // fully sent
-    int cursor_y = 0, cursor_x = 0;
-    bool frame_fresh = false;
+    uint8_t* h_frame[2] = {nullptr, nullptr};   // pinned; single pass: [0] only
+    size_t frame_bytes = 0;
+    cudaEvent_t ev_resolved[2] = {nullptr, nullptr};
+    // A band / pass is PUBLISHED (under mu) as soon as its resolve + copy have been enqueued on the side stream, together
+    // with an event recorded behind the copy; the consumer waits for that event before it reads the pinned rows.  (Host
+    // callbacks on the stream were measured first: their dispatch latency alone capped progressive mode at ~600 frames/s.)
+    std::vector<cudaEvent_t> band_copied;   // single pass: one per band
+    cudaEvent_t pass_copied[2] = {nullptr, nullptr};
+    // single pass: band b covers tile rows [band_ty[b], band_ty[b + 1])
+    int n_bands = 1;
+    std::vector<int> band_ty;
+    std::vector<char> band_done;        // guarded by mu: published
+    int bands_synced = 0;               // consumer only: bands whose copy it has waited for
+    std::atomic<int> next_band{0};
+    // progressive: pass index held by h_frame[b], -1 = free (guarded by mu)
+    int buf_pass[2] = {-1, -1};
+    int passes_done = 0;
+    // consumer side (one thread)
+    int pass_consumed = 0, cursor_x = 0, cursor_y = 0, avail_rows = 0;
+    const uint8_t* cur = nullptr;
+    std::atomic<double> stats_first_ms{-1.0};   // host time until the consumer held its first rows
     volatile int cancel = 0;
     int error = RTB_OK;
     std::string error_msg;
+    int workers_running = 0;
     bool finished = false;
+    rtb_stats stats{};                  // summed over finished bands / passes (guarded by mu)
+    std::chrono::steady_clock::time_point t_begin;
 };
 
 namespace {
 
 constexpr int PIXELS_PER_MSG = 60;  // RenderJob::PIXELS_PER_MSG, src/server.rs:145
+// Band schedule of a single-pass job: the first bands are small, so the first records leave early; later bands grow,
+// because every band pays for its own tail of under-filled wavefront iterations (sizes in samples: 8 Mi, 8 Mi, 16 Mi,
+// 32 Mi, then 64 Mi each; a frame below 16 Mi samples is one band)
+constexpr uint64_t BAND_MIN_SAMPLES = 8ull << 20;
+constexpr int BAND_GROWTH_CAP = 8;   // largest band = BAND_GROWTH_CAP x the first
 
-void job_worker(rtb_job* j) {
+double ms_since(const std::chrono::steady_clock::time_point& t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void add_stats(rtb_stats& d, const rtb_stats& s) {
+    d.samples += s.samples; d.rays_primary += s.rays_primary; d.rays_extension += s.rays_extension; d.rays_shadow += s.rays_shadow;
+    d.iterations += s.iterations; d.kernel_launches += s.kernel_launches; d.bvh_node_visits += s.bvh_node_visits;
+    d.bvh_tri_tests += s.bvh_tri_tests; d.render_ms += s.render_ms; d.extend_ms += s.extend_ms; d.bin_ms += s.bin_ms;
+    d.generate_ms += s.generate_ms; d.resolve_ms += s.resolve_ms; d.shade_ms += s.shade_ms; d.rays_bvh += s.rays_bvh;
+    d.shadow_bvh += s.shadow_bvh; d.paths_queued += s.paths_queued;
+}
+
+void publish_band(rtb_job* j, int band) {
+    {
+        std::lock_guard<std::mutex> lk(j->mu);
+        j->band_done[band] = 1;
+    }
+    j->cv.notify_all();
+}
+
+void publish_pass(rtb_job* j, int pass, int buffer) {
+    {
+        std::lock_guard<std::mutex> lk(j->mu);
+        j->buf_pass[buffer] = pass;
+        j->passes_done = pass + 1;
+    }
+    j->cv.notify_all();
+}
+
+void job_worker(rtb_job* j, int worker) {
     rtb_scene* sc = j->scene;
     const rtb_params& p = j->params;
-    RenderContext* c = acquire_context(sc);
-    RenderArgs a;
-    rtb_stats st{};
+    const int tiles_x = (p.width + TILE - 1) / TILE, tiles_y = (p.height + TILE - 1) / TILE;
+    const size_t frame = j->frame_bytes;
+    const bool progressive = j->passes > 1;
+    int band_tile_rows = progressive ? tiles_y : 1;   // the largest band
+    for (int b = 0; !progressive && b < j->n_bands; ++b) band_tile_rows = std::max(band_tile_rows, j->band_ty[b + 1] - j->band_ty[b]);
+    // samples in flight at once: one band of a single-pass job, one pass of a progressive one
+    uint64_t band_samples = (uint64_t)band_tile_rows * tiles_x * 1024ull * 4ull * (uint64_t)std::max(1, p.spp / 4);
+    if (progressive) band_samples = (band_samples + j->passes - 1) / j->passes;
+    const uint32_t P = pool_for(band_samples, p.pool_paths);
+    const uint32_t SP = p.estimator == RTB_EST_NEE ? P : 2 * P;
+    RenderContext* c = acquire_context(sc, P);
     auto finish = [&](int rc) {
-        {
-            std::lock_guard<std::mutex> lk(sc->mu);
-            sc->last_stats = st;
-        }
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);   // the pinned frame is no longer written by this worker
         release_context(sc, c);
-        std::lock_guard<std::mutex> lk(j->mu);
-        if (rc != RTB_OK && rc != RTB_ECANCELLED) { j->error = rc; j->error_msg = g_last_error; }
-        j->finished = true;
+        bool last;
+        {
+            std::lock_guard<std::mutex> lk(j->mu);
+            if (rc != RTB_OK && rc != RTB_ECANCELLED && j->error == RTB_OK) { j->error = rc; j->error_msg = g_last_error; j->cancel = 1; }
+            last = --j->workers_running == 0;
+            if (last) {
+                j->finished = true;
+                j->stats.wall_ms = ms_since(j->t_begin);
+            }
+        }
+        if (last) publish_stats(sc, j->stats, false);
         j->cv.notify_all();
     };
-    uint32_t P = default_pool(&p);
-    uint32_t SP = p.estimator == RTB_EST_NEE ? P : 2 * P;
     const size_t accum_elems = (size_t)p.width * p.height * 4;
-    const size_t frame = (size_t)p.width * p.height * 3;
-    int rc = ensure_context(sc, c, P, SP, accum_elems);
-    if (rc == RTB_OK) rc = ensure_rgb(c, frame, true);
+    int rc = ensure_context(sc, c, P, SP, accum_elems, requested_bin_bits(sc, &p) > 0);
+    if (rc == RTB_OK) rc = ensure_rgb(c, frame * (progressive ? 2 : 1), false);
     if (rc != RTB_OK) return finish(rc);
+    RenderArgs a;
     fill_args(sc, &p, c, a);
-    if (cudaMemsetAsync(c->accum, 0, accum_elems * sizeof(float4), c->stream) != cudaSuccess) return finish(fail(RTB_ECUDA, "memset"));
     const uint32_t ks_total = (uint32_t)a.num_samples * 4u;
-    const int passes = std::max(1, j->passes);
+    auto cuda_fail = [&](cudaError_t e) { return finish(fail(RTB_ECUDA, std::string("streaming job: ") + cudaGetErrorString(e))); };
+
+    if (!progressive) {
+        for (;;) {
+            const int b = j->next_band.fetch_add(1);
+            if (b >= j->n_bands) break;
+            if (j->cancel) return finish(RTB_ECANCELLED);
+            const int ty0 = j->band_ty[b], ty1 = j->band_ty[b + 1];
+            const int row0 = ty0 * TILE, row1 = std::min(p.height, ty1 * TILE);
+            a.tile_base = ty0 * tiles_x;
+            a.n_local_tiles = (ty1 - ty0) * tiles_x;
+            cudaError_t e = cudaMemsetAsync(c->accum + (size_t)row0 * p.width * 4, 0, (size_t)(row1 - row0) * p.width * 4 * sizeof(float4), c->stream);
+            if (e != cudaSuccess) return cuda_fail(e);
+            rtb_stats bs{};
+            bool cancelled = false;
+            if (ks_total > 0) {
+                rc = run_wavefront(sc, c, a, 0u, ks_total, false, &j->cancel, bs, cancelled);   // returns with the band's paths finished
+                if (rc != RTB_OK) return finish(rc);
+            }
+            if (cancelled || j->cancel) return finish(RTB_ECANCELLED);
+            // resolve + copy + publish on the side stream; this thread goes straight on to its next band
+            const int n = a.n_local_tiles * 1024;
+            k_resolve<<<(n + 255) / 256, 256, 0, c->copy_stream>>>(a, c->d_rgb, nullptr, 1);
+            const size_t off = (size_t)row0 * p.width * 3, bytes = (size_t)(row1 - row0) * p.width * 3;
+            e = cudaMemcpyAsync(j->h_frame[0] + off, c->d_rgb + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(j->band_copied[b], c->copy_stream);
+            if (e != cudaSuccess) return cuda_fail(e);
+            bs.kernel_launches += 1;
+            {
+                std::lock_guard<std::mutex> lk(j->mu);
+                add_stats(j->stats, bs);
+            }
+            publish_band(j, b);
+        }
+        return finish(RTB_OK);
+    }
+
+    // progressive: one band = the frame; pass n + 1 renders while pass n is copied and consumed
+    a.tile_base = 0;
+    a.n_local_tiles = tiles_x * tiles_y;
+    if (cudaError_t e = cudaMemsetAsync(c->accum, 0, accum_elems * sizeof(float4), c->stream); e != cudaSuccess) return cuda_fail(e);
+    const int passes = j->passes;
     for (int pass = 0; pass < passes; ++pass) {
-        uint32_t k0 = (uint32_t)((uint64_t)ks_total * pass / passes), k1 = (uint32_t)((uint64_t)ks_total * (pass + 1) / passes);
+        const uint32_t k0 = (uint32_t)((uint64_t)ks_total * pass / passes), k1 = (uint32_t)((uint64_t)ks_total * (pass + 1) / passes);
+        rtb_stats ps{};
         bool cancelled = false;
         if (k1 > k0) {
-            rc = run_wavefront(sc, c, a, k0, k1, false, &j->cancel, st, cancelled);
+            rc = run_wavefront(sc, c, a, k0, k1, false, &j->cancel, ps, cancelled);
             if (rc != RTB_OK) return finish(rc);
         }
         if (cancelled || j->cancel) return finish(RTB_ECANCELLED);
-        // resolve with the per-sub-pixel sample counts reached so far
+        const int b = pass & 1;
+        {   // the pinned frame of this parity must have been consumed (passes stay in order, memory stays bounded)
+            std::unique_lock<std::mutex> lk(j->mu);
+            j->cv.wait(lk, [&] { return j->buf_pass[b] < 0 || j->cancel; });
+            if (j->cancel) { lk.unlock(); return finish(RTB_ECANCELLED); }
+            add_stats(j->stats, ps);
+        }
         RenderArgs r = a;
-        r.ks_done = k1;
-        rc = resolve_to(c, r, c->d_rgb, nullptr, 1, st);
-        if (rc != RTB_OK) return finish(rc);
-        cudaError_t e = cudaMemcpyAsync(c->h_rgb, c->d_rgb, frame, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) return finish(fail(RTB_ECUDA, cudaGetErrorString(e)));
-        std::unique_lock<std::mutex> lk(j->mu);
-        // wait until the consumer has drained the previous pass (keeps passes in order, bounded memory)
-        j->cv.wait(lk, [&] { return !j->frame_fresh || j->cancel; });
-        if (j->cancel) { lk.unlock(); return finish(RTB_ECANCELLED); }
-        j->frame.assign(c->h_rgb, c->h_rgb + frame);
-        j->frame_fresh = true;
-        j->passes_done = pass + 1;
-        j->cursor_x = j->cursor_y = 0;
-        j->cv.notify_all();
+        r.ks_done = k1;   // resolve with the per-sub-pixel sample counts reached so far
+        const int n = a.n_local_tiles * 1024;
+        k_resolve<<<(n + 255) / 256, 256, 0, c->stream>>>(r, c->d_rgb + (size_t)b * frame, nullptr, 1);   // in stream order: before the next pass adds samples
+        cudaError_t e = cudaEventRecord(j->ev_resolved[b], c->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, j->ev_resolved[b], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(j->h_frame[b], c->d_rgb + (size_t)b * frame, frame, cudaMemcpyDeviceToHost, c->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(j->pass_copied[b], c->copy_stream);
+        if (e != cudaSuccess) return cuda_fail(e);
+        publish_pass(j, pass, b);
     }
     finish(RTB_OK);
+}
+
+// Makes rows [cursor_y, avail_rows) of job->cur readable.  block = false: only looks.  Returns 1 = rows available,
+// 0 = the job is complete, RTB_ESTOPPED / negative error, 2 = nothing yet (non-blocking only).
+int job_acquire_rows(rtb_job* job, bool block) {
+    if (job->cursor_y < job->avail_rows) return 1;
+    const bool progressive = job->passes > 1;
+    cudaEvent_t copied = nullptr;
+    int rows_after = 0;
+    {
+        std::unique_lock<std::mutex> lk(job->mu);
+        const int b = job->pass_consumed & 1;
+        const int band = job->bands_synced;   // single pass: the band the cursor is about to enter
+        auto ready = [&] {
+            return progressive ? job->buf_pass[b] == job->pass_consumed
+                               : (job->pass_consumed == 0 && band < job->n_bands && job->band_done[band]);
+        };
+        // a worker that failed raises `cancel` to stop its peers: the error is reported once they have all stopped
+        if (block) job->cv.wait(lk, [&] { return ready() || job->finished || (job->cancel && job->error == RTB_OK); });
+        if (job->cancel && job->error == RTB_OK) return RTB_ESTOPPED;
+        if (!ready()) {
+            if (!job->finished) return 2;
+            if (job->error != RTB_OK) return fail(job->error, job->error_msg);
+            return 0;
+        }
+        if (progressive) {
+            copied = job->pass_copied[b];
+            job->cur = job->h_frame[b];
+            rows_after = job->params.height;
+        } else {
+            copied = job->band_copied[band];
+            job->cur = job->h_frame[0];
+            rows_after = std::min(job->params.height, job->band_ty[band + 1] * TILE);
+        }
+    }
+    // the copy was enqueued before the band / pass was published: wait for it outside the lock
+    if (!block && cudaEventQuery(copied) == cudaErrorNotReady) return 2;
+    cudaError_t e = cudaEventSynchronize(copied);
+    if (e != cudaSuccess) return fail(RTB_ECUDA, std::string("streaming job: ") + cudaGetErrorString(e));
+    if (!progressive) job->bands_synced++;
+    job->avail_rows = rows_after;
+    if (job->stats_first_ms < 0) job->stats_first_ms = ms_since(job->t_begin);
+    return 1;
+}
+
+// the consumer has sent the last row of a pass
+void job_pass_consumed(rtb_job* job) {
+    std::lock_guard<std::mutex> lk(job->mu);
+    if (job->passes > 1) job->buf_pass[job->pass_consumed & 1] = -1;
+    job->pass_consumed++;
+    job->cursor_x = job->cursor_y = 0;
+    job->avail_rows = 0;
+    job->cv.notify_all();
+}
+
+
+int job_next_record(rtb_job* job, bool block, uint16_t* x, uint16_t* y, uint8_t* n, uint8_t* rgb) {
+    const int rc = job_acquire_rows(job, block);
+    if (rc != 1) return rc;
+    const int w = job->params.width, h = job->params.height;
+    int cx = job->cursor_x, cy = job->cursor_y;
+    const int cnt = std::min(PIXELS_PER_MSG, w - cx);  // windows(), src/server.rs:254-280
+    *x = (uint16_t)cx;
+    *y = (uint16_t)cy;
+    *n = (uint8_t)cnt;
+    std::memcpy(rgb, job->cur + ((size_t)cy * w + cx) * 3, (size_t)cnt * 3);
+    cx += cnt;
+    if (cx >= w) { cx = 0; ++cy; }
+    job->cursor_x = cx;
+    job->cursor_y = cy;
+    if (cy >= h) job_pass_consumed(job);
+    return 1;
 }
 
 }  // namespace
@@ -1251,11 +1547,51 @@ int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rt
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
     if (params->world != 1) return fail(RTB_EINVAL, "streaming jobs render whole frames (world must be 1)");
+    CU_TRY(cudaSetDevice(scene->device));
     rtb_job* j = new rtb_job();
     j->scene = scene;
     j->params = *params;
     j->passes = std::max(1, passes);
-    j->worker = std::thread(job_worker, j);
+    j->frame_bytes = (size_t)params->width * params->height * 3;
+    j->stats.first_record_ms = -1.0;
+    const bool progressive = j->passes > 1;
+    // bands of whole tile rows (see BAND_MIN_SAMPLES)
+    const int tiles_x = (params->width + TILE - 1) / TILE, tiles_y = (params->height + TILE - 1) / TILE;
+    const uint64_t row_samples = (uint64_t)tiles_x * 1024ull * 4ull * (uint64_t)std::max(1, params->spp / 4);
+    int rows = (int)std::max<uint64_t>(1, (BAND_MIN_SAMPLES + row_samples - 1) / row_samples);
+    int growth_cap = BAND_GROWTH_CAP;
+    if (const char* e = getenv("RTB_BAND_TILE_ROWS")) { rows = std::max(1, atoi(e)); growth_cap = 1; }   // test / experiment knobs
+    if (const char* e = getenv("RTB_BAND_GROWTH_CAP")) growth_cap = std::max(1, atoi(e));
+    j->band_ty.assign(1, 0);
+    if (progressive || 2 * rows > tiles_y) j->band_ty.push_back(tiles_y);   // one band
+    else
+        for (int ty = 0, k = 0, mult = 1; ty < tiles_y; ++k) {
+            if (k >= 2) mult = std::min(mult * 2, growth_cap);
+            ty = std::min(tiles_y, ty + rows * mult);
+            if (tiles_y - ty < rows) ty = tiles_y;   // no sliver at the end
+            j->band_ty.push_back(ty);
+        }
+    j->n_bands = (int)j->band_ty.size() - 1;
+    j->band_done.assign((size_t)j->n_bands, 0);
+    cudaError_t e = cudaMallocHost((void**)&j->h_frame[0], std::max<size_t>(j->frame_bytes, 1));
+    if (e == cudaSuccess && progressive) e = cudaMallocHost((void**)&j->h_frame[1], std::max<size_t>(j->frame_bytes, 1));
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&j->ev_resolved[k], cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&j->pass_copied[k], cudaEventDisableTiming);
+    j->band_copied.assign((size_t)j->n_bands, nullptr);
+    for (int k = 0; k < j->n_bands && e == cudaSuccess && !progressive; ++k) e = cudaEventCreateWithFlags(&j->band_copied[k], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        for (auto& h : j->h_frame) if (h) cudaFreeHost(h);
+        for (auto& ev : j->ev_resolved) if (ev) cudaEventDestroy(ev);
+        for (auto& ev : j->pass_copied) if (ev) cudaEventDestroy(ev);
+        for (auto& ev : j->band_copied) if (ev) cudaEventDestroy(ev);
+        delete j;
+        return fail(RTB_ECUDA, std::string("rtb_job_begin: ") + cudaGetErrorString(e));
+    }
+    int n_workers = !progressive && j->n_bands >= 4 ? 2 : 1;
+    if (const char* env = getenv("RTB_JOB_WORKERS")) n_workers = std::min(std::max(1, atoi(env)), std::max(1, j->n_bands));
+    j->workers_running = n_workers;
+    j->t_begin = std::chrono::steady_clock::now();
+    for (int w = 0; w < n_workers; ++w) j->workers.emplace_back(job_worker, j, w);
     *out = j;
     return RTB_OK;
 }
@@ -1263,48 +1599,24 @@ int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rt
 // returns 1 = record produced, 0 = frame(s) complete, RTB_ESTOPPED after a cancel, or another negative error
 int rtb_job_next(rtb_job* job, uint16_t* x, uint16_t* y, uint8_t* n, uint8_t* rgb) {
     if (!job || !x || !y || !n || !rgb) return fail(RTB_EINVAL, "NULL argument");
-    std::unique_lock<std::mutex> lk(job->mu);
-    job->cv.wait(lk, [&] { return job->frame_fresh || job->finished || job->cancel; });
-    if (job->cancel) return RTB_ESTOPPED;
-    if (!job->frame_fresh) {
-        if (job->error != RTB_OK) return fail(job->error, job->error_msg);
-        return 0;
-    }
-    const int w = job->params.width, h = job->params.height;
-    int cx = job->cursor_x, cy = job->cursor_y;
-    int cnt = std::min(PIXELS_PER_MSG, w - cx);  // windows(), src/server.rs:254-280
-    *x = (uint16_t)cx;
-    *y = (uint16_t)cy;
-    *n = (uint8_t)cnt;
-    std::memcpy(rgb, job->frame.data() + ((size_t)cy * w + cx) * 3, (size_t)cnt * 3);
-    cx += cnt;
-    if (cx >= w) { cx = 0; ++cy; }
-    job->cursor_x = cx;
-    job->cursor_y = cy;
-    if (cy >= h) {  // pass fully sent
-        job->frame_fresh = false;
-        job->pass_consumed++;
-        job->cv.notify_all();
-    }
-    return 1;
+    return job_next_record(job, true, x, y, n, rgb);
 }
 
-// whole-frame form of rtb_job_next: hands out the latest finished pass in one copy
+// whole-frame form of rtb_job_next: hands out the next finished pass in one copy (a single-pass job: the frame, once every band is in)
 int rtb_job_next_frame(rtb_job* job, uint8_t* rgb8_out, int32_t* pass_index) {
     if (!job || !rgb8_out) return fail(RTB_EINVAL, "NULL argument");
-    std::unique_lock<std::mutex> lk(job->mu);
-    job->cv.wait(lk, [&] { return job->frame_fresh || job->finished || job->cancel; });
-    if (job->cancel) return RTB_ESTOPPED;
-    if (!job->frame_fresh) {
-        if (job->error != RTB_OK) return fail(job->error, job->error_msg);
-        return 0;
+    const int h = job->params.height;
+    // a single-pass job delivers its frame once every band is in: walk the cursor to the last band
+    for (;;) {
+        const int rc = job_acquire_rows(job, true);
+        if (rc != 1) return rc;
+        if (job->avail_rows >= h) break;
+        job->cursor_x = 0;
+        job->cursor_y = job->avail_rows;
     }
-    std::memcpy(rgb8_out, job->frame.data(), job->frame.size());
-    if (pass_index) *pass_index = job->passes_done - 1;
-    job->frame_fresh = false;
-    job->pass_consumed++;
-    job->cursor_x = job->cursor_y = 0;
-    job->cv.notify_all();
+    std::memcpy(rgb8_out, job->cur, job->frame_bytes);
+    if (pass_index) *pass_index = job->pass_consumed;
+    job_pass_consumed(job);
     return 1;
 }
 
@@ -1313,13 +1625,9 @@ int rtb_job_next_messages(rtb_job* job, uint8_t* buf, int64_t buf_bytes, int32_t
     int64_t off = 0;
     int produced = 0;
     while (produced < max_records && off + 6 + 3 * PIXELS_PER_MSG <= buf_bytes) {
-        {   // never block once something has been produced
-            std::unique_lock<std::mutex> lk(job->mu);
-            if (produced > 0 && !job->frame_fresh) break;
-        }
         uint16_t x, y;
         uint8_t n;
-        int rc = rtb_job_next(job, &x, &y, &n, buf + off + 6);
+        const int rc = job_next_record(job, produced == 0, &x, &y, &n, buf + off + 6);   // never block once something has been produced
         if (rc != 1) {
             *bytes_written = off;
             return produced > 0 ? produced : rc;
@@ -1336,6 +1644,16 @@ int rtb_job_next_messages(rtb_job* job, uint8_t* buf, int64_t buf_bytes, int32_t
     return produced;
 }
 
+// counters of the job so far (finished bands / passes); first_record_ms and wall_ms are filled for jobs only
+int rtb_job_stats(rtb_job* job, rtb_stats* stats) {
+    if (!job || !stats) return fail(RTB_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(job->mu);
+    *stats = job->stats;
+    stats->first_record_ms = job->stats_first_ms.load();
+    if (!job->finished) stats->wall_ms = ms_since(job->t_begin);
+    return RTB_OK;
+}
+
 int rtb_job_cancel(rtb_job* job) {
     if (!job) return fail(RTB_EINVAL, "NULL job");
     std::lock_guard<std::mutex> lk(job->mu);
@@ -1346,13 +1664,22 @@ int rtb_job_cancel(rtb_job* job) {
 
 int rtb_job_end(rtb_job* job) {
     if (!job) return fail(RTB_EINVAL, "NULL job");
+    bool early;
     {
         std::lock_guard<std::mutex> lk(job->mu);
-        if (!job->finished) job->cancel = 1;
+        early = !job->finished;
+        if (early) job->cancel = 1;
         job->cv.notify_all();
     }
-    if (job->worker.joinable()) job->worker.join();
-    int was_cancelled = job->cancel && job->error == RTB_OK && job->passes_done < job->passes;
+    for (auto& t : job->workers) if (t.joinable()) t.join();
+    bool complete = job->passes > 1 ? job->passes_done >= job->passes : true;
+    for (char d : job->band_done) complete = complete && (job->passes > 1 || d);
+    const int was_cancelled = job->cancel && job->error == RTB_OK && !complete;
+    cudaSetDevice(job->scene->device);
+    for (auto& h : job->h_frame) if (h) cudaFreeHost(h);
+    for (auto& ev : job->ev_resolved) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : job->pass_copied) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : job->band_copied) if (ev) cudaEventDestroy(ev);
     delete job;
     return was_cancelled ? RTB_ECANCELLED : RTB_OK;
 }

@@ -22,8 +22,10 @@
 namespace rtb {
 
 constexpr int STACK_SMEM = 24;   // stack levels kept in shared memory (per thread); a 4-wide step pushes up to three
-constexpr int STACK_LOCAL = 72;  // overflow levels in local memory: 96 in total covers any Karras tree over
-                                 // 63-bit keys + 32-bit tie-break (prefix lengths grow strictly along a path)
+constexpr int STACK_LOCAL = 72;  // overflow levels in local memory.  The loader measures the depth of the tree it built and
+                                 // refuses (RTB_EUNSUPPORTED) what does not fit BVH_MAX_DEPTH = STACK_SMEM + STACK_LOCAL levels
+                                 // (lbvh.hpp; PLOC trees have no a-priori depth bound, a too deep one is rebuilt as a Karras
+                                 // tree first); the spill path below additionally never writes past the array
 constexpr int NODE_SENTINEL = (int)0x80000000;  // negative like a leaf, but no leaf encodes to it (first < 2^28)
 constexpr float T_EPS = 1e-4f;          // sphere / triangle t threshold
 constexpr float DN_EPS = 1e-4f;         // plane / triangle parallel threshold
@@ -420,8 +422,10 @@ __device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, uint32_t 
         T.sp += both ? 1 : (none && T.sp > 0 ? -1 : 0);
     } else {  // spill levels (local memory); T.sp == STACK_SMEM pops from shared memory via trav_pop
         if (both) {
-            lstack[T.sp - STACK_SMEM] = farc;
-            ++T.sp;
+            if (T.sp - STACK_SMEM < STACK_LOCAL) {   // cannot fail for a tree the loader accepted; never write past the array
+                lstack[T.sp - STACK_SMEM] = farc;
+                ++T.sp;
+            }
             T.node = nearc;
         } else if (none) {
             trav_pop(T, sbase, sstride, lstack);
@@ -434,7 +438,8 @@ __device__ __forceinline__ void trav_inner(const DevScene& S, Trav& T, uint32_t 
 // ---- 4-wide step ----------------------------------------------------------------------------------
 __device__ __forceinline__ void trav_push(Trav& T, uint32_t sbase, uint32_t sstride, int* lstack, int v) {
     if (T.sp < STACK_SMEM) sts_i32(sbase + (uint32_t)T.sp * sstride, v);
-    else lstack[T.sp - STACK_SMEM] = v;
+    else if (T.sp - STACK_SMEM < STACK_LOCAL) lstack[T.sp - STACK_SMEM] = v;
+    else return;   // deeper than any accepted tree (see STACK_LOCAL)
     ++T.sp;
 }
 // one node of the 4-wide table: four slab tests, then the hit children sorted by entry distance — the nearest is

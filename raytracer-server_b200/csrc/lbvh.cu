@@ -471,7 +471,8 @@ __global__ void k_quantise_nodes(int n_nodes, const float4* __restrict__ nodes, 
     out[(size_t)i * 2 + 1] = b;
 }
 
-static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err);
+static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err,
+                           bool force_karras = false);
 
 // The 4-wide table: every binary node kept becomes a node with up to four children — its two children, the larger
 // (by box area) inner child replaced by its own two children until four are there.  A ray then waits for half as many
@@ -501,6 +502,20 @@ static bool collapse_to_bvh4(cudaStream_t stream, LbvhResult& out, const float* 
         const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
         return dx * dy + dy * dz + dz * dx;
     };
+    {   // depth of the binary tree (the traversal stack is finite: build_lbvh checks it against BVH_MAX_DEPTH)
+        std::vector<std::pair<int, int>> st;
+        st.push_back({out.root, 1});
+        out.depth = 0;
+        while (!st.empty()) {
+            const auto [node, d] = st.back();
+            st.pop_back();
+            out.depth = std::max(out.depth, d);
+            Child c[2];
+            children_of(node, c);
+            for (int k = 0; k < 2; ++k)
+                if (c[k].ref >= 0) st.push_back({c[k].ref, d + 1});
+        }
+    }
     std::vector<uint32_t> words;      // 16 per wide node
     std::vector<int> todo;            // binary nodes that become wide nodes, in emission order
     std::vector<int> wide_of(out.n_nodes, -1);
@@ -552,8 +567,9 @@ static bool collapse_to_bvh4(cudaStream_t stream, LbvhResult& out, const float* 
     return true;
 }
 
-bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err) {
-    if (!build_lbvh_f32(d_verts, d_tri_obj, n, stream, out, err)) return false;
+static bool build_lbvh_tables(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err,
+                              bool force_karras) {
+    if (!build_lbvh_f32(d_verts, d_tri_obj, n, stream, out, err, force_karras)) return false;
     if (n <= 0) return true;
     float3 qinv;
     float* qi = &qinv.x;
@@ -573,10 +589,31 @@ bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStrea
     return collapse_to_bvh4(stream, out, qi, err);
 }
 
-static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err) {
+// The traversal stack holds BVH_MAX_DEPTH levels.  A Karras tree over 63-bit keys + a 32-bit tie-break cannot be deeper
+// than 95; a PLOC tree has no such bound (a chain of single mutual-pair merges adds one level per round), so a PLOC tree
+// that came out too deep is rebuilt with the Karras hierarchy, and a mesh whose tree still does not fit is refused
+// ("unsupported: ..." -> RTB_EUNSUPPORTED) instead of being traversed with an overflowing stack.
+bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err) {
+    int max_depth = BVH_MAX_DEPTH;
+    if (const char* e = getenv("RTB_BVH_MAX_DEPTH")) max_depth = std::min(BVH_MAX_DEPTH, std::max(1, atoi(e)));   // test hook
+    if (!build_lbvh_tables(d_verts, d_tri_obj, n, stream, out, err, false)) return false;
+    if (out.depth > max_depth) {
+        free_lbvh(out);
+        if (!build_lbvh_tables(d_verts, d_tri_obj, n, stream, out, err, true)) return false;
+    }
+    if (out.depth > max_depth) {
+        err = "unsupported: the mesh's BVH is " + std::to_string(out.depth) + " levels deep, the traversal stack holds " + std::to_string(max_depth);
+        free_lbvh(out);
+        return false;
+    }
+    return true;
+}
+
+static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err,
+                           bool force_karras) {
     out = LbvhResult();
     if (n <= 0) return true;
-    if (const char* e = getenv("RTB_BVH")) if (std::string(e) == "sah") return build_sah_host(d_verts, d_tri_obj, n, stream, out, err);
+    if (const char* e = getenv("RTB_BVH")) if (!force_karras && std::string(e) == "sah") return build_sah_host(d_verts, d_tri_obj, n, stream, out, err);
     const int T = 256;
     const int nb = (n + T - 1) / T;
     const int ni = n - 1;
@@ -609,7 +646,7 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
     out.d_tris = d_tris;
     LBVH_CHECK(cudaMalloc((void**)&out.d_tri_nrm, (size_t)n * sizeof(float4)));
     const char* mode_env = getenv("RTB_BVH");
-    const bool karras = mode_env && std::string(mode_env) == "lbvh";   // default: PLOC on the same Morton order
+    const bool karras = force_karras || (mode_env && std::string(mode_env) == "lbvh");   // default: PLOC on the same Morton order
 
     Bounds6 hb;
     int leaf_max = LEAF_MAX;

@@ -8,6 +8,8 @@
 
 namespace rtb {
 
+constexpr int BVH_MAX_DEPTH = 96;   // levels the traversal stack holds (intersect.cuh: STACK_SMEM + STACK_LOCAL)
+
 struct LbvhResult {
     float4* d_nodes = nullptr;  // 4 x float4 per node: c0 (lo.x hi.x lo.y hi.y), c1 (same), (c0.lo.z c0.hi.z c1.lo.z c1.hi.z), refs
     uint4* d_qnodes = nullptr;  // the node table the traversal reads: 2 x uint4 (32 B) per node, child boxes quantised to 16 bits
@@ -21,6 +23,7 @@ struct LbvhResult {
     int root = 0;               // encoded reference: >= 0 node index, < 0 leaf ~((first << 3) | (count - 1))
     int n_nodes = 0;
     int n_leaves = 0;
+    int depth = 0;              // levels of inner nodes on the longest root-to-leaf path (0: the whole mesh is one leaf)
     float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
 };
 

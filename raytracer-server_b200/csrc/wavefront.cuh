@@ -65,6 +65,7 @@ struct alignas(128) PaddedCounter {
 struct DevCtrl {
     PaddedCounter ext_head_[2], ext_tail_[2], sh_head_[2], cursor_trav_, cursor_shade_;
     uint32_t gen_count;
+    int32_t tile_base, n_tiles;   // local tiles [tile_base, tile_base + n_tiles) are the frame region of this run (streaming jobs go band by band)
     uint32_t live[2], sh_live[2];   // FILLED entries of path / shadow queue c (the heads / tails also count reserved-but-unfilled slots)
     uint32_t active;        // paths alive in the current queue after k_prepare (+ reserved samples + pending shadow rays)
     unsigned long long gen_base, work_next, work_total;
@@ -91,6 +92,7 @@ struct RenderArgs {
     SmallScene ss;       // analytic table of small scenes (k_shade<MODE, NP, NS> with NP > 0)
     int estimator;
     int rank, world, tiles_x, tiles_y, n_local_tiles;
+    int tile_base;       // first LOCAL tile of this launch series (streaming jobs render a frame band by band; 0 = whole shard)
     uint32_t P, SP;          // most paths / shadow rays alive at once
     uint32_t Pcap, SPcap;    // physical slots per queue: P, SP + room for the unfilled tails of k_shade's per-warp segments
     PathQueue q[2];
@@ -108,6 +110,8 @@ struct RenderArgs {
     const int32_t* probe_py;
     const int32_t* probe_sample;
     int n_probe;
+    int pixel_list;      // 1: probe_px / probe_py list PIXELS (rtb_sample_pixels): every listed pixel gets the full sample set,
+                         //    work order (k, sub-pixel) major like a frame, accumulator index = list index * 4 + sub-pixel
     int tune_refill, tune_steps;   // traversal knobs (0 = defaults above); rtb_params.reserved[1], [2]
     // graph mode (small frames): k_prepare publishes {iteration, live paths} to mapped pinned host memory so the
     // host can stop launching without a copy or an event per iteration
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(const __grid_constant__
             unsigned long long wi = base + j;
             int x, y, sample;
             uint32_t acc, rng_pixel;
-            if (a.probe_px) {
+            if (a.probe_px && !a.pixel_list) {
                 x = a.probe_px[wi];
                 y = a.probe_py[wi];
                 sample = a.probe_sample[wi];
@@ -239,14 +243,20 @@ __global__ void __launch_bounds__(WF_THREADS) k_generate(const __grid_constant__
                 rng_pixel = (uint32_t)(y * a.width + x);
             } else {
                 // work order: (k, sub-pixel) major, local pixel minor -> neighbouring lanes = neighbouring pixels
-                unsigned long long npl = (unsigned long long)a.n_local_tiles * 1024ull;
+                unsigned long long npl = a.pixel_list ? (unsigned long long)a.n_probe : (unsigned long long)C->n_tiles * 1024ull;
                 uint32_t ks = (uint32_t)(wi / npl);
                 int lp = (int)(wi - (unsigned long long)ks * npl);
                 int k = ks >> 2, sub = ks & 3;
-                valid = local_to_xy(lp, a.rank, a.world, a.tiles_x, a.width, a.height, x, y);
+                if (a.pixel_list) {
+                    x = a.probe_px[lp];
+                    y = a.probe_py[lp];
+                    acc = (uint32_t)lp * 4u + (uint32_t)sub;
+                } else {
+                    valid = local_to_xy(lp + C->tile_base * 1024, a.rank, a.world, a.tiles_x, a.width, a.height, x, y);
+                    acc = (uint32_t)(y * a.width + x) * 4u + (uint32_t)sub;
+                }
                 sample = sub * a.num_samples + k;
                 rng_pixel = (uint32_t)(y * a.width + x);
-                acc = rng_pixel * 4u + (uint32_t)sub;
             }
             if (valid) {
                 int sub = sample / a.num_samples;
@@ -728,7 +738,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                 }
                 const float p = depth <= 5u ? 1.0f : 0.9f;  // MAX_BOUNCES / SURVIVAL_PROBABILITY (src/scene.rs:109-110,164-168)
                 const float inv_p = depth <= 5u ? 1.0f : (1.0f / 0.9f);
-                const uint32_t rng_pixel = probe_mode ? (uint32_t)(a.probe_py[acc] * a.width + a.probe_px[acc]) : acc >> 2;
+                const uint32_t pidx = probe_mode && a.pixel_list ? acc >> 2 : acc;   // probe item, or entry of the pixel list
+                const uint32_t rng_pixel = probe_mode ? (uint32_t)(a.probe_py[pidx] * a.width + a.probe_px[pidx]) : acc >> 2;
                 const bool dead_surface = mat.brdf == 0 && mat.k.x == 0.f && mat.k.y == 0.f && mat.k.z == 0.f;
                 const bool dead_path = beta.x == 0.f && beta.y == 0.f && beta.z == 0.f;
                 if (!dead_surface && !dead_path && depth < MAX_DEPTH_FIELD) {
@@ -978,7 +989,7 @@ __global__ void k_resolve(RenderArgs a, unsigned char* __restrict__ out_rgb8, fl
     int lp = blockIdx.x * blockDim.x + threadIdx.x;
     if (lp >= a.n_local_tiles * 1024) return;
     int x, y;
-    bool in = local_to_xy(lp, a.rank, a.world, a.tiles_x, a.width, a.height, x, y);
+    bool in = local_to_xy(lp + a.tile_base * 1024, a.rank, a.world, a.tiles_x, a.width, a.height, x, y);
     float3 px = f3(0.f, 0.f, 0.f);
     if (in) {
         uint32_t p = (uint32_t)(y * a.width + x);
@@ -1006,6 +1017,24 @@ __global__ void k_resolve(RenderArgs a, unsigned char* __restrict__ out_rgb8, fl
         size_t o = (size_t)lp * 3;
         out_rgb8[o] = in ? r : 0; out_rgb8[o + 1] = in ? g : 0; out_rgb8[o + 2] = in ? b : 0;
     }
+}
+
+// sample_pixel's return value for a LIST of pixels (rtb_sample_pixels): accumulators [i*4 + sub] -> Vec3 in 0..255.5, i.e.
+// gamma_correct applied, before RenderJob::run's `as u8` (src/server.rs:360-368)
+__global__ void k_resolve_list(const float4* __restrict__ accum, int n, int num_samples, float* __restrict__ out3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float inv = num_samples > 0 ? 1.0f / (float)num_samples : 0.0f;
+    float3 px = f3(0.f, 0.f, 0.f);
+    for (int s = 0; s < 4; ++s) {
+        const float4 v = accum[(size_t)i * 4 + s];
+        px.x += clamp01_keep_nan(v.x * inv) * 0.25f;
+        px.y += clamp01_keep_nan(v.y * inv) * 0.25f;
+        px.z += clamp01_keep_nan(v.z * inv) * 0.25f;
+    }
+    out3[3 * i] = powf(clamp01_keep_nan(px.x), 1.0f / 2.2f) * 255.0f + 0.5f;
+    out3[3 * i + 1] = powf(clamp01_keep_nan(px.y), 1.0f / 2.2f) * 255.0f + 0.5f;
+    out3[3 * i + 2] = powf(clamp01_keep_nan(px.z), 1.0f / 2.2f) * 255.0f + 0.5f;
 }
 
 // scatter `world` tile-ordered shards into a scan-line frame

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -223,12 +224,26 @@ class Scene:
         return out
 
 
+def sample_pixels(xs, ys_screen, width: int, height: int, samples_per_pixel: int, scene: Scene, *, seed: int = 0,
+                  use_mis: bool = False) -> np.ndarray:
+    """sample_pixel for a batch of pixels (x, screen row y; rtb_sample_pixels): float32 [n, 3], the Vec3 of
+    src/server.rs:363 per pixel (0..255.5; `as u8` truncates it to the frame's bytes)."""
+    p = make_params(width, height, samples_per_pixel, use_mis=use_mis, seed=seed)
+    px = np.ascontiguousarray(xs, dtype=np.int32).reshape(-1)
+    py = np.ascontiguousarray(ys_screen, dtype=np.int32).reshape(-1)
+    assert px.size == py.size
+    out = np.empty((px.size, 3), dtype=np.float32)
+    ip = C.POINTER(C.c_int32)
+    _check(_abi.lib().rtb_sample_pixels(scene._h, C.byref(p), px.size, px.ctypes.data_as(ip), py.ctypes.data_as(ip),
+                                        out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out
+
+
 def sample_pixel(x: int, y: int, width: int, height: int, samples_per_pixel: int, scene: Scene, *, seed: int = 0,
                  use_mis: bool = False) -> np.ndarray:
-    """src/server.rs:320-364 for ONE pixel (the sampler's own bottom-up y).  Provided for interface
-    parity and spot checks; a GPU is driven per frame, so this renders the frame and picks the pixel."""
-    frame = scene.render(width, height, samples_per_pixel, seed=seed, use_mis=use_mis)
-    return frame[height - y - 1, x].copy()
+    """src/server.rs:320-364 for ONE pixel, same arguments: y is the sampler's own bottom-up row (the caller passes
+    height - y_screen - 1, src/server.rs:181).  Returns the Vec3 (0..255.5) — only this pixel's paths are traced."""
+    return sample_pixels([x], [height - y - 1], width, height, samples_per_pixel, scene, seed=seed, use_mis=use_mis)[0]
 
 
 class RenderJob:
@@ -242,9 +257,12 @@ class RenderJob:
         self.scene = scene
         self.params = make_params(width, height, samples_per_pixel, use_mis=use_mis, seed=seed, pool_paths=pool_paths)
         self._h = C.c_void_p()
+        # guards the handle: stop() may come from another thread (the server's event loop) while close() frees the job
+        self._lock = threading.Lock()
         _check(_abi.lib().rtb_job_begin(scene._h, C.byref(self.params), passes, C.byref(self._h)))
         self._buf = (C.c_uint8 * (256 * (6 + 3 * self.PIXELS_PER_MSG)))()
         self.cancelled = False
+        self.final_stats = None
 
     def messages(self, max_records: int = 256):
         """Iterates over byte strings, each one reference wire message (header + n*rgb)."""
@@ -281,16 +299,33 @@ class RenderJob:
                 return
             yield idx.value, frame
 
+    def stats(self) -> dict:
+        """Counters of the job so far (rtb_job_stats), incl. first_record_ms / wall_ms; after close(): the final ones."""
+        with self._lock:
+            if not self._h.value:
+                return dict(self.final_stats or {})
+            s = Stats()
+            _check(_abi.lib().rtb_job_stats(self._h, C.byref(s)))
+            return s.as_dict()
+
     def stop(self):
-        if self._h.value:
-            _abi.lib().rtb_job_cancel(self._h)
+        with self._lock:   # never touches a handle close() has already handed to rtb_job_end
+            if self._h.value:
+                _abi.lib().rtb_job_cancel(self._h)
 
     def close(self) -> bool:
         """Returns True if the job was stopped before completion (RenderJob::run's bool)."""
-        if not self._h.value:
+        with self._lock:
+            h, self._h = self._h, C.c_void_p()   # from here on stop() / stats() see no handle
+            if h.value:
+                s = Stats()
+                if _abi.lib().rtb_job_stats(h, C.byref(s)) == 0:
+                    self.final_stats = s.as_dict()
+        if not h.value:
             return self.cancelled
-        rc = _abi.lib().rtb_job_end(self._h)
-        self._h = C.c_void_p()
+        # rtb_job_end joins the worker threads: outside the lock, so that a concurrent stop() returns at once (no handle)
+        # -- a stop() that raced ahead of the swap has already cancelled the job, which only makes the join faster
+        rc = _abi.lib().rtb_job_end(h)
         self.cancelled = self.cancelled or rc == _abi.RTB_ECANCELLED
         return self.cancelled
 

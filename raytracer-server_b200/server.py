@@ -12,8 +12,11 @@ Protocol (reference `src/server.rs`):
   * one job per connection; scenes are shared by all connections (:24); frame size 600 x 450 (:29-30);
     `$PORT`, default 8080 (src/main.rs:16,38); scene names cornell_box, cubes, flying_unicorn (src/main.rs:17).
 
-Differences from the reference, on purpose: malformed JSON closes that connection with code 1007 instead of
-panicking the task (:92); an unknown scene name is answered with nothing instead of an `unwrap` panic (:100).
+Differences from the reference, on purpose: malformed JSON (including an "spp" that is not a JSON integer in i32
+range, which serde rejects) closes that connection with code 1007 instead of panicking the task (:92); an unknown
+scene name is answered with nothing instead of an `unwrap` panic (:100); a request the library refuses (spp beyond the
+20-bit sample index) is logged and ignored, the connection stays open.  spp < 4 — negative values included — streams
+a black frame exactly like the reference (`num_samples = spp / 4`, :332).
 
 Run:  python -m raytracer_server_b200.server <scenes dir>
 """
@@ -32,22 +35,6 @@ WIDTH, HEIGHT = 600, 450                                   # Server::WIDTH / HEI
 DEFAULT_PORT = "8080"                                      # src/main.rs:16
 
 
-class _JobHandle:
-    """What a connection needs from a render job: an iterable of wire messages plus stop/close."""
-
-    def __init__(self, job):
-        self.job = job
-
-    def messages(self) -> Iterable[bytes]:
-        return self.job.messages()
-
-    def stop(self):
-        self.job.stop()
-
-    def close(self) -> bool:
-        return self.job.close()
-
-
 def default_job_factory(scenes: dict, width: int, height: int):
     from .host import RenderJob
 
@@ -55,7 +42,9 @@ def default_job_factory(scenes: dict, width: int, height: int):
         scene = scenes.get(scene_name)
         if scene is None:
             return None
-        return _JobHandle(RenderJob(scene, width, height, spp, passes=passes, seed=random.getrandbits(63)))
+        # spp is an i32 in the reference (`ClientMessage::Render`, :123); `num_samples = spp / 4` makes every spp < 4,
+        # negative ones included, an empty sample loop: a black frame is streamed (src/server.rs:332-362)
+        return RenderJob(scene, width, height, max(0, spp), passes=passes, seed=random.getrandbits(63))
 
     return make
 
@@ -95,12 +84,19 @@ class Server:
                 running = state["task"] is not None and not state["task"].done()
                 if kind == "render" and not running:
                     try:
-                        scene_name, spp = str(req["scene"]), int(req["spp"])
-                        passes = max(1, int(req.get("passes", 1)))
-                    except (KeyError, TypeError, ValueError):
+                        scene_name, spp, passes = req["scene"], req["spp"], req.get("passes", 1)
+                        # serde: `scene: String`, `spp: i32` — a JSON string / float / bool / out-of-range number is a parse error
+                        if not isinstance(scene_name, str) or type(spp) is not int or not -2 ** 31 <= spp < 2 ** 31 or type(passes) is not int:
+                            raise TypeError
+                        passes = max(1, passes)
+                    except (KeyError, TypeError):
                         await websocket.close(code=1007, reason="failed to parse message")
                         break
-                    job = self.job_factory(scene_name, spp, passes)
+                    try:
+                        job = self.job_factory(scene_name, spp, passes)
+                    except RuntimeError as e:                  # the library refused the request (RtbError): not a reason to drop the client
+                        self.log(f"[{cid}] render request refused: {e}")
+                        continue
                     if job is None:
                         self.log(f"[{cid}] unknown scene '{scene_name}'")
                         continue

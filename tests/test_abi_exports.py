@@ -24,14 +24,31 @@ def test_every_declared_symbol_is_exported(rtb):
     assert sorted(_abi.EXPORTS) == names
 
 
-def test_struct_layouts_match_header(rtb):
+def test_struct_layouts_match_header(rtb, tmp_path):
+    # sizes and a few field offsets as a C compiler sees include/rtb200.h, against the ctypes mirrors
+    import subprocess
+
     from raytracer_server_b200 import _abi
 
-    assert C.sizeof(_abi.Params) == 4 * 4 + 8 + 3 * 4 + 5 * 4 + 0 or C.sizeof(_abi.Params) == 56
-    assert C.sizeof(_abi.Params) == 56
-    assert C.sizeof(_abi.SceneInfo) == 12 * 4 + 12 * 4 + 8
-    assert C.sizeof(_abi.Stats) == 8 * 8 + 6 * 8 + 3 * 8
-    assert C.sizeof(_abi.ObjectInfo) == 4 * 4 + 8 * (3 * 6 + 1 + 3 * 2 + 1)
+    src = tmp_path / "layout.c"
+    src.write_text("""#include <stdio.h>
+#include <stddef.h>
+#include "rtb200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu ", sizeof(rtb_params), sizeof(rtb_scene_info), sizeof(rtb_stats), sizeof(rtb_object_info),
+           sizeof(rtb_object_desc), sizeof(rtb_scene_desc));
+    printf("%zu %zu %zu %zu %d\\n", offsetof(rtb_params, seed), offsetof(rtb_scene_info, bvh_min), offsetof(rtb_stats, rays_bvh),
+           offsetof(rtb_stats, wall_ms), RTB_ABI_VERSION);
+    return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    v = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert v[:6] == [C.sizeof(_abi.Params), C.sizeof(_abi.SceneInfo), C.sizeof(_abi.Stats), C.sizeof(_abi.ObjectInfo),
+                     C.sizeof(_abi.ObjectDesc), C.sizeof(_abi.SceneDesc)]
+    assert v[6:10] == [_abi.Params.seed.offset, _abi.SceneInfo.bvh_min.offset, _abi.Stats.rays_bvh.offset, _abi.Stats.wall_ms.offset]
+    assert v[10] == 2 and C.sizeof(_abi.Params) == 56
 
 
 def test_param_validation_is_cpu_side(rtb):

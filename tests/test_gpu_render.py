@@ -227,6 +227,99 @@ def test_progressive_whole_frames(gpu_scene, rtb):
     assert got[0][1].mean() < 0.75 * final.mean()
 
 
+@pytest.mark.parametrize("workers", ["1", "2"])
+def test_streaming_bands_match_blocking_render(gpu_scene, rtb, monkeypatch, workers):
+    # a streaming job renders the frame in bands of tile rows and publishes each band from a side stream while the
+    # next ones render (RenderJob::run sends windows as they are sampled, src/server.rs:166-194); forced to 1 tile
+    # row per band here: 6 bands, the last one partial (170 = 5 * 32 + 10 rows), one or two worker threads
+    monkeypatch.setenv("RTB_BAND_TILE_ROWS", "1")
+    monkeypatch.setenv("RTB_JOB_WORKERS", workers)
+    g = gpu_scene("flying_unicorn")
+    W, H, spp = 200, 170, 16
+    whole = g.render(W, H, spp, seed=21).astype(int)
+    job = rtb.RenderJob(g, W, H, spp, seed=21)
+    frame, order = np.zeros((H, W, 3), dtype=np.uint8), []
+    for m in job.messages():
+        n, x, y = m[1], int.from_bytes(m[2:4], "little"), int.from_bytes(m[4:6], "little")
+        frame[y, x: x + n] = np.frombuffer(m[6:], dtype=np.uint8).reshape(n, 3)
+        order.append((y, x))
+    st = job.stats()
+    assert job.close() is False
+    assert order == sorted(order) and len(order) == H * 4          # windows of 60, 60, 60, 20
+    assert np.abs(frame.astype(int) - whole).max() <= 1
+    assert st["samples"] == W * H * spp and 0 < st["first_record_ms"] <= st["wall_ms"]
+    assert job.stats()["samples"] == W * H * spp                    # the final counters survive close()
+    # the whole-frame form waits for the last band
+    job = rtb.RenderJob(g, W, H, spp, seed=21)
+    (idx, f), = list(job.frames())
+    job.close()
+    assert idx == 0 and np.abs(f.astype(int) - whole).max() <= 1
+
+
+def test_first_record_arrives_while_the_frame_renders(gpu_scene, rtb, parity_log):
+    # BASELINE configs[2]: 1920x1080, 256 spp.  Bands of >= 8 Mi samples: the first rows are out long before the frame is done
+    g = gpu_scene("flying_unicorn")
+    W, H, spp = 1920, 1080, 256
+    g.render(W, H, 8)
+    t0 = time.time()
+    g.render(W, H, spp, seed=5)
+    blocking_ms = (time.time() - t0) * 1e3
+    for attempt in range(2):    # the first job on a scene allocates its band-sized contexts and pinned frame (100s of ms, once)
+        job = rtb.RenderJob(g, W, H, spp, seed=5)
+        n = sum(1 for _ in job.messages())
+        st = job.stats()
+        job.close()
+    assert n == H * 32 and st["samples"] == W * H * spp
+    parity_log("gpu/streaming/flying_unicorn_1920x1080_256spp", first_record_ms=st["first_record_ms"], job_wall_ms=st["wall_ms"],
+               blocking_render_ms=blocking_ms, msamples_per_s=st["samples"] / st["wall_ms"] / 1e3)
+    assert st["first_record_ms"] <= 0.10 * st["wall_ms"]
+    assert st["wall_ms"] <= 1.35 * blocking_ms
+
+
+def test_sample_pixels_is_the_frame(gpu_scene, rtb):
+    # sample_pixel (src/server.rs:320-364) through rtb_sample_pixels: same random numbers as the frame render, so the
+    # truncated Vec3 is the frame's byte (up to the order of the fp32 adds); only the listed pixels are traced
+    from raytracer_server_b200.host import sample_pixel, sample_pixels
+
+    g = gpu_scene("flying_unicorn")
+    W, H, spp = 160, 120, 16
+    frame = g.render(W, H, spp, seed=6).astype(int)
+    rng = np.random.default_rng(1)
+    xs, ys = rng.integers(0, W, 500), rng.integers(0, H, 500)
+    v = sample_pixels(xs, ys, W, H, spp, g, seed=6)
+    st = g.stats()
+    assert st["samples"] == 500 * spp
+    assert v.shape == (500, 3) and v.min() >= 0.5 and v.max() <= 255.5
+    assert np.abs(np.floor(v).astype(int) - frame[ys, xs]).max() <= 1
+    one = sample_pixel(17, H - 40 - 1, W, H, spp, g, seed=6)       # the reference's signature: bottom-up y
+    assert np.abs(np.floor(one).astype(int) - frame[40, 17]).max() <= 1
+    assert (sample_pixels([3], [3], W, H, 3, g) == 0.5).all()       # spp < 4: no samples, gamma_correct(0) = 0.5
+
+
+def test_stats_belong_to_the_calling_thread(gpu_scene):
+    g = gpu_scene("cubes")
+    out = {}
+
+    def work(name, w, h, spp):
+        g.render(w, h, spp, seed=1)
+        out[name] = g.stats()["samples"]
+
+    ts = [threading.Thread(target=work, args=("a", 64, 48, 8)), threading.Thread(target=work, args=("b", 96, 64, 16))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert out == {"a": 64 * 48 * 8, "b": 96 * 64 * 16}
+
+
+def test_bvh_depth_is_checked_against_the_stack(rtb, gpu_scene, monkeypatch):
+    assert 8 <= gpu_scene("flying_unicorn").info.bvh_depth <= 96 and gpu_scene("cornell_box").info.bvh_depth == 0
+    monkeypatch.setenv("RTB_BVH_MAX_DEPTH", "6")     # pretend the traversal stack holds 6 levels: PLOC and Karras trees are both deeper
+    with pytest.raises(rtb.LoadTomlError) as e:
+        rtb.Scene.from_toml(scene_path("flying_unicorn"), device=0)
+    assert e.value.kind == "Unsupported" and "levels deep" in str(e.value)
+    monkeypatch.setenv("RTB_BVH_MAX_DEPTH", "96")
+    assert rtb.Scene.from_toml(scene_path("cubes"), device=0).info.bvh_depth >= 1
+
+
 def test_job_cancel(gpu_scene, rtb):
     g = gpu_scene("flying_unicorn")
     job = rtb.RenderJob(g, 1920, 1080, 4096, seed=1)   # seconds of work
