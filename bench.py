@@ -4,23 +4,30 @@
 Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line (rank 0).
 
 Workload (BASELINE.json configs):
-  N = 1 : configs[2]  flying_unicorn at 1920x1080, 256 spp (the BVH-heavy scene the target is quoted on)
-  N > 1 : configs[3]  flying_unicorn at 3840x2160, tile-sharded over the ranks, 64*N spp
-          (weak scaling: 530.8 M samples per GPU at every N, the same count as the N = 1 frame),
-          RGB8 shards all_gathered with NCCL and scattered into scan-line order.
-A "step" is one complete frame: generation -> wavefront iterations until every path has ended ->
-per-sub-pixel resolve (clamp, gamma, RGB8).  Nothing is cached between steps (accumulators are
-cleared, every sample is re-traced; the seed changes per step).
+  N = 1 : configs[2]  flying_unicorn at 1920x1080, 256 spp (the BVH-heavy scene the target is quoted on).
+          The same run also measures every other config as a `configs` block — C1 cornell_box 600x450 64 spp (both
+          estimators), C2 cubes 600x450 256 spp MIS off / on, C4 flying_unicorn 3840x2160 4096 spp (one true step),
+          C5 progressive cornell_box (frames/s through the streaming job, time to 30 / 35 / 40 dB against the committed
+          4096-spp oracle frame) — and `scaling_reference`: the N > 1 frame rendered on this one GPU.
+  N > 1 : configs[3]  flying_unicorn at 3840x2160, 256 spp, the SAME frame at every N (strong scaling): 32x32 tiles
+          interleaved over the ranks, RGB8 shards all_gathered with NCCL and scattered into scan-line order.  The line
+          also carries `weak` (64*N spp: 530.8 M samples per GPU at every N) and, at N = 8, `c4_full`: one true 4096-spp
+          step of configs[3].
+A "step" is one complete frame: generation -> wavefront iterations until every path has ended -> per-sub-pixel
+resolve (clamp, gamma, RGB8).  Nothing is cached between steps (accumulators are cleared, every sample is re-traced,
+the seed changes per step).
 
   value    : whole-job samples/s, scene + BVH resident in HBM, frame left in device memory
-  e2e      : same metric through the host-buffer C-ABI call (rtb_scene_upload from pinned memory +
-             rtb_render into a host buffer: H2D of the flattened scene and D2H of the frame inside
-             the timed region)
-  roofline : the kernel with the largest share of the step (k_shade or k_traverse) against the HBM peak
-             by its algorithmic queue bytes; `fp32` is the whole step against the measured FP32 FMA
-             peak with SURVEY §8(d)'s flop model; `roofline_other` is the second kernel
-  cpu_baseline / --impl reference : oracle/ (f64 C++ port of the reference, octree-faithful, live
-             NEE) on the host cores, bounded sample of the same frame.
+  e2e      : the same metric through the host-buffer path, H2D and D2H inside the timed region of every step.
+             N = 1: rtb_scene_upload (flattened scene, pinned -> device) + rtb_render into a host frame.
+             N > 1: every rank uploads the scene and renders its shard, all_gather over NCCL, rank 0 scatters the shards
+             and copies the full frame to pinned host memory; timed by the slowest rank (barrier + synchronize brackets).
+  roofline : the kernel with the largest share of the step.  Neither hot kernel is HBM bound: what binds them is
+             instruction issue, so `bound` = "issue" (warp-instructions issued per second against 4 schedulers x SMs x
+             clock, instruction counts per unit from the committed ncu capture, units and kernel time measured live);
+             the HBM view (algorithmic queue bytes) and the FP32 view (SURVEY 8(d) flop model) ride along.
+  cpu_baseline / --impl reference : oracle/ (f64 C++ port of the reference, octree traversal, live NEE) on the
+             host cores, bounded sample of the same frame.
 """
 from __future__ import annotations
 
@@ -49,13 +56,15 @@ UNIT = "samples/s"
 #              (+ the LBVH itself, 4 MB, which lives in L1/L2)
 SHADE_B_VERTEX, SHADE_B_EXT, SHADE_B_SHQ, SHADE_B_RED = 56.0, 56.0, 48.0, 16.0
 TRAV_B_EXT, TRAV_B_SH = 48.0, 64.0
+STRONG_FRAME = (3840, 2160, 256)     # the fixed frame of the N > 1 runs
 
 
 def workload(n_gpus: int):
     if n_gpus == 1:
         return {"width": 1920, "height": 1080, "spp": 256, "name": "flying_unicorn 1920x1080 256spp (configs[2])"}
-    return {"width": 3840, "height": 2160, "spp": 64 * n_gpus,
-            "name": f"flying_unicorn 3840x2160 {64 * n_gpus}spp tile-sharded over {n_gpus} GPUs (configs[3], 64 spp per GPU)"}
+    w, h, spp = STRONG_FRAME
+    return {"width": w, "height": h, "spp": spp,
+            "name": f"flying_unicorn {w}x{h} {spp}spp, one frame tile-sharded over {n_gpus} GPUs (configs[3] geometry, fixed frame)"}
 
 
 class ClockSampler:
@@ -105,14 +114,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(width, height, spp, seconds_target=20.0, threads=None):
+CPU_BUILD = "oracle/Makefile: g++ -O3 -march=x86-64-v3 -ffp-contract=off (portable across the GPU boxes; not -march=native)"
+CPU_SCHED = "dynamic row scheduling over all host threads (the reference's static bands, src/server.rs:166-168, never run in parallel: SURVEY F2)"
+
+
+def cpu_reference_run(width, height, spp, seconds_target=20.0, threads=None, scene=SCENE, mis=False):
     """Times the oracle port (reference algorithm: octree-faithful traversal, live NEE, f64) on the host
     cores over a bounded sample of the frame: every `stride`-th row at `spp_cpu` spp."""
     from oracle import oracle as O
 
     threads = threads or os.cpu_count() or 1
-    sc = O.OracleScene.from_toml(os.path.join(SCENES, SCENE + ".toml"))
-    sc.set_modes(O.ACCEL_OCTREE_FAITHFUL, O.EST_NEE)
+    sc = O.OracleScene.from_toml(os.path.join(SCENES, scene + ".toml"))
+    sc.set_modes(O.ACCEL_OCTREE_FAITHFUL, O.EST_MIS_DEAD if mis else O.EST_NEE)
     # calibrate on a thin sample, then size the real one for ~seconds_target
     stride = max(1, height // 16)
     t0 = time.perf_counter()
@@ -150,16 +163,96 @@ def run_reference(args):
     last = vals[-1]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": total / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total / steps * 1e3, "higher_is_better": True,
+        "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "reference scene fixtures (tests/golden/scenes), CPU",
         "config": {"workload": wl["name"], "width": wl["width"], "height": wl["height"], "spp": wl["spp"]},
         "mrays_per_s": sum(x["mrays"] for x in vals) / len(vals),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"],
+                         "build": CPU_BUILD, "scheduling": CPU_SCHED},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def psnr(a, b):
+    import numpy as np
+
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else float(10 * np.log10(255.0 ** 2 / mse))
+
+
+def measure_configs(R, device, full_c4=True):
+    """Every BASELINE.json config that is not the headline frame, on one GPU, in this run."""
+    import numpy as np
+
+    out = {}
+
+    def frame_rate(scene, name, w, h, spp, mis, reps):
+        scene.render(w, h, min(spp, 16), use_mis=mis)
+        best = None
+        for i in range(reps):
+            t0 = time.perf_counter()
+            scene.render(w, h, spp, seed=50 + i, use_mis=mis)
+            dt = time.perf_counter() - t0
+            st = scene.stats()
+            rays = st["rays_primary"] + st["rays_extension"] + st["rays_shadow"]
+            r = {"ms": dt * 1e3, "device_ms": st["render_ms"] + st["resolve_ms"], "samples_per_s": st["samples"] / dt,
+                 "mrays_per_s": rays / dt / 1e6, "rays_per_sample": rays / max(1, st["samples"]), "iterations": st["iterations"],
+                 "timed": "host clock around rtb_render (H2D nothing, D2H frame), best of %d" % reps}
+            if best is None or r["ms"] < best["ms"]:
+                best = r
+        out[name] = best
+
+    cornell = R.Scene.from_toml(os.path.join(SCENES, "cornell_box.toml"), device=device)
+    cubes = R.Scene.from_toml(os.path.join(SCENES, "cubes.toml"), device=device)
+    frame_rate(cornell, "C1_cornell_box_600x450_64spp_mis_dead_branch", 600, 450, 64, True, 5)
+    frame_rate(cornell, "C1_cornell_box_600x450_64spp_nee", 600, 450, 64, False, 5)
+    frame_rate(cubes, "C2_cubes_600x450_256spp_mis_off", 600, 450, 256, False, 5)
+    frame_rate(cubes, "C2_cubes_600x450_256spp_mis_on_dead_branch", 600, 450, 256, True, 5)
+    # C5: progressive cornell_box through the streaming job, 1 sample per pixel per frame (4 frames = reference spp 4)
+    gold = None
+    try:
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "converged", "cornell_box_nee_600x450_4096spp_seed7.npz"))["rgb8"]
+    except Exception:
+        pass
+    W, H, passes = 600, 450, 4096
+    for warm in (True, False):
+        job = R.RenderJob(cornell, W, H, 64 if warm else passes, seed=3, passes=64 if warm else passes)
+        marks, n, nxt = {}, 0, 4
+        reached = {30: None, 35: None, 40: None}
+        t0 = time.perf_counter()
+        for i, f in job.frames():
+            n += 1
+            if not warm and gold is not None and n >= nxt:      # PSNR on a geometric schedule: it costs more than a frame
+                t = time.perf_counter() - t0
+                p = psnr(f, gold)
+                marks[n] = [round(t * 1e3, 2), round(p, 2)]
+                for db in reached:
+                    if reached[db] is None and p >= db:
+                        reached[db] = {"frames": n, "ms": round(t * 1e3, 2)}
+                nxt = max(n + 1, int(n * 1.25))
+        dt = time.perf_counter() - t0
+        st = job.stats()
+        job.close()
+    # frames/s without the PSNR bookkeeping in the consumer
+    job = R.RenderJob(cornell, W, H, 1024, seed=4, passes=1024)
+    t0 = time.perf_counter()
+    m = sum(1 for _ in job.frames())
+    dt_plain = time.perf_counter() - t0
+    job.close()
+    out["C5_cornell_box_progressive_600x450"] = {
+        "frames_per_s": m / dt_plain, "frames": m, "samples_per_frame": W * H, "first_frame_ms": st["first_record_ms"],
+        "api": "rtb_job_begin(passes = spp) + rtb_job_next_frame: every frame resolved on the device and copied to pinned host memory",
+        "time_to_psnr_db": reached, "psnr_reference": "tests/golden/converged/cornell_box_nee_600x450_4096spp_seed7.npz (f64 oracle, other seed: its own noise caps the PSNR)",
+        "psnr_after_frames_ms_db": marks}
+    if full_c4:
+        g = R.Scene.from_toml(os.path.join(SCENES, SCENE + ".toml"), device=device)
+        frame_rate(g, "C4_flying_unicorn_3840x2160_4096spp_one_gpu", 3840, 2160, 4096, False, 1)
+        del g
+    return out
 
 
 def main():
@@ -169,6 +262,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="rtb200", choices=["rtb200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs / scaling_reference / weak / c4_full blocks")
     ap.add_argument("--spp", type=int, default=0, help="override spp (debug only; invalidates the bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -203,80 +297,136 @@ def main():
     wl = workload(world)
     W, H, SPP = wl["width"], wl["height"], args.spp or wl["spp"]
     scene = R.Scene.from_toml(os.path.join(SCENES, SCENE + ".toml"), device=local_rank)
-    stride = sharding.shard_stride(W, H, world)
-    shard = torch.zeros(stride, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(world * stride, dtype=torch.uint8, device=dev) if world > 1 else None
-    frame = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
-    samples_per_step_total = W * H * (SPP // 4) * 4
+    L = _abi.lib()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step(i, totals):
-        p = R.make_params(W, H, SPP, seed=1000 + i, rank=rank, world=world)
-        scene.render_device(p, shard.data_ptr())
-        st = scene.stats()
-        for k in ("samples", "rays_primary", "rays_extension", "rays_shadow", "kernel_launches", "iterations", "rays_bvh",
-                  "shadow_bvh", "paths_queued"):
-            totals[k] = totals.get(k, 0) + st[k]
-        for k in ("render_ms", "extend_ms", "shade_ms", "resolve_ms"):
-            totals[k] = totals.get(k, 0.0) + st[k]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, shard)
-            torch.cuda.synchronize(dev)
-            if rank == 0:
-                R.host._check(_abi.lib().rtb_untile_device(C.byref(p), C.c_void_p(gathered.data_ptr()), stride,
-                                                           C.c_void_p(frame.data_ptr()), local_rank))
-            totals["kernel_launches"] += 1
+    class Frame:
+        """device buffers of one (w, h) frame geometry on this rank"""
 
-    for i in range(args.warmup):
-        step(i, {})
-    barrier()
+        def __init__(self, w, h):
+            self.w, self.h = w, h
+            self.stride = sharding.shard_stride(w, h, world)
+            self.shard = torch.zeros(self.stride, dtype=torch.uint8, device=dev)
+            self.gathered = torch.empty(world * self.stride, dtype=torch.uint8, device=dev) if world > 1 else None
+            self.frame = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+            self.host = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+
+    STAT_KEYS = ("samples", "rays_primary", "rays_extension", "rays_shadow", "kernel_launches", "iterations", "rays_bvh", "shadow_bvh", "paths_queued")
+    MS_KEYS = ("render_ms", "extend_ms", "shade_ms", "resolve_ms", "bin_ms")
+
+    def step(fr, spp, seed, totals, upload=False, to_host=False):
+        """one frame on `world` GPUs: [scene H2D] -> render shard -> [all_gather -> untile on rank 0] -> [frame D2H]"""
+        if upload:
+            totals["h2d"] = scene.upload()
+        p = R.make_params(fr.w, fr.h, spp, seed=seed, rank=rank, world=world)
+        scene.render_device(p, fr.shard.data_ptr())
+        st = scene.stats()
+        for k in STAT_KEYS:
+            totals[k] = totals.get(k, 0) + st[k]
+        for k in MS_KEYS:
+            totals[k] = totals.get(k, 0.0) + st[k]
+        src = fr.shard
+        if world > 1:
+            dist.all_gather_into_tensor(fr.gathered, fr.shard)
+            if rank == 0:   # on torch's current stream, right behind the collective: no device-wide synchronisation
+                R.host._check(L.rtb_untile_device_async(C.byref(p), C.c_void_p(fr.gathered.data_ptr()), fr.stride, C.c_void_p(fr.frame.data_ptr()),
+                                                        local_rank, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                totals["kernel_launches"] += 1
+            src = fr.frame
+        if to_host and rank == 0:
+            if world > 1:
+                fr.host.copy_(src, non_blocking=True)
+            else:   # single GPU: the shard IS the frame in tile order; the host-buffer API call (rtb_render) is timed instead
+                pass
+        if world > 1:
+            torch.cuda.synchronize(dev)
+
+    def timed(fr, spp, steps, warmup, seed0, **kw):
+        """W untimed + K timed steps, barrier + synchronize on both sides, max over ranks; counters summed over ranks"""
+        for i in range(warmup):
+            step(fr, spp, seed0 + i, {}, **kw)
+        barrier()
+        totals = {}
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step(fr, spp, seed0 + warmup + i, totals, **kw)
+        barrier()
+        elapsed = time.perf_counter() - t0
+        job = dict(totals)
+        if dist is not None:
+            t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed = float(t.item())
+            c = torch.tensor([float(totals[k]) for k in STAT_KEYS], dtype=torch.float64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            job.update(dict(zip(STAT_KEYS, [float(x) for x in c.tolist()])))
+            m = torch.tensor([float(totals[k]) for k in MS_KEYS], dtype=torch.float64, device=dev)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            job["render_ms_max_rank"] = float(m[0].item())
+        return elapsed, job, totals
+
+    def summary(elapsed, job, steps):
+        rays = job["rays_primary"] + job["rays_extension"] + job["rays_shadow"]
+        return {"samples_per_s": job["samples"] / elapsed, "mrays_per_s": rays / elapsed / 1e6, "ms_per_step": elapsed / max(1, steps) * 1e3,
+                "steps": steps}
+
+    # ---------------------------------------------------------------- value: K timed steps of the headline frame
+    fr = Frame(W, H)
     clocks = ClockSampler(local_rank)
+    for i in range(args.warmup):
+        step(fr, SPP, 1000 + i, {})
+    barrier()
     if rank == 0:
         clocks.start()
-    totals = {}
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(args.warmup + i, totals)
-    barrier()
-    elapsed = time.perf_counter() - t0
+    elapsed, job, totals = timed(fr, SPP, args.steps, 0, 1000 + args.warmup)
     clk = clocks.stop() if rank == 0 else None
-
-    # max over ranks of the bracketed time; sums of the counters
-    if dist is not None:
-        t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-        keys = ["samples", "rays_primary", "rays_extension", "rays_shadow", "kernel_launches"]
-        c = torch.tensor([float(totals[k]) for k in keys], dtype=torch.float64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        job = dict(zip(keys, [float(x) for x in c.tolist()]))
-    else:
-        job = {k: float(v) for k, v in totals.items()}
     value = job["samples"] / elapsed
     rays = job["rays_primary"] + job["rays_extension"] + job["rays_shadow"]
 
-    out = None
-    if rank == 0:
-        # ---- e2e: host-buffer C-ABI call, H2D scene upload + D2H frame inside the timed region (this rank's GPU;
-        # at N > 1 every rank would do the same on its shard, so the per-GPU figure is scaled by N)
+    # ---------------------------------------------------------------- e2e: host buffers, copies inside every step
+    e2e_steps = max(1, min(args.steps, 3))
+    if world == 1:
         host_frame = np.zeros((H, W, 3), dtype=np.uint8)
-        e2e_steps = max(1, min(args.steps, 2))
-        h2d = scene.upload()
-        scene.render(W, H, SPP, seed=5, rank=rank, world=world, out=host_frame)
+        scene.upload()
+        scene.render(W, H, SPP, seed=5, out=host_frame)
         t1 = time.perf_counter()
-        e2e_samples = 0
+        e2e_samples, h2d = 0, 0
         for i in range(e2e_steps):
             h2d = scene.upload()
-            scene.render(W, H, SPP, seed=2000 + i, rank=rank, world=world, out=host_frame)
+            scene.render(W, H, SPP, seed=2000 + i, out=host_frame)
             e2e_samples += scene.stats()["samples"]
         e2e_dt = time.perf_counter() - t1
-        d2h = int(sharding.local_pixels(W, H, rank, world) * 3) if world > 1 else W * H * 3
-        e2e_value = e2e_samples / e2e_dt * world
+        d2h = W * H * 3
+        e2e_api = "rtb_scene_upload + rtb_render (host RGB8 frame)"
+    else:
+        e2e_dt, e2e_job, e2e_tot = timed(fr, SPP, e2e_steps, 1, 3000, upload=True, to_host=True)
+        e2e_samples, h2d, d2h = e2e_job["samples"], int(e2e_tot.get("h2d", 0)) * world, W * H * 3
+        e2e_api = ("every rank: rtb_scene_upload + rtb_render_device (shard); all_gather_into_tensor over NCCL; rank 0: rtb_untile_device_async + "
+                   "frame -> pinned host memory; slowest rank")
+    e2e_value = e2e_samples / e2e_dt
 
+    extra = {}
+    if not args.no_configs and not args.spp:
+        if world == 1:
+            sw, sh, sspp = STRONG_FRAME
+            sfr = Frame(sw, sh)
+            el, jb, _ = timed(sfr, sspp, 2, 1, 4000)
+            extra["scaling_reference"] = dict(summary(el, jb, 2), workload=f"flying_unicorn {sw}x{sh} {sspp}spp on one GPU: the N > 1 frame, for fixed-frame (strong) scaling")
+            del sfr
+        else:
+            # the N = 1 workload's sample count per GPU (weak scaling, as round 1 reported it)
+            el, jb, _ = timed(fr, 64 * world, 2, 1, 5000)
+            extra["weak"] = dict(summary(el, jb, 2), workload=f"flying_unicorn {W}x{H} {64 * world}spp: 530.8 M samples per GPU at every N")
+            if world == 8:
+                el, jb, _ = timed(fr, 4096, 1, 0, 6000)
+                extra["c4_full"] = dict(summary(el, jb, 1), workload=f"flying_unicorn {W}x{H} 4096spp (configs[3] in full), one step")
+
+    out = None
+    if rank == 0:
         # ---- rooflines of the two hot kernels, measured live over the timed region (CUDA events around every launch,
         # recorded on the render stream inside librtb200 and summed); the one with the larger share is `roofline`
         n_launch = max(1.0, totals["iterations"])
@@ -293,31 +443,39 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = {}
+        prof = {}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f)
+                prof = json.load(f)
         except Exception:
             pass
-
-        # measured DRAM traffic (ncu --set full, profiles/traffic.json) is stored per unit and scaled to this run's
-        # units per launch, because the path pool (hence a launch) is sized per frame
-        traffic_per_launch = {
-            "k_shade": traffic.get("k_shade_dram_bytes_per_vertex", 0.0) * vertices / n_launch or None,
-            "k_traverse": traffic.get("k_traverse_dram_bytes_per_bvh_ray", 0.0) * (totals["rays_bvh"] + totals["shadow_bvh"]) / n_launch or None,
-        }
+        props = torch.cuda.get_device_properties(dev)
+        sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = props.multi_processor_count * 4 * sm_hz          # one warp instruction per scheduler and clock
+        units = {"k_shade": vertices, "k_traverse": totals["rays_bvh"] + totals["shadow_bvh"]}
+        unit_name = {"k_shade": "path vertex", "k_traverse": "LBVH ray (extension + shadow)"}
+        per_unit_key = {"k_shade": "k_shade_warp_inst_per_vertex", "k_traverse": "k_traverse_warp_inst_per_bvh_ray"}
+        traffic_key = {"k_shade": "k_shade_dram_bytes_per_vertex", "k_traverse": "k_traverse_dram_bytes_per_bvh_ray"}
 
         def roof(kernel, ms, nbytes):
-            gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-            return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "traffic": traffic_per_launch[kernel],
-                    # neither hot kernel is HBM bound (DESIGN.md "Rooflines"): what limits them is instruction issue, so the
-                    # ncu-measured issue utilisation and SIMD lanes per instruction of the committed profile ride along
-                    "issue_active_pct_ncu": traffic.get(kernel + "_issue_active_pct"),
-                    "lanes_per_instruction_ncu": traffic.get(kernel + "_lanes_per_instruction"),
-                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
-                    "algorithmic_bytes_per_launch": nbytes / n_launch, "avg_launch_ms": ms / n_launch,
-                    "share_of_step": ms / max(totals["render_ms"], 1e-9)}
+            secs = ms * 1e-3
+            gbs = nbytes / secs / 1e9 if ms > 0 else 0.0
+            inst = prof.get(per_unit_key[kernel], 0.0) * units[kernel]          # warp instructions issued in the timed region
+            ips = inst / secs if ms > 0 else 0.0
+            traffic = prof.get(traffic_key[kernel], 0.0) * units[kernel] / n_launch or None
+            return {"kernel": kernel, "bound": "issue", "achieved": ips / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s",
+                    "frac": ips / issue_peak,
+                    "how": f"{prof.get(per_unit_key[kernel])} warp instructions per {unit_name[kernel]} (ncu smsp__inst_executed.sum over one frame / counted units, "
+                           f"profiles/traffic.json, build {prof.get('commit')}) x units counted live / kernel time from CUDA events; peak = {props.multi_processor_count} SMs x 4 "
+                           f"schedulers x {sm_hz / 1e6:.0f} MHz (median SM clock of this run)",
+                    "traffic": traffic, "traffic_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per unit on build {prof.get('commit')} (profiles/traffic.json) x this run's units per launch",
+                    "issue_active_pct_ncu": prof.get(kernel + "_issue_active_pct"),
+                    "lanes_per_instruction_ncu": prof.get(kernel + "_lanes_per_instruction"),
+                    "pipe_fma_pct_ncu": prof.get(kernel + "_pipe_fma_pct"), "pipe_alu_pct_ncu": prof.get(kernel + "_pipe_alu_pct"),
+                    "hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                            "algorithmic_bytes_per_launch": nbytes / n_launch,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
+                    "avg_launch_ms": ms / n_launch, "share_of_step": ms / max(totals["render_ms"], 1e-9)}
 
         roofs = [roof("k_shade", totals["shade_ms"], shade_bytes), roof("k_traverse", totals["extend_ms"], trav_bytes)]
         roofs.sort(key=lambda r: -r["share_of_step"])
@@ -340,20 +498,26 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             c = cpu_reference_run(W, H, SPP, seconds_target=15.0)
             cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
-                   "mrays_per_s": c["mrays"]}
+                   "mrays_per_s": c["mrays"], "build": CPU_BUILD, "scheduling": CPU_SCHED}
+        if world == 1 and not args.no_configs and not args.spp:
+            extra["configs"] = measure_configs(R, local_rank)
 
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": elapsed / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "reference scene fixtures (tests/golden/scenes), Philox seeds per step",
-            "config": {"workload": wl["name"], "width": W, "height": H, "spp": SPP, "samples_per_step": samples_per_step_total,
-                       "parallelism": f"tiles32x32 interleaved x{world}" if world > 1 else "single GPU",
-                       "l2": "no flush needed: every step re-traces the whole frame, streaming ~270 GB through HBM (path / shadow queue entries of the paths that leave registers + the 127 MiB accumulator buffer, cleared per step), far more than the 126 MB L2; only the 4 MB scene + LBVH is meant to stay cache-resident"},
+            "config": {"workload": wl["name"], "width": W, "height": H, "spp": SPP},
+            "workload_detail": {
+                "samples_per_step": W * H * (SPP // 4) * 4,
+                "parallelism": f"tiles32x32 interleaved x{world}, one all_gather per frame" if world > 1 else "single GPU",
+                "scaling_note": "N > 1 renders ONE fixed frame (3840x2160, 256 spp) at every N; the N = 1 line is configs[2] and carries the fixed frame as scaling_reference",
+                "l2": "no flush needed: every step re-traces the whole frame, streaming ~270 GB through HBM (path / shadow queue entries of the paths that leave registers + the accumulator buffer, cleared per step), far more than the 126 MB L2; only the 4 MB scene + LBVH is meant to stay cache-resident",
+                "timing": "host clock between barrier + torch.cuda.synchronize brackets (rtb_render_device returns synchronised), max over ranks; device_ms_per_step = CUDA events on the render stream"},
             "mrays_per_s": rays / elapsed / 1e6,
             "rays_per_sample": rays / max(1.0, job["samples"]),
             "device_ms_per_step": totals["render_ms"] / max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_dt / e2e_steps * 1e3, "api": "rtb_scene_upload + rtb_render (host RGB8 frame)"},
+                    "ms_per_step": e2e_dt / e2e_steps * 1e3, "steps": e2e_steps, "api": e2e_api},
             "gpu_launches": int(job["kernel_launches"]),
             "clocks": clk,
             "roofline": dict(roofs[0], fp32={"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -366,6 +530,7 @@ def main():
                                  "shadow": totals["shadow_bvh"] / max(1.0, totals["rays_shadow"])},
             "cpu_baseline": cpu,
         }
+        out.update(extra)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
