@@ -47,6 +47,9 @@ typedef struct rtb_job rtb_job;
 /* estimator selection (src/scene.rs:187-229) */
 #define RTB_EST_NEE 0      /* live branch: next-event estimation, src/scene.rs:217-229 */
 #define RTB_EST_MIS_DEAD 1 /* the `if false` "MIS" branch verbatim, src/scene.rs:189-216 */
+#define RTB_EST_MIS_BALANCE 2 /* NOT in the reference: light sample + BRDF sample combined with the balance heuristic, i.e. the
+                                 "TODO: Do multiple importance sampling properly" of src/scene.rs:187 done.  Same expectation as
+                                 RTB_EST_NEE, less variance near the light; sphere lights only; never used for parity */
 
 /* Render request.  spp has the reference's meaning: spp/4 samples in each of 2x2 sub-pixels
  * (src/server.rs:332), so spp < 4 renders black.  (rank, world) select an interleaved tile

@@ -24,6 +24,7 @@ RTB_ECANCELLED = 1
 
 EST_NEE = 0
 EST_MIS_DEAD = 1
+EST_MIS_BALANCE = 2
 
 
 class Params(C.Structure):

@@ -16,12 +16,15 @@ namespace rtb {
 // ---------------------------------------------------------------- primitive codes
 // pcode: bit31 = hit normal flipped w.r.t. the geometric normal, bit30 = previous vertex was
 // specular (emission + ks/p still to be applied), bit29 = `o` is stale (reference quirk,
-// src/scene.rs:178), bits 0..28 = id: analytic primitive index (< TRI_BASE) or TRI_BASE + leaf slot.
+// src/scene.rs:178), bit28 = the ray is a BRDF sample of the balance-heuristic estimator (RTB_EST_MIS_BALANCE: its pdf
+// rides in the `ov` slot, the light's emission is still to be added with the MIS weight),
+// bits 0..27 = id: analytic primitive index (< TRI_BASE) or TRI_BASE + leaf slot.
 constexpr uint32_t PC_FLIPPED = 0x80000000u;
 constexpr uint32_t PC_SPEC_PENDING = 0x40000000u;
 constexpr uint32_t PC_STALE_O = 0x20000000u;
-constexpr uint32_t PC_ID_MASK = 0x1fffffffu;
-constexpr uint32_t PC_NONE = 0x1fffffffu;
+constexpr uint32_t PC_MIS_PENDING = 0x10000000u;
+constexpr uint32_t PC_ID_MASK = 0x0fffffffu;
+constexpr uint32_t PC_NONE = 0x0fffffffu;
 constexpr uint32_t TRI_BASE = 256u;  // == MAX_OBJECTS
 constexpr int TRI_STRIDE = 4;        // float4 per LBVH triangle record: 48 B of data padded to 64 B so that the first 32 B
                                      // can be fetched by one 256-bit load

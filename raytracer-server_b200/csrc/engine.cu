@@ -455,7 +455,8 @@ int check_params(const rtb_params* p) {
     if (p->spp < 0) return fail(RTB_EINVAL, "spp must be >= 0");
     if ((long long)p->spp / 4 * 4 >= (1 << 20)) return fail(RTB_EINVAL, "spp too large (sample index field is 20 bits)");
     if (p->world < 1 || p->rank < 0 || p->rank >= p->world) return fail(RTB_EINVAL, "need 0 <= rank < world");
-    if (p->estimator != RTB_EST_NEE && p->estimator != RTB_EST_MIS_DEAD) return fail(RTB_EINVAL, "unknown estimator");
+    if (p->estimator != RTB_EST_NEE && p->estimator != RTB_EST_MIS_DEAD && p->estimator != RTB_EST_MIS_BALANCE)
+        return fail(RTB_EINVAL, "unknown estimator");
     if ((long long)p->width * p->height * 4 >= (1ll << 31)) return fail(RTB_EINVAL, "frame too large for 31-bit accumulator indices");
     return RTB_OK;
 }
@@ -630,7 +631,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     // Small frames are launch-bound (four tiny kernels per iteration): replay one captured CUDA graph per
     // iteration and let k_prepare publish the live-path count to mapped host memory instead of copying it back.
     // compile-time specialisation of k_shade for the common case (see its definition)
-    bool fast_shade = !a.probe_px && sc->fs.light_geom == GEOM_SPHERE && !getenv("RTB_NO_FAST_SHADE");
+    if (a.estimator == RTB_EST_MIS_BALANCE && sc->fs.light_geom != GEOM_SPHERE)
+        return fail(RTB_EUNSUPPORTED, "RTB_EST_MIS_BALANCE needs a sphere light (the reference's mesh-light sampler does not return points of the mesh, src/geometry.rs:622-628)");
+    bool fast_shade = !a.probe_px && a.estimator != RTB_EST_MIS_BALANCE && sc->fs.light_geom == GEOM_SPHERE && !getenv("RTB_NO_FAST_SHADE");
     for (const FlatMaterial& m : sc->fs.materials) fast_shade = fast_shade && m.brdf != BRDF_PHONG;
     const int shade_mode = !fast_shade ? 0 : (a.estimator == 0 ? 1 : 2);
     // the mesh-less instantiation runs 160-thread CTAs: its grid and warp count (static first chunks, k_prepare) differ

@@ -618,7 +618,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
     const PathQueue &Q = a.qin, &N = a.qout;
     const int light_obj = hdr->light_obj;
     const bool light_is_mesh = FAST ? false : hdr->light_geom == 2;
-    const bool mis = MODE == 1 ? false : (MODE == 2 ? true : a.estimator != 0);
+    const bool mis = MODE == 1 ? false : (MODE == 2 ? true : a.estimator == 1);     // the reference's dead "MIS" branch
+    // RTB_EST_MIS_BALANCE (general instantiation only): next-event estimation and the BRDF sample combined with the balance
+    // heuristic — what src/scene.rs:187 ("TODO: Do multiple importance sampling properly") asks for.  Diffuse surfaces under
+    // a sphere light; Phong surfaces keep plain NEE (the reference's Phong sampler never leaves the local frame, its pdf
+    // for a world direction is undefined).  Never used for parity.
+    const bool mis2 = FAST ? false : a.estimator == 2;
     const bool probe_mode = FAST ? false : a.probe_px != nullptr;
     const float3 Le = f3(sh.mats[light_obj].emitted);
     const int n_prims = a.S.n_prims, n_planes = a.S.n_planes;
@@ -730,6 +735,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                 // emitted(next) un-attenuated and then scales the reflected part by ks/p (src/scene.rs:176-181)
                 if (depth == 1u) {
                     if (emits) accum_add(a.accum, acc, beta * emitted);
+                } else if (mis2 && (origin & PC_MIS_PENDING)) {
+                    // the BRDF sample of the previous (diffuse) vertex reached the sampled light: its emission counts with the
+                    // balance weight pdf_brdf / (pdf_brdf + pdf_light), both per solid angle at the previous vertex
+                    if (emits && hg.obj == light_obj) {
+                        const float pdf_b = cont ? tri_n.w : Q.ov[cur_slot].w;
+                        const float pdf_l = a.light_pdf * (t * t) / fmaxf(dot(hg.n, -d), 1e-20f);
+                        accum_add(a.accum, acc, beta * emitted * (pdf_b / (pdf_b + pdf_l)));
+                    }
                 } else if (origin & PC_SPEC_PENDING) {
                     if (emits) accum_add(a.accum, acc, beta * emitted);
                     const DevMaterial& pm = sh.mats[object_of(a.S, sh, origin & PC_ID_MASK)];
@@ -780,6 +793,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                         if (!mis) {  // live NEE, src/scene.rs:217-229 (no cosine is clamped)
                             float g = __fdividef(dot(hg.n, inc) * dot(ny, -inc), r2 * pdf_a);
                             contrib = beta * Le * f * g;
+                            if (mis2 && mat.brdf == 0) {   // balance weight of the light sample: pdf_light / (pdf_light + pdf_brdf(inc))
+                                const float pdf_l = pdf_a * r2 / fmaxf(fabsf(dot(ny, -inc)), 1e-20f);
+                                const float pdf_b = fmaxf(dot(hg.n, inc), 0.f) * INV_PI_F;
+                                contrib = contrib * (pdf_l / (pdf_l + pdf_b));
+                            }
                         } else {                 // dead branch, src/scene.rs:191-201
                             float pdf_light = pdf_a * (r2 / dot(ny, -inc));
                             float3 itmp;
@@ -848,6 +866,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                                 ext_push = true;
                                 eo = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
                                 eb = make_float4(nb.x, nb.y, nb.z, __uint_as_float((sample << 12) | (depth + 1u)));
+                                if (mis2 && mat.brdf == 0) {   // the sample's pdf travels with the ray (see PC_MIS_PENDING)
+                                    eo.w = __uint_as_float(hg.pcode | PC_MIS_PENDING);
+                                    ev = make_float4(0.f, 0.f, 0.f, pdf1);
+                                }
                             }
                         }
                     }
@@ -908,7 +930,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                 N.d[slot] = ed;
                 N.beta[slot] = eb;
                 N.hit[slot] = eh;
-                if (__float_as_uint(eo.w) & PC_STALE_O) N.ov[slot] = ev;
+                if (__float_as_uint(eo.w) & (PC_STALE_O | PC_MIS_PENDING)) N.ov[slot] = ev;
                 ++n_queued;
             }
         }

@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 from . import _abi
-from ._abi import EST_MIS_DEAD, EST_NEE, ObjectDesc, ObjectInfo, Params, SceneDesc, SceneInfo, Stats
+from ._abi import EST_MIS_BALANCE, EST_MIS_DEAD, EST_NEE, ObjectDesc, ObjectInfo, Params, SceneDesc, SceneInfo, Stats
 
 
 class RtbError(RuntimeError):
@@ -44,11 +44,11 @@ def _check(rc: int, load: bool = False):
 
 def make_params(width: int, height: int, spp: int, *, use_mis: bool = False, seed: int = 0, rank: int = 0, world: int = 1,
                 pool_paths: int = 0, count_work: bool = False, tune_refill: int = 0, tune_steps: int = 0,
-                bin_bits: int | None = None, bin_octant_major: bool = False) -> Params:
+                bin_bits: int | None = None, bin_octant_major: bool = False, estimator: int | None = None) -> Params:
     """bin_bits: coherence binning of the LBVH rays — None = library default, 0 = off, 2..5 = cell bits per axis."""
     p = Params()
     p.width, p.height, p.spp = width, height, spp
-    p.estimator = EST_MIS_DEAD if use_mis else EST_NEE
+    p.estimator = estimator if estimator is not None else (EST_MIS_DEAD if use_mis else EST_NEE)
     p.seed = seed
     p.rank, p.world, p.pool_paths = rank, world, pool_paths
     p.reserved[0] = 1 if count_work else 0
@@ -169,11 +169,12 @@ class Scene:
     # ---- RenderJob::run, blocking whole-frame form ----------------------------------------------
     def render(self, width: int, height: int, spp: int, *, use_mis: bool = False, seed: int = 0, rank: int = 0,
                world: int = 1, pool_paths: int = 0, out: np.ndarray | None = None, count_work: bool = False,
-               tune_refill: int = 0, tune_steps: int = 0, bin_bits: int | None = None, bin_octant_major: bool = False) -> np.ndarray:
+               tune_refill: int = 0, tune_steps: int = 0, bin_bits: int | None = None, bin_octant_major: bool = False,
+               estimator: int | None = None) -> np.ndarray:
         """Returns the frame as uint8 [height, width, 3], row 0 = top (the bytes of src/server.rs:187-189)."""
         p = make_params(width, height, spp, use_mis=use_mis, seed=seed, rank=rank, world=world, pool_paths=pool_paths,
                         count_work=count_work, tune_refill=tune_refill, tune_steps=tune_steps, bin_bits=bin_bits,
-                        bin_octant_major=bin_octant_major)
+                        bin_octant_major=bin_octant_major, estimator=estimator)
         if out is None:
             out = np.zeros((height, width, 3), dtype=np.uint8)
         assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size == width * height * 3
@@ -212,8 +213,8 @@ class Scene:
             res["work"] = {"node_visits": work[0], "tri_tests": work[1]}
         return res
 
-    def sample_radiance(self, width, height, spp, px, py, sample_idx, *, use_mis=False, seed=0) -> np.ndarray:
-        p = make_params(width, height, spp, use_mis=use_mis, seed=seed)
+    def sample_radiance(self, width, height, spp, px, py, sample_idx, *, use_mis=False, seed=0, estimator=None) -> np.ndarray:
+        p = make_params(width, height, spp, use_mis=use_mis, seed=seed, estimator=estimator)
         px = np.ascontiguousarray(px, dtype=np.int32)
         py = np.ascontiguousarray(py, dtype=np.int32)
         si = np.ascontiguousarray(sample_idx, dtype=np.int32)

@@ -320,6 +320,34 @@ def test_bvh_depth_is_checked_against_the_stack(rtb, gpu_scene, monkeypatch):
     assert rtb.Scene.from_toml(scene_path("cubes"), device=0).info.bvh_depth >= 1
 
 
+def test_balance_heuristic_mis_mode(gpu_scene, rtb, parity_log):
+    # RTB_EST_MIS_BALANCE: the estimator the reference's TODO (src/scene.rs:187) asks for — NOT a parity mode.
+    # Same expectation as the live NEE estimator, less variance where BRDF sampling finds the light easily (the
+    # ceiling right above the lamp), and the dead "MIS" branch stays what it was.
+    g = gpu_scene("cornell_box")
+    W, H, spp, n = 600, 450, 4096, 400_000
+    rng = np.random.default_rng(3)
+    px, py, si = rng.integers(0, W, n), rng.integers(0, H, n), rng.integers(0, spp, n)
+    nee = g.sample_radiance(W, H, spp, px, py, si, seed=1).astype(np.float64)
+    bal = g.sample_radiance(W, H, spp, px, py, si, seed=1, estimator=rtb.EST_MIS_BALANCE).astype(np.float64)
+    se = np.sqrt(nee.var(0) / n + bal.var(0) / n)
+    parity_log("gpu/mis_balance/cornell_box", paths=n, mean_nee=nee.mean(0), mean_balance=bal.mean(0), std_nee=nee.std(0), std_balance=bal.std(0))
+    assert (np.abs(nee.mean(0) - bal.mean(0)) < 4 * se).all(), (nee.mean(0), bal.mean(0), se)
+    assert not np.array_equal(nee, bal)
+    # the hot spot on the ceiling above the light (screen rows 30..60, columns 250..350): NEE suffers from 1 / r^2 there
+    m = 100_000
+    px, py, si = rng.integers(250, 350, m), rng.integers(30, 60, m), rng.integers(0, spp, m)
+    v_nee = g.sample_radiance(W, H, spp, px, py, si, seed=2).astype(np.float64)
+    v_bal = g.sample_radiance(W, H, spp, px, py, si, seed=2, estimator=rtb.EST_MIS_BALANCE).astype(np.float64)
+    parity_log("gpu/mis_balance/cornell_box_ceiling", paths=m, mean_nee=v_nee.mean(0), mean_balance=v_bal.mean(0), std_nee=v_nee.std(0), std_balance=v_bal.std(0))
+    assert (v_bal.std(0) < 0.8 * v_nee.std(0)).all()
+    se = np.sqrt(v_nee.var(0) / m + v_bal.var(0) / m)
+    assert (np.abs(v_nee.mean(0) - v_bal.mean(0)) < 4 * se).all()
+    # frames: the whole-frame entry point accepts the mode; the scene's mesh-light twin refuses it
+    f = g.render(200, 150, 64, seed=5, estimator=rtb.EST_MIS_BALANCE).astype(int)
+    assert abs(f.mean() - g.render(200, 150, 64, seed=6).astype(int).mean()) < 0.02 * f.mean()
+
+
 def test_job_cancel(gpu_scene, rtb):
     g = gpu_scene("flying_unicorn")
     job = rtb.RenderJob(g, 1920, 1080, 4096, seed=1)   # seconds of work
