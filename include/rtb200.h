@@ -51,6 +51,13 @@ typedef struct rtb_job rtb_job;
                                  "TODO: Do multiple importance sampling properly" of src/scene.rs:187 done.  Same expectation as
                                  RTB_EST_NEE, less variance near the light; sphere lights only; never used for parity */
 
+/* mesh acceleration (Mesh::intersect, src/geometry.rs:883-905) */
+#define RTB_ACCEL_LBVH 0             /* true nearest hit = the reference's brute-force branch (:887-903), through the device-built LBVH */
+#define RTB_ACCEL_OCTREE_REFERENCE 1 /* the branch the reference actually runs: its per-mesh octree with the early exit on the first child
+                                        that reports any hit (:1237-1295; Octree::build :1149-1216 restated on the host).  NOT a nearest-hit
+                                        structure — it is what makes the Rust binary's flying_unicorn differ from the exact image by 30 dB.
+                                        Slower than the LBVH; for results identical to the binary's */
+
 /* Render request.  spp has the reference's meaning: spp/4 samples in each of 2x2 sub-pixels
  * (src/server.rs:332), so spp < 4 renders black.  (rank, world) select an interleaved tile
  * shard: this call renders the 32x32 tiles t with t % world == rank (world = 1: whole frame). */
@@ -63,7 +70,9 @@ typedef struct rtb_params {
     int32_t rank;
     int32_t world;
     int32_t pool_paths; /* in-flight path slots; 0 = default */
-    int32_t reserved[5];
+    int32_t accel;      /* RTB_ACCEL_*: which Mesh::intersect the mesh rays get */
+    int32_t tuning[4];  /* experiment knobs, 0 = library defaults: [0] 1 = counting build (bvh_node_visits / bvh_tri_tests), [1] refill
+                           threshold and [2] inner steps of k_traverse, [3] coherence binning (1 off, 2..5 cell bits per axis, +256 octant-major) */
 } rtb_params;
 
 typedef struct rtb_scene_info {
@@ -78,7 +87,8 @@ typedef struct rtb_scene_info {
     int32_t device;
     int32_t bvh_depth;    /* inner-node levels on the longest root-to-leaf path; the loader refuses trees deeper than the
                              traversal stack (96) with RTB_EUNSUPPORTED */
-    int32_t reserved[2];
+    int32_t octree_nodes;     /* RTB_ACCEL_OCTREE_REFERENCE tables: 0 until the first request for that mode builds them */
+    int32_t octree_tri_refs;  /* triangle references in the octrees' leaves (the reference copies a triangle into every octant it overlaps) */
     float bvh_min[3];
     float bvh_max[3];
     float camera_pos[3];
@@ -174,6 +184,10 @@ int rtb_scene_upload(rtb_scene* scene, uint64_t* bytes);
  * global triangle order; returns the count (call with cap = 0 to query) */
 int64_t rtb_scene_triangles(const rtb_scene* scene, float* out9, int64_t cap);
 
+/* Octree::build (src/geometry.rs:1149-1216) for one mesh object, on the host: counts4 = {nodes, parents, leaves, triangle
+ * references}.  What RTB_ACCEL_OCTREE_REFERENCE traverses; needs no device. */
+int rtb_scene_octree_stats(const rtb_scene* scene, int32_t object, int64_t* counts4);
+
 const char* rtb_last_error(void);
 
 /* ---- whole frame: what RenderJob::run has sent once all messages are out -------------------
@@ -238,6 +252,10 @@ int rtb_trace_primary(rtb_scene* scene, int32_t width, int32_t height, int32_t s
                       int32_t* obj, int32_t* tri, float* t);
 int rtb_trace_rays(rtb_scene* scene, int64_t n, const float* org3, const float* dir3, int32_t* obj, int32_t* tri,
                    float* t, uint64_t* work2);
+/* rtb_trace_rays under a chosen RTB_ACCEL_* mode: with RTB_ACCEL_OCTREE_REFERENCE the (object, triangle, t) the reference's
+ * Octree::intersect returns, which need not be the nearest triangle (src/geometry.rs:1263-1273) */
+int rtb_trace_rays_accel(rtb_scene* scene, int32_t accel, int64_t n, const float* org3, const float* dir3, int32_t* obj, int32_t* tri,
+                         float* t);
 /* radiance of explicit (pixel x, screen row y, sample index) camera paths, fp32 rgb — the
  * path-level probe matching the oracle's or_sample_radiance under the shared RNG contract */
 int rtb_sample_radiance(rtb_scene* scene, const rtb_params* params, int64_t n, const int32_t* px, const int32_t* py,

@@ -25,18 +25,20 @@ RTB_ECANCELLED = 1
 EST_NEE = 0
 EST_MIS_DEAD = 1
 EST_MIS_BALANCE = 2
+ACCEL_LBVH = 0
+ACCEL_OCTREE_REFERENCE = 1
 
 
 class Params(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("estimator", C.c_int32),
                 ("seed", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32), ("pool_paths", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("accel", C.c_int32), ("tuning", C.c_int32 * 4)]
 
 
 class SceneInfo(C.Structure):
     _fields_ = [("n_objects", C.c_int32), ("n_planes", C.c_int32), ("n_spheres", C.c_int32), ("n_meshes", C.c_int32),
                 ("n_triangles", C.c_int32), ("light_object", C.c_int32), ("bvh_nodes", C.c_int32),
-                ("bvh_leaves", C.c_int32), ("device", C.c_int32), ("bvh_depth", C.c_int32), ("reserved", C.c_int32 * 2),
+                ("bvh_leaves", C.c_int32), ("device", C.c_int32), ("bvh_depth", C.c_int32), ("octree_nodes", C.c_int32), ("octree_tri_refs", C.c_int32),
                 ("bvh_min", C.c_float * 3), ("bvh_max", C.c_float * 3), ("camera_pos", C.c_float * 3),
                 ("camera_dir", C.c_float * 3), ("build_ms", C.c_double)]
 
@@ -76,7 +78,7 @@ EXPORTS = [
     "rtb_scene_upload", "rtb_scene_triangles", "rtb_render", "rtb_local_pixels", "rtb_tile_map", "rtb_render_device",
     "rtb_untile_device", "rtb_get_stats", "rtb_job_begin", "rtb_job_next", "rtb_job_next_messages", "rtb_job_next_frame", "rtb_job_cancel",
     "rtb_job_end", "rtb_trace_primary", "rtb_trace_rays", "rtb_sample_radiance", "rtb_fp32_peak",
-    "rtb_untile_device_async", "rtb_job_stats", "rtb_sample_pixels",
+    "rtb_untile_device_async", "rtb_job_stats", "rtb_sample_pixels", "rtb_trace_rays_accel", "rtb_scene_octree_stats",
 ]
 
 _lib = None
@@ -124,6 +126,8 @@ def lib():
     L.rtb_untile_device_async.argtypes = [C.POINTER(Params), vp, C.c_int64, vp, C.c_int, vp]
     L.rtb_job_stats.argtypes = [vp, C.POINTER(Stats)]
     L.rtb_sample_pixels.argtypes = [vp, C.POINTER(Params), C.c_int64, ip, ip, fp]
+    L.rtb_scene_octree_stats.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64)]
+    L.rtb_trace_rays_accel.argtypes = [vp, C.c_int32, C.c_int64, fp, fp, ip, ip, fp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:

@@ -11,14 +11,12 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librtb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-lineinfo", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
-          "--use_fast_math=false"] if False else ["-O3", "-lineinfo", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Xcompiler",
-                                                  "-fPIC",
-                                                  # denormals flushed: __fdividef / rsqrtf become single MUFU instructions
-                                                  # (without it each carries a 4-instruction denormal rescue)
-                                                  "-ftz=true"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC",
+          # denormals flushed: __fdividef / rsqrtf become single MUFU instructions
+          # (without it each carries a 4-instruction denormal rescue)
+          "-ftz=true"]
 EXTRA = os.environ.get("RTB_NVCC_EXTRA", "").split()   # experiment knobs, e.g. -DRTB_SHADE_THREADS=160 -DRTB_SHADE_MINB=4
-SOURCES = ["engine.cu", "lbvh.cu", "scene_host.cpp"]
+SOURCES = ["engine.cu", "lbvh.cu", "scene_host.cpp", "octree_host.cpp"]
 
 
 def _deps(src: str) -> list[str]:

@@ -19,6 +19,7 @@
 
 #include "../../include/rtb200.h"
 #include "lbvh.hpp"
+#include "octree_host.hpp"
 #include "scene_host.hpp"
 #include "wavefront.cuh"
 
@@ -121,11 +122,21 @@ struct rtb_scene {
     std::vector<RenderContext*> pool;
     rtb_stats last_stats{};
     cudaStream_t stream = nullptr;
+    // RTB_ACCEL_OCTREE_REFERENCE: the reference's octrees, built on first use
+    bool octrees_built = false;
+    float4* d_oct_nodes = nullptr;
+    int32_t* d_oct_tris = nullptr;
+    int32_t* d_oct_roots = nullptr;
+    int oct_nodes = 0, oct_refs = 0;
+    double oct_build_ms = 0;
 
     ~rtb_scene() {
         if (device < 0) return;
         cudaSetDevice(device);
         for (auto* c : pool) delete c;
+        cudaFree(d_oct_nodes);
+        cudaFree(d_oct_tris);
+        cudaFree(d_oct_roots);
         free_lbvh(bvh);
         cudaFree(d_stage);
         cudaFree(d_tri_orig);
@@ -311,6 +322,74 @@ int finish_scene(rtb_scene* sc, int rc, const std::string& err, rtb_scene** out)
     return RTB_OK;
 }
 
+// ---------------------------------------------------------------- the reference's octrees (RTB_ACCEL_OCTREE_REFERENCE)
+// Built on first use: Octree::build per mesh on the host in f64 (octree_host.cpp), flattened into one node table whose
+// leaves reference the LBVH's triangle table (the LBVH build reordered the triangles: its `global id` column gives the
+// inverse map), uploaded once.  Afterwards sc->view carries the tables and every render may ask for either accel mode.
+int ensure_octrees(rtb_scene* sc) {
+    std::lock_guard<std::mutex> lk(sc->mu);
+    if (sc->octrees_built) return RTB_OK;
+    CU_TRY(cudaSetDevice(sc->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const int n_tris = sc->view.n_tris;
+    std::vector<int32_t> slot_of((size_t)n_tris, -1);   // global triangle index -> slot in the LBVH triangle table
+    if (n_tris) {
+        std::vector<float4> tris((size_t)n_tris * TRI_STRIDE);
+        CU_TRY(cudaMemcpy(tris.data(), sc->bvh.d_tris, tris.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (int s = 0; s < n_tris; ++s) {
+            int g;
+            std::memcpy(&g, &tris[(size_t)s * TRI_STRIDE + 1].w, 4);
+            if (g < 0 || g >= n_tris) return fail(RTB_ECUDA, "internal error: LBVH triangle table holds an invalid triangle id");
+            slot_of[(size_t)g] = s;
+        }
+    }
+    std::vector<float4> nodes;
+    std::vector<int32_t> refs, roots;
+    auto as_f = [](int v) { float f; std::memcpy(&f, &v, 4); return f; };
+    for (int i = 0; i < sc->fs.n_objects; ++i) {
+        const HostObject& ob = sc->hs.objects[(size_t)i];
+        if (ob.geom != GEOM_MESH) continue;
+        HostOctree ot;
+        build_reference_octree(ob, ot);
+        if (ot.nodes.empty()) { roots.push_back(-1); continue; }
+        const int node_base = (int)(nodes.size() / 4), ref_base = (int)refs.size();
+        const int first_tri = sc->fs.materials[(size_t)i].first_tri;
+        roots.push_back(node_base);
+        for (const HostOctreeNode& n : ot.nodes) {
+            nodes.push_back(make_float4((float)n.mn[0], (float)n.mn[1], (float)n.mn[2], as_f(n.count >= 0 ? ref_base + n.first : 0)));
+            nodes.push_back(make_float4((float)n.mx[0], (float)n.mx[1], (float)n.mx[2], as_f(n.count)));
+            int c[8];
+            for (int k = 0; k < 8; ++k) c[k] = n.child[k] >= 0 ? node_base + n.child[k] : -1;
+            nodes.push_back(make_float4(as_f(c[0]), as_f(c[1]), as_f(c[2]), as_f(c[3])));
+            nodes.push_back(make_float4(as_f(c[4]), as_f(c[5]), as_f(c[6]), as_f(c[7])));
+        }
+        for (int32_t t : ot.tri_refs) refs.push_back(slot_of[(size_t)(first_tri + t)]);
+    }
+    if (!nodes.empty()) {
+        CU_TRY(cudaMalloc((void**)&sc->d_oct_nodes, nodes.size() * sizeof(float4)));
+        CU_TRY(cudaMemcpy(sc->d_oct_nodes, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    if (!refs.empty()) {
+        CU_TRY(cudaMalloc((void**)&sc->d_oct_tris, refs.size() * sizeof(int32_t)));
+        CU_TRY(cudaMemcpy(sc->d_oct_tris, refs.data(), refs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if (!roots.empty()) {
+        CU_TRY(cudaMalloc((void**)&sc->d_oct_roots, roots.size() * sizeof(int32_t)));
+        CU_TRY(cudaMemcpy(sc->d_oct_roots, roots.data(), roots.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    sc->view.oct_nodes = sc->d_oct_nodes;
+    sc->view.oct_tris = sc->d_oct_tris;
+    sc->view.oct_roots = sc->d_oct_roots;
+    sc->view.n_oct_meshes = (int)roots.size();
+    sc->oct_nodes = (int)(nodes.size() / 4);
+    sc->oct_refs = (int)refs.size();
+    sc->oct_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    sc->info.octree_nodes = sc->oct_nodes;
+    sc->info.octree_tri_refs = sc->oct_refs;
+    sc->octrees_built = true;
+    return RTB_OK;
+}
+
 // ---------------------------------------------------------------- render contexts
 // want_paths: path slots the caller is going to ask for — the pooled context whose queues fit best is handed out
 // (smallest that is large enough, else the largest), so that nothing is reallocated when it can be avoided
@@ -342,10 +421,11 @@ void release_context(rtb_scene* sc, RenderContext* c) {
 
 int default_bin_bits();
 // cell bits per axis of the coherence binning this request asks for (0 = off):
-// rtb_params.reserved[3] = 0 library default | 1 off | 2..5 bits
+// rtb_params.tuning[3] & 255 = 0 library default | 1 off | 2..5 bits
 int requested_bin_bits(const rtb_scene* sc, const rtb_params* p) {
-    if (sc->view.n_tris == 0) return 0;   // scenes without triangles never traverse
-    return p->reserved[3] == 0 ? default_bin_bits() : (p->reserved[3] == 1 ? 0 : std::min(std::max(p->reserved[3], 2), BIN_MAX_BITS));
+    if (sc->view.n_tris == 0 || p->accel != RTB_ACCEL_LBVH) return 0;   // scenes without triangles never traverse
+    const int code = p->tuning[3] & 255;
+    return code == 0 ? default_bin_bits() : (code == 1 ? 0 : std::min(std::max(code, 2), BIN_MAX_BITS));
 }
 
 int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, size_t accum_elems, bool binning = false) {
@@ -442,6 +522,13 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
     return RTB_OK;
 }
 
+int ensure_octrees(rtb_scene* sc);
+// the tables the requested accel mode needs exist (the reference's octrees are built on first use)
+int need_accel(rtb_scene* sc, const rtb_params* p) {
+    if (p->accel == RTB_ACCEL_OCTREE_REFERENCE && sc->view.n_tris > 0) return ensure_octrees(sc);
+    return RTB_OK;
+}
+
 int need_device(const rtb_scene* sc) {
     if (!sc) return fail(RTB_EINVAL, "NULL scene");
     if (sc->device < 0) return fail(RTB_ECUDA, "host-only scene handle (device = -1): no CUDA device owns it, and there is no CPU fallback");
@@ -458,6 +545,7 @@ int check_params(const rtb_params* p) {
     if (p->estimator != RTB_EST_NEE && p->estimator != RTB_EST_MIS_DEAD && p->estimator != RTB_EST_MIS_BALANCE)
         return fail(RTB_EINVAL, "unknown estimator");
     if ((long long)p->width * p->height * 4 >= (1ll << 31)) return fail(RTB_EINVAL, "frame too large for 31-bit accumulator indices");
+    if (p->accel != RTB_ACCEL_LBVH && p->accel != RTB_ACCEL_OCTREE_REFERENCE) return fail(RTB_EINVAL, "unknown accel mode");
     return RTB_OK;
 }
 
@@ -494,6 +582,19 @@ int default_bin_bits() {
     return v;
 }
 
+// every mesh query of one iteration: the LBVH kernel (the product's fast path) or the reference's octrees
+void launch_traverse(RenderContext* c, const RenderArgs& a, int cur, bool count_work, size_t smem_stack) {
+    if (a.accel == RTB_ACCEL_OCTREE_REFERENCE) {
+        if (count_work) k_traverse_octree<true><<<c->grid_bin, WF_THREADS, 0, c->stream>>>(a, cur);
+        else k_traverse_octree<false><<<c->grid_bin, WF_THREADS, 0, c->stream>>>(a, cur);
+    } else if (count_work && a.S.wide) k_traverse<true, 4, true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+    else if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+    else if (a.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+    else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+    else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+    else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
+}
+
 void launch_binning(RenderContext* c, const RenderArgs& a, int cur) {
     if (a.bin_bits <= 0) return;
     k_bin_keys<<<c->grid_bin, WF_THREADS, 0, c->stream>>>(a, cur);
@@ -503,7 +604,7 @@ void launch_binning(RenderContext* c, const RenderArgs& a, int cur) {
 
 void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, RenderArgs& a) {
     std::memset(&a, 0, sizeof(a));
-    a.S = sc->view;
+    a.S = sc->view;   // (callers asking for RTB_ACCEL_OCTREE_REFERENCE have run ensure_octrees first: need_accel)
     a.cam = make_camera(sc->fs.cam_pos, sc->fs.cam_dir, p->width, p->height);
     a.width = p->width;
     a.height = p->height;
@@ -512,8 +613,9 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
     a.ks_done = (uint32_t)(p->spp / 4) * 4u;
     a.keys = philox_keys((uint32_t)p->seed, (uint32_t)(p->seed >> 32));
     a.estimator = p->estimator;
-    a.tune_refill = p->reserved[1];
-    a.tune_steps = p->reserved[2];
+    a.tune_refill = p->tuning[1];
+    a.tune_steps = p->tuning[2];
+    a.accel = p->accel;
     a.rank = p->rank;
     a.world = p->world;
     a.tiles_x = (p->width + TILE - 1) / TILE;
@@ -553,9 +655,9 @@ void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, Rende
         }
     a.trav_warps = (uint32_t)c->grid_ext * (WF_THREADS / 32);
     a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
-    // coherence binning: rtb_params.reserved[3] = 0 library default | 1 off | 2..5 cell bits per axis; reserved[4] & 1 = octant-major keys
+    // coherence binning: rtb_params.tuning[3] = 0 library default | 1 off | 2..5 cell bits per axis, + 256 = octant-major keys
     a.bin_bits = c->bin_buf && c->bin_hist ? requested_bin_bits(sc, p) : 0;
-    a.bin_octant_major = p->reserved[4] & 1;
+    a.bin_octant_major = (p->tuning[3] >> 8) & 1;
     a.bin_key = c->bin_buf;
     a.bin_perm = c->bin_buf ? c->bin_buf + c->bin_cap : nullptr;
     a.bin_hist = c->bin_hist;
@@ -660,10 +762,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
                 const RenderArgs agk = with_cur(ag, k);   // queue pointers of this parity, resolved here
                 launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, agk, k);
                 launch_binning(c, agk, k);
-                if (ag.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
-                else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
-                else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
-                else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(agk, k);
+                launch_traverse(c, agk, k, false, smem_stack);
                 launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, agk, k);
                 ge = cudaStreamEndCapture(c->stream, &g);
                 if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->graph_exec[k], g, 0);
@@ -720,12 +819,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         CU_TRY(cudaEventRecord(ev[3], c->stream));
         launch_binning(c, ac, cur);
         CU_TRY(cudaEventRecord(ev[0], c->stream));
-        if (count_work && a.S.wide) k_traverse<true, 4, true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
-        else if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
-        else if (a.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
-        else if (c->trav_minb == 5) k_traverse<false, 5><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
-        else if (c->trav_minb == 6) k_traverse<false, 6><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
-        else k_traverse<false><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(ac, cur);
+        launch_traverse(c, ac, cur, count_work, smem_stack);
         CU_TRY(cudaEventRecord(ev[1], c->stream));
         launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, ac, cur);
         CU_TRY(cudaEventRecord(ev[2], c->stream));
@@ -801,7 +895,7 @@ int render_into_context(rtb_scene* sc, const rtb_params* p, RenderContext* c, Re
     st = rtb_stats{};
     cancelled = false;
     if (a.num_samples > 0 && a.n_local_tiles > 0) {
-        bool count_work = p->reserved[0] == 1;
+        bool count_work = p->tuning[0] == 1;
         rc = run_wavefront(sc, c, a, 0u, (uint32_t)a.num_samples * 4u, count_work, cancel, st, cancelled);
         if (rc != RTB_OK) return rc;
     }
@@ -998,6 +1092,7 @@ int rtb_render_device(rtb_scene* scene, const rtb_params* params, void* d_rgb8_t
     if (int rc0 = need_device(scene)) return rc0;
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
+    if ((rc = need_accel(scene, params)) != RTB_OK) return rc;
     RenderContext* c = acquire_context(scene, default_pool(params));
     RenderArgs a;
     rtb_stats st{};
@@ -1016,6 +1111,7 @@ int rtb_render(rtb_scene* scene, const rtb_params* params, uint8_t* rgb8_out, vo
     if (int rc0 = need_device(scene)) return rc0;
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
+    if ((rc = need_accel(scene, params)) != RTB_OK) return rc;
     RenderContext* c = acquire_context(scene, default_pool(params));
     RenderArgs a;
     rtb_stats st{};
@@ -1075,9 +1171,12 @@ int rtb_untile_device(const rtb_params* params, const void* d_shards, int64_t sh
 
 // ---------------------------------------------------------------- parity hooks
 static int trace_common(rtb_scene* scene, int64_t n, const float* org3, const float* dir3, int width, int height, int sx, int sy,
-                        float dx, float dy, int32_t* obj, int32_t* tri, float* t, uint64_t* work2) {
+                        float dx, float dy, int32_t* obj, int32_t* tri, float* t, uint64_t* work2, int accel = RTB_ACCEL_LBVH) {
     if (!scene || !obj || !tri || !t) return fail(RTB_EINVAL, "NULL argument");
     if (int rc0 = need_device(scene)) return rc0;
+    if (accel != RTB_ACCEL_LBVH && accel != RTB_ACCEL_OCTREE_REFERENCE) return fail(RTB_EINVAL, "unknown accel mode");
+    if (accel == RTB_ACCEL_OCTREE_REFERENCE && scene->view.n_tris > 0)
+        if (int rc1 = ensure_octrees(scene)) return rc1;
     if (n <= 0) return RTB_OK;
     CU_TRY(cudaSetDevice(scene->device));
     float *d_org = nullptr, *d_dir = nullptr, *d_t = nullptr;
@@ -1103,10 +1202,10 @@ static int trace_common(rtb_scene* scene, int64_t n, const float* org3, const fl
         int grid = (int)std::min<int64_t>((n + WF_THREADS - 1) / WF_THREADS, 148 * 8);
         if (work2) {
             T(cudaFuncSetAttribute(k_trace_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_scene_bytes(MAX_OBJECTS, MAX_OBJECTS, WF_THREADS)));
-            k_trace_rays<true><<<grid, WF_THREADS, smem>>>(scene->view, n, d_org, d_dir, cam, width, height, sx, sy, dx, dy, d_obj, d_tri, d_t, d_work);
+            k_trace_rays<true><<<grid, WF_THREADS, smem>>>(scene->view, n, d_org, d_dir, cam, width, height, sx, sy, dx, dy, d_obj, d_tri, d_t, d_work, accel);
         } else {
             T(cudaFuncSetAttribute(k_trace_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_scene_bytes(MAX_OBJECTS, MAX_OBJECTS, WF_THREADS)));
-            k_trace_rays<false><<<grid, WF_THREADS, smem>>>(scene->view, n, d_org, d_dir, cam, width, height, sx, sy, dx, dy, d_obj, d_tri, d_t, d_work);
+            k_trace_rays<false><<<grid, WF_THREADS, smem>>>(scene->view, n, d_org, d_dir, cam, width, height, sx, sy, dx, dy, d_obj, d_tri, d_t, d_work, accel);
         }
         T(cudaDeviceSynchronize());
         T(cudaGetLastError());
@@ -1132,12 +1231,36 @@ int rtb_trace_rays(rtb_scene* scene, int64_t n, const float* org3, const float* 
     return trace_common(scene, n, org3, dir3, 1, 1, 0, 0, 0.f, 0.f, obj, tri, t, work2);
 }
 
+// host-only: Octree::build for one mesh object — counts[4] = {nodes, parents, leaves, triangle references}; works on
+// device = -1 handles too (the loader checks run without a GPU)
+int rtb_scene_octree_stats(const rtb_scene* scene, int32_t object, int64_t* counts4) {
+    if (!scene || !counts4) return fail(RTB_EINVAL, "NULL argument");
+    if (object < 0 || object >= scene->fs.n_objects) return fail(RTB_EINVAL, "object index out of range");
+    const HostObject& ob = scene->hs.objects[(size_t)object];
+    if (ob.geom != GEOM_MESH) return fail(RTB_EINVAL, "object is not a mesh");
+    HostOctree ot;
+    build_reference_octree(ob, ot);
+    int64_t parents = 0, leaves = 0;
+    for (const HostOctreeNode& n : ot.nodes) (n.count < 0 ? parents : leaves)++;
+    counts4[0] = (int64_t)ot.nodes.size();
+    counts4[1] = parents;
+    counts4[2] = leaves;
+    counts4[3] = (int64_t)ot.tri_refs.size();
+    return RTB_OK;
+}
+
+int rtb_trace_rays_accel(rtb_scene* scene, int32_t accel, int64_t n, const float* org3, const float* dir3, int32_t* obj, int32_t* tri, float* t) {
+    if (!org3 || !dir3) return fail(RTB_EINVAL, "NULL rays");
+    return trace_common(scene, n, org3, dir3, 1, 1, 0, 0, 0.f, 0.f, obj, tri, t, nullptr, accel);
+}
+
 int rtb_sample_radiance(rtb_scene* scene, const rtb_params* params, int64_t n, const int32_t* px, const int32_t* py,
                         const int32_t* sample_idx, float* rgb3) {
     if (!scene || !px || !py || !sample_idx || !rgb3) return fail(RTB_EINVAL, "NULL argument");
     if (int rc0 = need_device(scene)) return rc0;
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
+    if ((rc = need_accel(scene, params)) != RTB_OK) return rc;
     if (n <= 0) return RTB_OK;
     if (params->spp < 4) return fail(RTB_EINVAL, "spp < 4 has no samples");
     for (int64_t i = 0; i < n; ++i)
@@ -1171,7 +1294,7 @@ int rtb_sample_radiance(rtb_scene* scene, const rtb_params* params, int64_t n, c
         if (e != cudaSuccess) rc = fail(RTB_ECUDA, cudaGetErrorString(e));
     }
     bool cancelled = false;
-    if (rc == RTB_OK) rc = run_wavefront(scene, c, a, 0, 0, params->reserved[0] == 1, nullptr, st, cancelled);
+    if (rc == RTB_OK) rc = run_wavefront(scene, c, a, 0, 0, params->tuning[0] == 1, nullptr, st, cancelled);
     if (rc == RTB_OK) {
         std::vector<float4> host((size_t)n);
         cudaError_t e = cudaMemcpy(host.data(), c->accum, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost);
@@ -1193,6 +1316,7 @@ int rtb_sample_pixels(rtb_scene* scene, const rtb_params* params, int64_t n, con
     if (int rc0 = need_device(scene)) return rc0;
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
+    if ((rc = need_accel(scene, params)) != RTB_OK) return rc;
     if (n <= 0) return RTB_OK;
     if (n > (1 << 24)) return fail(RTB_EINVAL, "at most 2^24 pixels per call");
     for (int64_t i = 0; i < n; ++i)
@@ -1549,6 +1673,7 @@ int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rt
     if (int rc0 = need_device(scene)) return rc0;
     int rc = check_params(params);
     if (rc != RTB_OK) return rc;
+    if ((rc = need_accel(scene, params)) != RTB_OK) return rc;
     if (params->world != 1) return fail(RTB_EINVAL, "streaming jobs render whole frames (world must be 1)");
     CU_TRY(cudaSetDevice(scene->device));
     rtb_job* j = new rtb_job();

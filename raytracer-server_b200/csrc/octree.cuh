@@ -1,0 +1,156 @@
+// octree.cuh — RTB_ACCEL_OCTREE_REFERENCE: the reference's own Mesh::intersect on the device.
+//
+// The reference never runs its brute-force branch: SceneSpec::to_scene calls mesh.accelerate() for every mesh
+// (src/scene.rs:430-432), so every mesh ray goes through Octree::intersect / _intersect_recurse
+// (src/geometry.rs:1237-1295), which is NOT a nearest-hit query:
+//   * no test against the root box; the children of a parent are visited in the order of the distance from the ray
+//     ORIGIN to the centres of the ROOT's octants — the same order at every level (:1248-1260; stable insertion sort)
+//   * a child is entered if BoundingBox::intersect reports any of the six faces met at t >= 1e-7 (:977-1036; a boolean)
+//   * the FIRST child subtree that yields a hit ends the search (:1263-1273), and a leaf returns the nearest of ITS
+//     triangles even when that hit lies outside the leaf's box (:1276-1293)
+// so the triangle found can be farther away than another one in a later octant (~30 % of the mesh-origin
+// secondary rays on flying_unicorn), and Scene::trace_ray (src/scene.rs:272-289) then compares THAT hit with the other
+// objects.  This file reproduces exactly that in fp32, over the octree octree_host.cpp built in f64.
+// Node record (64 B, 4 x float4): min.xyz | first   max.xyz | count (-1: parent)   children[0..3]   children[4..7]
+// (int bits; child = node index or -1).  Leaf triangles are references into the LBVH's triangle table (leaf order), so
+// hit ids, self-intersection handling and shading are shared with the LBVH path.
+#pragma once
+
+#include "intersect.cuh"
+
+namespace rtb {
+
+constexpr int OCT_MAX_DEPTH = 10;   // Octree::MAX_DEPTH: the deepest node sits at depth 10, root = 1
+
+// BoundingBox::intersect as a boolean (src/geometry.rs:977-1036).  inv = 1 / d (IEEE: +-inf for a zero component, which
+// makes the corresponding face tests fail exactly as the reference's division does)
+__device__ __forceinline__ bool oct_box_hit(const float4 mn, const float4 mx, float3 o, float3 d, float3 inv) {
+    constexpr float EPS = 1e-7f;
+    float t;
+    t = (mn.x - o.x) * inv.x;
+    if (t >= EPS) { const float py = o.y + t * d.y, pz = o.z + t * d.z; if (mn.y <= py && py <= mx.y && mn.z <= pz && pz <= mx.z) return true; }
+    t = (mx.x - o.x) * inv.x;
+    if (t >= EPS) { const float py = o.y + t * d.y, pz = o.z + t * d.z; if (mn.y <= py && py <= mx.y && mn.z <= pz && pz <= mx.z) return true; }
+    t = (mn.y - o.y) * inv.y;
+    if (t >= EPS) { const float px = o.x + t * d.x, pz = o.z + t * d.z; if (mn.x <= px && px <= mx.x && mn.z <= pz && pz <= mx.z) return true; }
+    t = (mx.y - o.y) * inv.y;
+    if (t >= EPS) { const float px = o.x + t * d.x, pz = o.z + t * d.z; if (mn.x <= px && px <= mx.x && mn.z <= pz && pz <= mx.z) return true; }
+    t = (mn.z - o.z) * inv.z;
+    if (t >= EPS) { const float px = o.x + t * d.x, py = o.y + t * d.y; if (mn.x <= px && px <= mx.x && mn.y <= py && py <= mx.y) return true; }
+    t = (mx.z - o.z) * inv.z;
+    if (t >= EPS) { const float px = o.x + t * d.x, py = o.y + t * d.y; if (mn.x <= px && px <= mx.x && mn.y <= py && py <= mx.y) return true; }
+    return false;
+}
+
+// Node::Leaf: the nearest of the leaf's triangles, Triangle::intersect each (src/geometry.rs:637-670, :1276-1293).
+// Same arithmetic as trav_leaf (intersect.cuh), but over triangle REFERENCES and without an upper bound on t.
+__device__ __forceinline__ bool oct_leaf(const DevScene& S, int first, int count, float3 o, float3 d, uint32_t origin, float& t_out, uint32_t& id_out) {
+    const uint32_t origin_id = origin & PC_ID_MASK;
+    float best = INFINITY;
+    uint32_t best_id = PC_NONE;
+    for (int k = first; k < first + count; ++k) {
+        const uint32_t s = (uint32_t)__ldg(S.oct_tris + k);
+        const float4* tp = S.tris + (size_t)s * TRI_STRIDE;
+        float4 t0, t1;
+        ldg256(tp, t0, t1);
+        const float4 t2 = __ldg(tp + 2);
+        const float3 e1 = f3(t1), e2 = f3(t2);
+        const float3 pvec = cross(d, e2);
+        const float det = dot(e1, pvec);
+        const float nd = det * t0.w;
+        if (fabsf(nd) < DN_EPS) continue;
+        const float inv = __fdividef(1.0f, det);
+        const float3 tvec = o - f3(t0);
+        const float u = dot(tvec, pvec) * inv;
+        const float3 qvec = cross(tvec, e1);
+        const float vv = dot(d, qvec) * inv;
+        float t = dot(e2, qvec) * inv;
+        if (TRI_BASE + s == origin_id) {   // the triangle the ray starts on: as the reference's f64 arithmetic sees it (intersect.cuh header)
+            const float dnf = (origin & PC_FLIPPED) ? -nd : nd;
+            t = -SURF_OFFSET / dnf;
+        }
+        if (u < 0.0f || vv < 0.0f || u + vv > 1.0f || !(t > T_EPS)) continue;
+        if (t < best) { best = t; best_id = TRI_BASE + s; }   // strict '<': the first of equal hits stays (:1281)
+    }
+    t_out = best;
+    id_out = best_id;
+    return best_id != PC_NONE;
+}
+
+// Octree::intersect for ONE mesh (root node index `root`): true + (t, id) of the hit the reference would return
+__device__ __forceinline__ bool oct_intersect(const DevScene& S, int root, float3 o, float3 d, float3 inv, uint32_t origin, float& t_out, uint32_t& id_out,
+                                              uint32_t* work) {
+    const float4* N = S.oct_nodes;
+    const float4 rmn = __ldg(N + (size_t)root * 4), rmx = __ldg(N + (size_t)root * 4 + 1);
+    if (__float_as_int(rmx.w) >= 0) {   // the root is a leaf (a mesh of at most SMALL_NODE triangles)
+        if (work) work[1] += (uint32_t)__float_as_int(rmx.w);
+        return oct_leaf(S, __float_as_int(rmn.w), __float_as_int(rmx.w), o, d, origin, t_out, id_out);
+    }
+    // octant_search_order (:1245-1260): insertion sort of 0..7 by the distance from ray.pos to the centre of the ROOT's
+    // octant, ascending, stable — a rank computation gives the same order (ties: lower index first)
+    const float cx = 0.5f * (rmn.x + rmx.x), cy = 0.5f * (rmn.y + rmx.y), cz = 0.5f * (rmn.z + rmx.z);
+    float dist[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float ox = 0.5f * ((i & 4) ? cx + rmx.x : rmn.x + cx) - o.x;
+        const float oy = 0.5f * ((i & 2) ? cy + rmx.y : rmn.y + cy) - o.y;
+        const float oz = 0.5f * ((i & 1) ? cz + rmx.z : rmn.z + cz) - o.z;
+        dist[i] = sqrtf(ox * ox + oy * oy + oz * oz);   // Vec3::mag: the comparison is made on the rounded root
+    }
+    uint32_t order = 0;   // 3 bits per position
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rank += (dist[j] < dist[i] || (dist[j] == dist[i] && j < i)) ? 1 : 0;
+        order |= (uint32_t)i << (3 * rank);
+    }
+    int node[OCT_MAX_DEPTH];
+    unsigned long long pos = 0;   // 4 bits per level: next position in `order` to try
+    int level = 0;
+    node[0] = root;
+    for (;;) {
+        const unsigned p = (unsigned)(pos >> (4 * level)) & 15u;
+        if (p == 8u) {   // this parent is exhausted without a hit
+            if (level == 0) return false;
+            pos &= ~(15ull << (4 * level));
+            --level;
+            continue;
+        }
+        pos += 1ull << (4 * level);
+        const int i = (int)(order >> (3 * p)) & 7;
+        const float4* np = N + (size_t)node[level] * 4;
+        const float4 cq = __ldg(np + 2 + (i >> 2));
+        const int c = __float_as_int((i & 3) == 0 ? cq.x : (i & 3) == 1 ? cq.y : (i & 3) == 2 ? cq.z : cq.w);
+        if (c < 0) continue;   // children[i] == None
+        const float4 cmn = __ldg(N + (size_t)c * 4), cmx = __ldg(N + (size_t)c * 4 + 1);
+        if (work) work[0]++;
+        if (!oct_box_hit(cmn, cmx, o, d, inv)) continue;
+        const int cnt = __float_as_int(cmx.w);
+        if (cnt >= 0) {   // leaf: its nearest triangle ends the whole search, wherever the hit lies
+            if (work) work[1] += (uint32_t)cnt;
+            if (oct_leaf(S, __float_as_int(cmn.w), cnt, o, d, origin, t_out, id_out)) return true;
+        } else if (level + 1 < OCT_MAX_DEPTH) {
+            ++level;
+            node[level] = c;
+        }
+    }
+}
+
+// Scene::trace_ray's mesh part under the reference's octrees: every mesh in object order, strict '<' against the best so
+// far (src/scene.rs:277-284).  best_t comes in as the nearest analytic hit (or a shadow ray's limit).
+__device__ __forceinline__ void oct_trace_meshes(const DevScene& S, float3 o, float3 d, uint32_t origin, float& best_t, uint32_t& best_id, uint32_t* work) {
+    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    for (int m = 0; m < S.n_oct_meshes; ++m) {
+        const int root = __ldg(S.oct_roots + m);
+        if (root < 0) continue;
+        float t;
+        uint32_t id;
+        if (oct_intersect(S, root, o, d, inv, origin, t, id, work) && t < best_t) {
+            best_t = t;
+            best_id = id;
+        }
+    }
+}
+
+}  // namespace rtb

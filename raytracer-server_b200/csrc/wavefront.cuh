@@ -20,6 +20,7 @@
 #pragma once
 
 #include "intersect.cuh"
+#include "octree.cuh"
 #include "shade.cuh"
 
 namespace rtb {
@@ -125,6 +126,7 @@ struct RenderArgs {
     uint32_t* bin_offs;    // [BIN_MAX + 1]
     int bin_bits;          // cell bits per axis (0 = binning off); bins = 8 octants x 2^(3 bits)
     int bin_octant_major;
+    int accel;             // RTB_ACCEL_*: 1 = the mesh rays go through the reference's octrees (k_traverse_octree)
 };
 
 // ---------------------------------------------------------------- tile order <-> pixels
@@ -544,6 +546,53 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_cons
             atomicAdd(&C->node_visits, (unsigned long long)work[0]);
             atomicAdd(&C->tri_tests, (unsigned long long)work[1]);
             for (int k = 0; k < 6; ++k) atomicAdd(&C->dbg[k], dbg[k]);
+        }
+    }
+}
+
+// k_traverse_octree: the same job as k_traverse — every mesh query of one iteration — under RTB_ACCEL_OCTREE_REFERENCE:
+// each ray walks the reference's octrees (octree.cuh) instead of the LBVH.  One ray per thread, grid-stride; the octree
+// search is not a nearest-hit query, so a shadow ray cannot stop at the first triangle below its limit either: it takes
+// the hit the reference's trace_ray would see and compares (mutually_visible, src/scene.rs:258-270).
+template <bool COUNT>
+__global__ void __launch_bounds__(WF_THREADS) k_traverse_octree(const __grid_constant__ RenderArgs a, int c) {
+    DevCtrl* C = a.ctrl;
+    const uint32_t n_ext = C->ext_head(c);
+    const uint32_t count = n_ext + C->sh_head(c);
+    const int light_obj = a.S.hdr->light_obj;
+    uint32_t work[2] = {0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        if (i < n_ext) {
+            const float2 h2 = a.qin.hit[i];
+            if (__float_as_uint(h2.y) == HIT_HOLE) continue;
+            const float4 o4 = a.qin.o[i], d4 = a.qin.d[i];
+            float t = h2.x;
+            uint32_t id = PC_NONE;
+            oct_trace_meshes(a.S, f3(o4), f3(d4), __float_as_uint(o4.w), t, id, COUNT ? work : nullptr);
+            if (id != PC_NONE) a.qin.hit[i] = make_float2(t, __uint_as_float(id));
+        } else {
+            const uint32_t j = i - n_ext;
+            const float4 d4 = a.sqin.d[j];
+            if (__float_as_uint(d4.w) == TLIM_HOLE) continue;
+            const float4 o4 = a.sqin.o[j], c4 = a.sqin.c[j];
+            float t = d4.w;   // NEE candidate: |y - x| - margin; dead-MIS probe: the analytic hit distance
+            uint32_t id = PC_NONE;
+            oct_trace_meshes(a.S, f3(o4), f3(d4), __float_as_uint(o4.w), t, id, COUNT ? work : nullptr);
+            bool add;
+            if (__float_as_uint(c4.w) & SHADOW_PROBE)
+                add = id != PC_NONE && __float_as_int(__ldg(a.S.tris + (size_t)(id - TRI_BASE) * TRI_STRIDE + 2).w) == light_obj;
+            else add = id == PC_NONE;   // no mesh hit below the limit: visible
+            if (add) accum_add(a.accum, __float_as_uint(c4.w) & ~SHADOW_PROBE, f3(c4));
+        }
+    }
+    if (COUNT) {
+        for (int off = 16; off; off >>= 1) {
+            work[0] += __shfl_down_sync(0xffffffffu, work[0], off);
+            work[1] += __shfl_down_sync(0xffffffffu, work[1], off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&C->node_visits, (unsigned long long)work[0]);
+            atomicAdd(&C->tri_tests, (unsigned long long)work[1]);
         }
     }
 }
@@ -1079,7 +1128,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(WF_THREADS) k_trace_rays(DevScene S, long long n, const float* __restrict__ org, const float* __restrict__ dir,
                                                            const Camera cam, int width, int height, int sx, int sy, float dx, float dy,
                                                            int32_t* __restrict__ obj, int32_t* __restrict__ tri, float* __restrict__ tout,
-                                                           unsigned long long* __restrict__ work_out) {
+                                                           unsigned long long* __restrict__ work_out, int accel = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SharedScene sh = stage_scene(S, smem_raw);
     uint32_t work[2] = {0, 0};
@@ -1096,7 +1145,9 @@ __global__ void __launch_bounds__(WF_THREADS) k_trace_rays(DevScene S, long long
         float t;
         uint32_t id;
         analytic_closest(sh, S.n_planes, S.n_prims, o, d, PC_NONE, t, id);
-        if (ray_hits_bvh_box(S, o, d, t)) {
+        if (accel == 1) {   // RTB_ACCEL_OCTREE_REFERENCE
+            oct_trace_meshes(S, o, d, PC_NONE, t, id, COUNT ? work : nullptr);
+        } else if (ray_hits_bvh_box(S, o, d, t)) {
             if (S.wide) bvh_traverse<false, COUNT, true>(S, sh, o, d, PC_NONE, t, id, 0.0f, work);
             else bvh_traverse<false, COUNT, false>(S, sh, o, d, PC_NONE, t, id, 0.0f, work);
         }

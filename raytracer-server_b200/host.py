@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 from . import _abi
-from ._abi import EST_MIS_BALANCE, EST_MIS_DEAD, EST_NEE, ObjectDesc, ObjectInfo, Params, SceneDesc, SceneInfo, Stats
+from ._abi import ACCEL_LBVH, ACCEL_OCTREE_REFERENCE, EST_MIS_BALANCE, EST_MIS_DEAD, EST_NEE, ObjectDesc, ObjectInfo, Params, SceneDesc, SceneInfo, Stats
 
 
 class RtbError(RuntimeError):
@@ -44,18 +44,19 @@ def _check(rc: int, load: bool = False):
 
 def make_params(width: int, height: int, spp: int, *, use_mis: bool = False, seed: int = 0, rank: int = 0, world: int = 1,
                 pool_paths: int = 0, count_work: bool = False, tune_refill: int = 0, tune_steps: int = 0,
-                bin_bits: int | None = None, bin_octant_major: bool = False, estimator: int | None = None) -> Params:
+                bin_bits: int | None = None, bin_octant_major: bool = False, estimator: int | None = None,
+                accel: int = 0) -> Params:
     """bin_bits: coherence binning of the LBVH rays — None = library default, 0 = off, 2..5 = cell bits per axis."""
     p = Params()
     p.width, p.height, p.spp = width, height, spp
     p.estimator = estimator if estimator is not None else (EST_MIS_DEAD if use_mis else EST_NEE)
     p.seed = seed
     p.rank, p.world, p.pool_paths = rank, world, pool_paths
-    p.reserved[0] = 1 if count_work else 0
-    p.reserved[1] = tune_refill
-    p.reserved[2] = tune_steps
-    p.reserved[3] = 0 if bin_bits is None else (1 if bin_bits <= 0 else max(2, bin_bits))
-    p.reserved[4] = 1 if bin_octant_major else 0
+    p.accel = accel
+    p.tuning[0] = 1 if count_work else 0
+    p.tuning[1] = tune_refill
+    p.tuning[2] = tune_steps
+    p.tuning[3] = (0 if bin_bits is None else (1 if bin_bits <= 0 else max(2, bin_bits))) + (256 if bin_octant_major else 0)
     return p
 
 
@@ -156,6 +157,12 @@ class Scene:
             _abi.lib().rtb_scene_triangles(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), n)
         return out
 
+    def octree_stats(self, index: int) -> dict:
+        """Octree::build for mesh object `index` on the host (what ACCEL_OCTREE_REFERENCE traverses)."""
+        c = (C.c_int64 * 4)()
+        _check(_abi.lib().rtb_scene_octree_stats(self._h, index, c))
+        return {"nodes": c[0], "parents": c[1], "leaves": c[2], "tri_refs": c[3]}
+
     def upload(self) -> int:
         b = C.c_uint64()
         _check(_abi.lib().rtb_scene_upload(self._h, C.byref(b)))
@@ -170,11 +177,11 @@ class Scene:
     def render(self, width: int, height: int, spp: int, *, use_mis: bool = False, seed: int = 0, rank: int = 0,
                world: int = 1, pool_paths: int = 0, out: np.ndarray | None = None, count_work: bool = False,
                tune_refill: int = 0, tune_steps: int = 0, bin_bits: int | None = None, bin_octant_major: bool = False,
-               estimator: int | None = None) -> np.ndarray:
+               estimator: int | None = None, accel: int = 0) -> np.ndarray:
         """Returns the frame as uint8 [height, width, 3], row 0 = top (the bytes of src/server.rs:187-189)."""
         p = make_params(width, height, spp, use_mis=use_mis, seed=seed, rank=rank, world=world, pool_paths=pool_paths,
                         count_work=count_work, tune_refill=tune_refill, tune_steps=tune_steps, bin_bits=bin_bits,
-                        bin_octant_major=bin_octant_major, estimator=estimator)
+                        bin_octant_major=bin_octant_major, estimator=estimator, accel=accel)
         if out is None:
             out = np.zeros((height, width, 3), dtype=np.uint8)
         assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size == width * height * 3
@@ -197,7 +204,7 @@ class Scene:
                                             tri.ctypes.data_as(ip), t.ctypes.data_as(fp)))
         return {"obj": obj, "tri": tri, "t": t}
 
-    def trace_rays(self, org, dirs, count_work: bool = False):
+    def trace_rays(self, org, dirs, count_work: bool = False, accel: int = 0):
         org = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)
         dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
         n = org.shape[0]
@@ -206,15 +213,19 @@ class Scene:
         t = np.empty(n, dtype=np.float32)
         work = (C.c_uint64 * 2)(0, 0)
         ip, fp = C.POINTER(C.c_int32), C.POINTER(C.c_float)
-        _check(_abi.lib().rtb_trace_rays(self._h, n, org.ctypes.data_as(fp), dirs.ctypes.data_as(fp), obj.ctypes.data_as(ip),
-                                         tri.ctypes.data_as(ip), t.ctypes.data_as(fp), work if count_work else None))
+        if accel:
+            _check(_abi.lib().rtb_trace_rays_accel(self._h, accel, n, org.ctypes.data_as(fp), dirs.ctypes.data_as(fp), obj.ctypes.data_as(ip),
+                                                   tri.ctypes.data_as(ip), t.ctypes.data_as(fp)))
+        else:
+            _check(_abi.lib().rtb_trace_rays(self._h, n, org.ctypes.data_as(fp), dirs.ctypes.data_as(fp), obj.ctypes.data_as(ip),
+                                             tri.ctypes.data_as(ip), t.ctypes.data_as(fp), work if count_work else None))
         res = {"obj": obj, "tri": tri, "t": t}
         if count_work:
             res["work"] = {"node_visits": work[0], "tri_tests": work[1]}
         return res
 
-    def sample_radiance(self, width, height, spp, px, py, sample_idx, *, use_mis=False, seed=0, estimator=None) -> np.ndarray:
-        p = make_params(width, height, spp, use_mis=use_mis, seed=seed, estimator=estimator)
+    def sample_radiance(self, width, height, spp, px, py, sample_idx, *, use_mis=False, seed=0, estimator=None, accel=0) -> np.ndarray:
+        p = make_params(width, height, spp, use_mis=use_mis, seed=seed, estimator=estimator, accel=accel)
         px = np.ascontiguousarray(px, dtype=np.int32)
         py = np.ascontiguousarray(py, dtype=np.int32)
         si = np.ascontiguousarray(sample_idx, dtype=np.int32)

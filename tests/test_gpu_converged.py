@@ -78,3 +78,17 @@ def test_distance_to_the_reference_octree(gpu_scene, parity_log, path):
         assert 28.0 <= m["psnr"] <= 33.0
         ys, xs = np.nonzero(d > 40)              # the gross differences sit on the mesh (screen centre-left), not on the walls
         assert 150 < np.median(xs) < 350 and 100 < np.median(ys) < 400
+
+
+@pytest.mark.skipif(not OCTREE, reason="no octree-faithful golden frames committed yet")
+@pytest.mark.parametrize("path", OCTREE, ids=[os.path.basename(f)[:-4] for f in OCTREE])
+def test_octree_mode_reproduces_the_reference_frame(rtb, gpu_scene, parity_log, path):
+    # ACCEL_OCTREE_REFERENCE: the GPU walks the reference's own octrees — BASELINE.json's image gate against what the Rust
+    # binary renders, flying_unicorn included
+    z = np.load(path)
+    w, h, spp, seed = int(z["width"]), int(z["height"]), int(z["spp"]), int(z["seed"])
+    got = gpu_scene(scene_of(path)).render(w, h, spp, seed=seed, accel=rtb.ACCEL_OCTREE_REFERENCE)
+    m = measure(got, z["rgb8"])
+    parity_log(f"gpu/octree_mode_frame/{os.path.basename(path)[:-4]}", spp=spp, **m)
+    assert (m["pixel_mre"] < 0.01).all() and (m["channel_mre"] < 0.01).all()
+    assert m["psnr"] >= 40.0 and m["frac_beyond_3_levels"] < 0.01

@@ -423,3 +423,59 @@ def test_wide_table_gives_the_same_hits(rtb, gpu_scene, monkeypatch):
     assert (a["tri"] >= 0).mean() > 0.05
     f2, f4 = g2.render(160, 120, 16, seed=2).astype(int), g4.render(160, 120, 16, seed=2).astype(int)
     assert np.abs(f2 - f4).max() <= 1
+
+
+# ---------------------------------------------------------------- ACCEL_OCTREE_REFERENCE: the reference's real mesh path
+@pytest.mark.parametrize("name", ["cubes", "flying_unicorn"])
+def test_octree_mode_returns_the_reference_hits(rtb, gpu_scene, oracle_scene, oracle_mod, parity_log, name):
+    # Octree::intersect is not a nearest-hit query (early exit on the first child with any hit, src/geometry.rs:1263-1273);
+    # the device traversal must return the SAME (possibly non-nearest) triangle as the oracle's octree_faithful mode
+    g, o = gpu_scene(name), oracle_scene(name)
+    W, H = 600, 450
+    org, dirs = o.primary_rays(W, H, 0, 0, 0.0, 0.0)
+    rng = np.random.default_rng(9)
+    n = 200_000
+    lo, hi = np.array(g.info.bvh_min, dtype=np.float64), np.array(g.info.bvh_max, dtype=np.float64)
+    so = lo + (hi - lo) * (rng.random((n, 3)) * 1.4 - 0.2)          # origins in and around the meshes: the secondary-ray case
+    sd = rng.normal(size=(n, 3))
+    sd /= np.linalg.norm(sd, axis=1, keepdims=True)
+    org32 = np.concatenate([org, so]).astype(np.float32)
+    d32 = np.concatenate([dirs, sd]).astype(np.float32)
+    d32 /= np.linalg.norm(d32.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    o.set_modes(oracle_mod.ACCEL_OCTREE_FAITHFUL, oracle_mod.EST_NEE)
+    ro = o.trace_rays(org32.astype(np.float64), d32.astype(np.float64))
+    o.set_modes(oracle_mod.ACCEL_EXACT, oracle_mod.EST_NEE)
+    rx = o.trace_rays(org32.astype(np.float64), d32.astype(np.float64))
+    rg = g.trace_rays(org32, d32, accel=rtb.ACCEL_OCTREE_REFERENCE)
+    differ = (ro["obj"] != rg["obj"]) | (ro["tri"] != rg["tri"])
+    # two surfaces at the same distance (the cubes' bottom faces lie IN the floor plane, two triangles share an edge): which one
+    # is reported is decided by rounding on both sides — the same exclusion as ambiguous_mask's first rule
+    with np.errstate(invalid="ignore"):
+        tie = differ & (np.abs(rg["t"].astype(np.float64) - ro["t"]) <= 1e-5 * np.abs(ro["t"]))
+    mism = differ & ~tie
+    non_nearest = (ro["tri"] != rx["tri"]) | (ro["obj"] != rx["obj"])      # where the reference itself misses the nearest triangle
+    ok = ~differ & (ro["obj"] >= 0)
+    rel = np.abs(rg["t"][ok].astype(np.float64) - ro["t"][ok]) / np.maximum(ro["t"][ok], 1e-3)
+    parity_log(f"gpu/octree_mode_rays/{name}", rays=int(mism.size), mesh_hits=int((ro["tri"] >= 0).sum()), mismatches=int(mism.sum()), equal_distance_ties=int(tie.sum()),
+               reference_non_nearest_hits=int(non_nearest.sum()), gpu_agrees_on_those=int((non_nearest & ~mism).sum()),
+               t_rel_q9999=np.quantile(rel, 0.9999))
+    assert mism.mean() < 1e-3            # fp32 vs f64 decisions at box faces / triangle edges
+    assert np.quantile(rel, 0.9999) < T_REL_TOL
+    if name == "flying_unicorn":
+        assert non_nearest.sum() > 1000 and (non_nearest & ~mism).sum() > 0.98 * non_nearest.sum()   # the defect itself is reproduced
+
+
+@pytest.mark.parametrize("name", ["cubes", "flying_unicorn"])
+def test_octree_mode_path_radiance(rtb, gpu_scene, oracle_scene, oracle_mod, parity_log, name):
+    g, o = gpu_scene(name), oracle_scene(name)
+    W, H, spp, n = 600, 450, 64, 20000
+    rng = np.random.default_rng(13)
+    px, py, si = rng.integers(0, W, n), rng.integers(0, H, n), rng.integers(0, spp, n)
+    o.set_modes(oracle_mod.ACCEL_OCTREE_FAITHFUL, oracle_mod.EST_NEE)
+    Lo = o.sample_radiance(W, H, spp, 42, px, py, si)
+    o.set_modes(oracle_mod.ACCEL_EXACT, oracle_mod.EST_NEE)
+    Lg = g.sample_radiance(W, H, spp, px, py, si, seed=42, accel=rtb.ACCEL_OCTREE_REFERENCE).astype(np.float64)
+    fin = np.isfinite(Lo).all(axis=1) & np.isfinite(Lg).all(axis=1)
+    err = path_error(Lg[fin], Lo[fin])
+    parity_log(f"gpu/octree_mode_path_radiance/{name}", paths=n, err_median=np.median(err), err_q99=np.quantile(err, 0.99), frac_beyond_1e3=(err > 1e-3).mean())
+    assert fin.mean() > 0.999 and np.median(err) < 1e-5 and (err > 1e-3).mean() < 0.03

@@ -210,3 +210,25 @@ geometry = { type = "plane", pos = [0.0, -1.0, 0.0], n = [0.0, 1.0, 0.0] }
     with pytest.raises(rtb.LoadTomlError) as e:
         rtb.Scene.from_objects((0, 0, 10), (0, 0, -1), [{"brdf": ("diffuse", (1, 1, 1)), "geometry": ("sphere", (0, 0, 0), 1.0)}], device=-1)
     assert e.value.kind == "NoLight"
+
+
+@pytest.mark.parametrize("name", ["cubes", "flying_unicorn"])
+def test_reference_octree_build_matches_oracle(rtb, oracle_scene, name):
+    # Octree::build (src/geometry.rs:1149-1216) restated twice — in the product (octree_host.cpp, what
+    # ACCEL_OCTREE_REFERENCE traverses on the device) and in the oracle: same node / leaf / triangle-reference census.
+    # flying_unicorn: SURVEY's probe of the reference structure (47 183 nodes, 187 766 references).
+    sc = rtb.Scene.from_toml(scene_path(name), device=-1)
+    osc = oracle_scene(name)
+    seen = 0
+    for i in range(sc.info.n_objects):
+        st = osc.mesh_stats(i)
+        if st is None:
+            with pytest.raises(rtb.RtbError):
+                sc.octree_stats(i)
+            continue
+        mine = sc.octree_stats(i)
+        assert (mine["parents"], mine["leaves"], mine["tri_refs"]) == (st["octree_parents"], st["octree_leaves"], st["octree_tri_refs"])
+        seen += 1
+    assert seen == (2 if name == "cubes" else 1)
+    if name == "flying_unicorn":
+        assert mine == {"nodes": 47183, "parents": 9540, "leaves": 37643, "tri_refs": 187766}

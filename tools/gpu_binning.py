@@ -1,4 +1,4 @@
-"""A/B of the coherence binning in front of k_traverse (rtb_params.reserved[3]).  Run under gpurun."""
+"""A/B of the coherence binning in front of k_traverse (rtb_params.tuning[3]).  Run under gpurun."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
