@@ -265,9 +265,9 @@ class RenderJob:
     PIXELS_PER_MSG = 60
 
     def __init__(self, scene: Scene, width: int, height: int, samples_per_pixel: int, *, passes: int = 1, seed: int = 0,
-                 use_mis: bool = False, pool_paths: int = 0):
+                 use_mis: bool = False, pool_paths: int = 0, accel: int = 0):
         self.scene = scene
-        self.params = make_params(width, height, samples_per_pixel, use_mis=use_mis, seed=seed, pool_paths=pool_paths)
+        self.params = make_params(width, height, samples_per_pixel, use_mis=use_mis, seed=seed, pool_paths=pool_paths, accel=accel)
         self._h = C.c_void_p()
         # guards the handle: stop() may come from another thread (the server's event loop) while close() frees the job
         self._lock = threading.Lock()

@@ -35,7 +35,9 @@ WIDTH, HEIGHT = 600, 450                                   # Server::WIDTH / HEI
 DEFAULT_PORT = "8080"                                      # src/main.rs:16
 
 
-def default_job_factory(scenes: dict, width: int, height: int):
+def default_job_factory(scenes: dict, width: int, height: int, accel: int = 0):
+    """accel: 0 = LBVH (true nearest hit, the fast path), 1 = the reference's own octrees (ACCEL_OCTREE_REFERENCE: the image the
+    Rust binary sends, non-nearest triangles included; 9 x slower on flying_unicorn).  `main` reads it from $RTB_ACCEL."""
     from .host import RenderJob
 
     def make(scene_name: str, spp: int, passes: int = 1):
@@ -44,7 +46,7 @@ def default_job_factory(scenes: dict, width: int, height: int):
             return None
         # spp is an i32 in the reference (`ClientMessage::Render`, :123); `num_samples = spp / 4` makes every spp < 4,
         # negative ones included, an empty sample loop: a black frame is streamed (src/server.rs:332-362)
-        return RenderJob(scene, width, height, max(0, spp), passes=passes, seed=random.getrandbits(63))
+        return RenderJob(scene, width, height, max(0, spp), passes=passes, seed=random.getrandbits(63), accel=accel)
 
     return make
 
@@ -176,7 +178,8 @@ def main(argv=None):
         return 2
     scenes = load_scenes(argv[0])
     port = os.environ.get("PORT", DEFAULT_PORT)
-    asyncio.run(Server(scenes).listen(port))
+    accel = 1 if os.environ.get("RTB_ACCEL", "lbvh").lower() in ("octree", "reference", "1") else 0
+    asyncio.run(Server(scenes, job_factory=default_job_factory(scenes, WIDTH, HEIGHT, accel)).listen(port))
     return 0
 
 
