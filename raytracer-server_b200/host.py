@@ -66,9 +66,13 @@ class Scene:
     def __init__(self, handle: int, name: str = ""):
         self._h = C.c_void_p(handle)
         self.name = name
+
+    @property
+    def info(self) -> SceneInfo:
+        """rtb_scene_get_info: counts, LBVH shape, and (once ACCEL_OCTREE_REFERENCE has been used) the octree tables' sizes"""
         info = SceneInfo()
         _check(_abi.lib().rtb_scene_get_info(self._h, C.byref(info)))
-        self.info = info
+        return info
 
     # ---- Scene::from_toml ------------------------------------------------------------------
     @classmethod

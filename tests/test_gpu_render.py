@@ -348,6 +348,38 @@ def test_balance_heuristic_mis_mode(gpu_scene, rtb, parity_log):
     assert abs(f.mean() - g.render(200, 150, 64, seed=6).astype(int).mean()) < 0.02 * f.mean()
 
 
+def test_binning_knob_changes_nothing_but_the_order(gpu_scene):
+    # coherence binning of the LBVH rays (tuning[3], off by default; DESIGN.md "Ray sorting, measured"): k_traverse fetches its
+    # rays through a permutation, results and ray counts are those of the unbinned run
+    g = gpu_scene("flying_unicorn")
+    W, H, spp = 240, 180, 32
+    ref = g.render(W, H, spp, seed=4).astype(int)
+    base = g.stats()
+    for bits, octm in ((3, False), (5, True)):
+        f = g.render(W, H, spp, seed=4, bin_bits=bits, bin_octant_major=octm).astype(int)
+        st = g.stats()
+        assert np.abs(f - ref).max() <= 1
+        assert all(st[k] == base[k] for k in ("samples", "rays_primary", "rays_extension", "rays_shadow", "rays_bvh", "shadow_bvh"))
+        assert st["kernel_launches"] == base["kernel_launches"] + 3 * st["iterations"]      # k_bin_keys, _scan, _scatter per iteration
+
+
+def test_streaming_job_in_reference_octree_mode(gpu_scene, rtb, monkeypatch):
+    # accel travels with the job: bands rendered through the reference's octrees equal the blocking render in that mode,
+    # and differ from the LBVH image where the octree's early exit picks other triangles (flying_unicorn)
+    monkeypatch.setenv("RTB_BAND_TILE_ROWS", "2")
+    g = gpu_scene("flying_unicorn")
+    W, H, spp = 200, 150, 16
+    octree = g.render(W, H, spp, seed=9, accel=rtb.ACCEL_OCTREE_REFERENCE).astype(int)
+    lbvh = g.render(W, H, spp, seed=9).astype(int)
+    job = rtb.RenderJob(g, W, H, spp, seed=9, accel=rtb.ACCEL_OCTREE_REFERENCE)
+    (idx, f), = list(job.frames())
+    job.close()
+    assert np.abs(f.astype(int) - octree).max() <= 1
+    assert (np.abs(octree - lbvh) > 8).mean() > 0.002
+    assert g.info.octree_nodes == 47183 and g.info.octree_tri_refs == 187766     # built on first use (SURVEY's census of the reference structure)
+    assert rtb.Scene.from_toml(scene_path("cubes"), device=0).render(64, 48, 8, accel=rtb.ACCEL_OCTREE_REFERENCE).shape == (48, 64, 3)
+
+
 def test_job_cancel(gpu_scene, rtb):
     g = gpu_scene("flying_unicorn")
     job = rtb.RenderJob(g, 1920, 1080, 4096, seed=1)   # seconds of work
