@@ -187,6 +187,23 @@ def test_frame_matches_oracle_same_seed(gpu_scene, oracle_scene, oracle_mod, par
     assert st["samples"] == W * H * spp
 
 
+@pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 2160)])
+def test_rows_of_the_bench_frames_match_oracle(gpu_scene, oracle_scene, parity_log, W, H):
+    # BASELINE.json configs[2] / configs[3] sizes: the oracle renders a few scan lines of the full-size frame (through the
+    # Pegasus, its mirror image and the light), the GPU the whole frame with the same seed — the bytes of those rows must agree
+    g, o = gpu_scene("flying_unicorn"), oracle_scene("flying_unicorn")
+    spp, seed = 16, 31
+    y0, stride = int(H * 0.07), H // 14
+    rows = list(range(y0, H, stride))                      # 14 scan lines, one oracle call (rows are scheduled over the host threads)
+    want = o.render(W, H, spp, seed=seed, y0=y0, y1=H, row_stride=stride, nthreads=-NCPU)["rgb8"][rows]
+    got = g.render(W, H, spp, seed=seed)[rows]
+    d = np.abs(got.astype(int) - want.astype(int))
+    parity_log(f"gpu/bench_frame_rows/flying_unicorn/{W}x{H}", rows=rows, spp=spp, pixel_mre=pixel_mre(got, want, blur=1), psnr=psnr(got, want),
+               frac_beyond_2_levels=(d > 2).mean(), max_level_diff=int(d.max()))
+    assert (pixel_mre(got, want, blur=1) < 0.01).all() and psnr(got, want) >= 40.0
+    assert (d > 2).mean() < 0.01
+
+
 def test_converged_frame_independent_seeds(gpu_scene, oracle_scene, parity_log):
     # statistical form of the 1 % / 40 dB gate: oracle and GPU with DIFFERENT seeds, against the noise floor
     # of two oracle renders.  Small frame, 1024 spp (the oracle is a scalar CPU program).
