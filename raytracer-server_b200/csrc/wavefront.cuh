@@ -332,8 +332,8 @@ __device__ __forceinline__ uint32_t bin_key_of(const RenderArgs& a, float3 o, fl
 
 __global__ void __launch_bounds__(WF_THREADS) k_bin_keys(const __grid_constant__ RenderArgs a, int c) {
     DevCtrl* C = a.ctrl;
-    const uint32_t n_ext = C->ext_head(c);
-    const uint32_t count = n_ext + C->sh_head(c);
+    const uint32_t n_ext = min(C->ext_head(c), a.Pcap);   // (the heads also count slots refused for lack of capacity — an error the host reports)
+    const uint32_t count = n_ext + min(C->sh_head(c), a.SPcap);
     const uint32_t bins = 8u << (3 * a.bin_bits);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         float4 o4, d4;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(BIN_SCAN_THREADS) k_bin_scan(const __grid_cons
 
 __global__ void __launch_bounds__(WF_THREADS) k_bin_scatter(const __grid_constant__ RenderArgs a, int c) {
     DevCtrl* C = a.ctrl;
-    const uint32_t count = C->ext_head(c) + C->sh_head(c);
+    const uint32_t count = min(C->ext_head(c), a.Pcap) + min(C->sh_head(c), a.SPcap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
         a.bin_perm[atomicAdd(&a.bin_offs[a.bin_key[i]], 1u)] = i;
 }
@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_cons
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<int*>(smem_raw) + threadIdx.x), sstride = blockDim.x * 4u;
     int lstack[STACK_LOCAL];
     DevCtrl* C = a.ctrl;
-    const uint32_t n_ext = C->ext_head(c);   // only the BVH class of the path queue needs a traversal
-    const uint32_t count = n_ext + C->sh_head(c);
+    const uint32_t n_ext = min(C->ext_head(c), a.Pcap);   // only the BVH class of the path queue needs a traversal
+    const uint32_t count = n_ext + min(C->sh_head(c), a.SPcap);
     const unsigned lane = threadIdx.x & 31;
     const PathQueue& Q = a.qin;
     const ShadowQueue& SQ = a.sqin;
@@ -557,8 +557,8 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_cons
 template <bool COUNT>
 __global__ void __launch_bounds__(WF_THREADS) k_traverse_octree(const __grid_constant__ RenderArgs a, int c) {
     DevCtrl* C = a.ctrl;
-    const uint32_t n_ext = C->ext_head(c);
-    const uint32_t count = n_ext + C->sh_head(c);
+    const uint32_t n_ext = min(C->ext_head(c), a.Pcap);
+    const uint32_t count = n_ext + min(C->sh_head(c), a.SPcap);
     const int light_obj = a.S.hdr->light_obj;
     uint32_t work[2] = {0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {

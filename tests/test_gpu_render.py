@@ -1,6 +1,7 @@
 """Behaviour of the render entry points on the GPU: frame conventions, size-independent properties
 at BASELINE.json sizes, tile sharding, streaming jobs, cancellation, error paths."""
 import ctypes as C
+import os
 import threading
 import time
 
@@ -428,3 +429,18 @@ def test_concurrent_renders_share_a_scene(gpu_scene):
 
 def test_fp32_peak_probe(rtb):
     assert 30.0 < rtb.fp32_peak_tflops(0) < 90.0
+
+
+def test_every_mode_with_tiny_pools(monkeypatch):
+    # tools/gpu_sanitize.py: every kernel, estimator, accel mode, probe / pixel-list entry point, the binning knob, banded,
+    # progressive and cancelled jobs on pools of 2-4 k paths (many regeneration rounds, queue segments with holes).
+    # Written for compute-sanitizer (closed on this pool); here it must simply run clean — the library reports queue
+    # overflows, CUDA errors and inconsistent counters as errors.
+    import runpy
+
+    from conftest import ROOT
+
+    for k in ("RTB_NO_GRAPH", "RTB_BAND_TILE_ROWS"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("RTB_KEEP", "1")       # (monkeypatch restores os.environ after the script's own changes)
+    runpy.run_path(os.path.join(ROOT, "tools", "gpu_sanitize.py"), run_name="__main__")
