@@ -40,6 +40,16 @@
 #include <thread>
 #include <vector>
 
+// ORACLE_F32 (liboracle_f32.so, `make liboracle_f32.so`): the SAME restatement with every stored quantity — scene data, rays,
+// hit records, accumulators — in fp32, so that tests can ask "does the f64 answer survive fp32 rounding of the inputs?" for a
+// ray on which the GPU (which stores fp32) and the f64 oracle disagree.  Only the intersection hooks (or_primary_rays /
+// or_trace_rays) are meaningful in this build: the reference leaves a surface through a 1e-5 offset that fp32 cannot resolve at
+// x ~ 100, so rendering with it self-intersects (the GPU handles that case analytically, intersect.cuh).  The C entry points then
+// take float* where they take double* here; oracle.py (OracleScene(..., f32=True)) passes float32 arrays.
+#ifdef ORACLE_F32
+#define double float
+#endif
+
 namespace {
 
 constexpr double PI = 3.14159265358979323846264338327950288;       // std::f64::consts::PI
@@ -644,7 +654,7 @@ struct Scene {  // src/scene.rs:101-107
                 return V(0, 0, 0);
             default: {
                 Vec3 reflection = flip_across(i, n);
-                double c = std::max(dot(o, reflection), 0.);
+                double c = std::max(dot(o, reflection), (double)0.);
                 double pw = 1.0;  // powi
                 for (int k = 0; k < f.power; ++k) pw *= c;
                 return f.color_d * f.kd * FRAC_1_PI + f.color_s * f.ks * (double)(f.power + 2) / (2. * PI) * pw;

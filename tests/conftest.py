@@ -64,6 +64,47 @@ def gpu_scene(rtb):
 NCPU = os.cpu_count() or 1
 
 
+@pytest.fixture(scope="session")
+def oracle_f32_twin(oracle_mod, gpu_scene, tmp_path_factory):
+    """The fp32-storage build of the oracle (liboracle_f32.so) fed with EXACTLY the geometry the GPU holds: analytic objects
+    from the loader's records (rounded to fp32 on both sides), meshes from the device scene's own fp32 triangles (written to
+    an OBJ with exact decimal representations, no transforms).  Answers "would the reference's arithmetic, on fp32 data,
+    decide like the GPU?" for rays on which the GPU and the f64 oracle disagree."""
+    cache = {}
+
+    def get(name):
+        if name in cache:
+            return cache[name]
+        g = gpu_scene(name)
+        d = tmp_path_factory.mktemp("f32twin_" + name)
+        tris = g.triangles()
+        info = g.info
+        objects = []
+        for i in range(info.n_objects):
+            ob = g.object(i)
+            brdf = ({"type": "diffuse", "kd": ob["k"]} if ob["brdf"] == 0 else {"type": "specular", "ks": ob["k"]} if ob["brdf"] == 1 else
+                    {"type": "phong", "kd": ob["k"][0], "ks": ob["k"][1], "power": int(ob["k"][2]), "color_d": ob["color_d"], "color_s": ob["color_s"]})
+            if ob["geometry"] == 0:
+                geom = {"type": "sphere", "pos": ob["pos"], "r": ob["r"]}
+            elif ob["geometry"] == 1:
+                geom = {"type": "plane", "pos": ob["pos"], "n": ob["n"]}
+            else:
+                t = tris[ob["first_triangle"]: ob["first_triangle"] + ob["n_triangles"]].reshape(-1, 3)
+                with open(d / f"mesh{i}.obj", "w") as f:
+                    for v in t:
+                        f.write(f"v {float(v[0])!r} {float(v[1])!r} {float(v[2])!r}\n")
+                    for k in range(ob["n_triangles"]):
+                        f.write(f"f {3 * k + 1} {3 * k + 2} {3 * k + 3}\n")
+                geom = {"type": "mesh", "path": f"mesh{i}.obj"}
+            objects.append({"emitted": ob["emitted"], "brdf": brdf, "geometry": geom})
+        spec = {"camera": {"pos": list(info.camera_pos), "dir": list(info.camera_dir)}, "objects": objects}
+        cache[name] = oracle_mod.OracleScene(spec, str(d), f32=True)
+        cache[name].set_modes(oracle_mod.ACCEL_EXACT, oracle_mod.EST_NEE)
+        return cache[name]
+
+    return get
+
+
 # ---- measured parity numbers: every parity test records what it measured (not only whether it passed); the session
 # writes them to gpurun_out/parity_{gpu,cpu}.json (override: $RTB_PARITY_OUT) — the GPU file is committed per round as
 # profiles/parity_rNN.json
