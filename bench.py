@@ -296,7 +296,9 @@ def main():
 
     wl = workload(world)
     W, H, SPP = wl["width"], wl["height"], args.spp or wl["spp"]
+    t_load = time.perf_counter()
     scene = R.Scene.from_toml(os.path.join(SCENES, SCENE + ".toml"), device=local_rank)
+    t_load = time.perf_counter() - t_load
     L = _abi.lib()
 
     def barrier():
@@ -529,6 +531,10 @@ def main():
             "bvh_ray_fraction": {"extension": totals["rays_bvh"] / max(1.0, vertices),
                                  "shadow": totals["shadow_bvh"] / max(1.0, totals["rays_shadow"])},
             "cpu_baseline": cpu,
+            # once per scene and rank, outside every timed region: each rank parses the TOML / OBJ and builds its own LBVH
+            # (deterministic; nothing is broadcast — 4 MB of tables would cost more to ship than the build does to run)
+            "setup": {"scene_load_ms": t_load * 1e3, "lbvh_build_ms": info.build_ms, "lbvh_nodes": info.bvh_nodes, "lbvh_depth": info.bvh_depth,
+                      "triangles": info.n_triangles, "note": "host TOML + OBJ parse, flatten, upload, device LBVH build (incl. the first CUDA context use)"},
         }
         out.update(extra)
     if dist is not None:
