@@ -560,8 +560,10 @@ __global__ void __launch_bounds__(WF_THREADS) k_traverse_octree(const __grid_con
     const uint32_t n_ext = min(C->ext_head(c), a.Pcap);
     const uint32_t count = n_ext + min(C->sh_head(c), a.SPcap);
     const int light_obj = a.S.hdr->light_obj;
+    const uint32_t* const perm = a.bin_bits > 0 ? a.bin_perm : nullptr;   // bin order: neighbouring lanes walk neighbouring octants
     uint32_t work[2] = {0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < count; pos += gridDim.x * blockDim.x) {
+        const uint32_t i = perm ? perm[pos] : pos;
         if (i < n_ext) {
             const float2 h2 = a.qin.hit[i];
             if (__float_as_uint(h2.y) == HIT_HOLE) continue;
