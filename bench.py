@@ -297,7 +297,11 @@ def main():
     wl = workload(world)
     W, H, SPP = wl["width"], wl["height"], args.spp or wl["spp"]
     t_load = time.perf_counter()
-    scene = R.Scene.from_toml(os.path.join(SCENES, SCENE + ".toml"), device=local_rank)
+    if world > 1:   # the scene and its LBVH are loaded / built on rank 0 and broadcast ONCE (NCCL); the other ranks import the tables
+        scene = sharding.broadcast_scene(os.path.join(SCENES, SCENE + ".toml") if rank == 0 else None, device=local_rank, src=0)
+        torch.cuda.synchronize(dev)
+    else:
+        scene = R.Scene.from_toml(os.path.join(SCENES, SCENE + ".toml"), device=local_rank)
     t_load = time.perf_counter() - t_load
     L = _abi.lib()
 
@@ -531,10 +535,12 @@ def main():
             "bvh_ray_fraction": {"extension": totals["rays_bvh"] / max(1.0, vertices),
                                  "shadow": totals["shadow_bvh"] / max(1.0, totals["rays_shadow"])},
             "cpu_baseline": cpu,
-            # once per scene and rank, outside every timed region: each rank parses the TOML / OBJ and builds its own LBVH
-            # (deterministic; nothing is broadcast — 4 MB of tables would cost more to ship than the build does to run)
+            # once per job, outside every timed region.  N = 1: parse TOML + OBJ, flatten, upload, build the LBVH on the device.
+            # N > 1: rank 0 does that, exports objects + LBVH tables (rtb_scene_export) and broadcasts the blob over NCCL; the
+            # other ranks import it (rtb_scene_import): no parsing, no build, bit-identical tables on every GPU
             "setup": {"scene_load_ms": t_load * 1e3, "lbvh_build_ms": info.build_ms, "lbvh_nodes": info.bvh_nodes, "lbvh_depth": info.bvh_depth,
-                      "triangles": info.n_triangles, "note": "host TOML + OBJ parse, flatten, upload, device LBVH build (incl. the first CUDA context use)"},
+                      "triangles": info.n_triangles, "broadcast_bytes": int(scene.export().size) if world > 1 else 0,
+                      "note": "scene_load_ms includes the first CUDA context use" + ("; rank 0: load + build + export + broadcast" if world > 1 else "")},
         }
         out.update(extra)
     if dist is not None:

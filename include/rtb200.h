@@ -176,6 +176,16 @@ typedef struct rtb_scene_desc {
 
 int rtb_scene_create(const rtb_scene_desc* desc, int device, rtb_scene** out);
 
+/* ---- scene + BVH as one blob, for the one-time broadcast of a multi-GPU job -------------------------------------------
+ * rtb_scene_export writes the loaded objects (f64, after transforms) and the device-built LBVH tables, byte for byte as they
+ * sit in device memory, into buf and returns the number of bytes (call with buf = NULL / cap too small to query the size).
+ * rtb_scene_import rebuilds a scene handle on `device` from such a blob WITHOUT parsing TOML / OBJ or building a BVH: the
+ * importing GPU traverses bit-identical tables.  A host-only handle (device = -1) exports the objects alone and the importer
+ * builds its own LBVH.  (The reference's analogue is the Arc<HashMap<String, Scene>> every
+ * connection shares, src/server.rs:24 — here the sharers are GPUs.) */
+int64_t rtb_scene_export(rtb_scene* scene, void* buf, int64_t cap);
+int rtb_scene_import(const void* buf, int64_t bytes, int device, rtb_scene** out);
+
 int rtb_scene_get_info(const rtb_scene* scene, rtb_scene_info* info);
 int rtb_scene_object(const rtb_scene* scene, int32_t index, rtb_object_info* out);
 /* re-copy the flattened host scene (pinned) to the device; returns bytes copied via *bytes */

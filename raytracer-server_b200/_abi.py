@@ -78,7 +78,7 @@ EXPORTS = [
     "rtb_scene_upload", "rtb_scene_triangles", "rtb_render", "rtb_local_pixels", "rtb_tile_map", "rtb_render_device",
     "rtb_untile_device", "rtb_get_stats", "rtb_job_begin", "rtb_job_next", "rtb_job_next_messages", "rtb_job_next_frame", "rtb_job_cancel",
     "rtb_job_end", "rtb_trace_primary", "rtb_trace_rays", "rtb_sample_radiance", "rtb_fp32_peak",
-    "rtb_untile_device_async", "rtb_job_stats", "rtb_sample_pixels", "rtb_trace_rays_accel", "rtb_scene_octree_stats",
+    "rtb_untile_device_async", "rtb_job_stats", "rtb_sample_pixels", "rtb_trace_rays_accel", "rtb_scene_octree_stats", "rtb_scene_export", "rtb_scene_import",
 ]
 
 _lib = None
@@ -126,6 +126,9 @@ def lib():
     L.rtb_untile_device_async.argtypes = [C.POINTER(Params), vp, C.c_int64, vp, C.c_int, vp]
     L.rtb_job_stats.argtypes = [vp, C.POINTER(Stats)]
     L.rtb_sample_pixels.argtypes = [vp, C.POINTER(Params), C.c_int64, ip, ip, fp]
+    L.rtb_scene_export.argtypes = [vp, vp, C.c_int64]
+    L.rtb_scene_export.restype = C.c_int64
+    L.rtb_scene_import.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(vp)]
     L.rtb_scene_octree_stats.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64)]
     L.rtb_trace_rays_accel.argtypes = [vp, C.c_int32, C.c_int64, fp, fp, ip, ip, fp]
     for name in EXPORTS:

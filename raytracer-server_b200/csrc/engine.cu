@@ -166,7 +166,15 @@ int upload_scene(rtb_scene* sc, uint64_t* bytes) {
     return RTB_OK;
 }
 
-int build_device_scene(rtb_scene* sc) {
+// LBVH tables of an exported scene (rtb_scene_export): host copies, laid out like the device arrays
+struct LbvhImport {
+    LbvhResult meta;   // scalars; the pointers are unused
+    int n_tris;
+    const float4 *nodes, *tris, *tri_nrm;
+    const uint4 *qnodes, *qnodes4;
+};
+
+int build_device_scene(rtb_scene* sc, const LbvhImport* import = nullptr) {
     const FlatScene& fs = sc->fs;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -203,7 +211,24 @@ int build_device_scene(rtb_scene* sc) {
     CU_TRY(cudaEventCreate(&e1));
     CU_TRY(cudaEventRecord(e0, sc->stream));
     std::string err;
-    if (!build_lbvh(d_verts, d_triobj, n_tris, sc->stream, sc->bvh, err))
+    if (import) {   // the tables another rank built: copy instead of building (the scene + BVH broadcast of a multi-GPU job)
+        LbvhResult& B = sc->bvh;
+        B = import->meta;
+        B.d_nodes = nullptr; B.d_qnodes = nullptr; B.d_qnodes4 = nullptr; B.d_tris = nullptr; B.d_tri_nrm = nullptr;
+        if (import->n_tris != n_tris) return fail(RTB_EPARSE, "exported scene: triangle count does not match the LBVH tables");
+        auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+            cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+            if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, sc->stream);
+            return e;
+        };
+        if (n_tris) {
+            CU_TRY(up((void**)&B.d_nodes, import->nodes, (size_t)B.n_nodes * 4 * sizeof(float4)));
+            CU_TRY(up((void**)&B.d_qnodes, import->qnodes, (size_t)B.n_nodes * 2 * sizeof(uint4)));
+            CU_TRY(up((void**)&B.d_qnodes4, import->qnodes4, (size_t)std::max(B.n_nodes4, 1) * 4 * sizeof(uint4)));
+            CU_TRY(up((void**)&B.d_tris, import->tris, (size_t)n_tris * TRI_STRIDE * sizeof(float4)));
+            CU_TRY(up((void**)&B.d_tri_nrm, import->tri_nrm, (size_t)n_tris * sizeof(float4)));
+        }
+    } else if (!build_lbvh(d_verts, d_triobj, n_tris, sc->stream, sc->bvh, err))
         return fail(err.rfind("unsupported:", 0) == 0 ? RTB_EUNSUPPORTED : RTB_ECUDA, err);
     if (n_tris) {
         CU_TRY(cudaMalloc((void**)&sc->d_tri_orig, (size_t)n_tris * 3 * sizeof(float4)));
@@ -286,7 +311,7 @@ int build_device_scene(rtb_scene* sc) {
     return RTB_OK;
 }
 
-int finish_scene(rtb_scene* sc, int rc, const std::string& err, rtb_scene** out) {
+int finish_scene(rtb_scene* sc, int rc, const std::string& err, rtb_scene** out, const LbvhImport* import = nullptr) {
     if (rc != RTB_OK) {
         delete sc;
         return fail(rc, err);
@@ -311,7 +336,7 @@ int finish_scene(rtb_scene* sc, int rc, const std::string& err, rtb_scene** out)
         *out = sc;
         return RTB_OK;
     }
-    rc = build_device_scene(sc);
+    rc = build_device_scene(sc, import);
     if (rc != RTB_OK) {
         std::string keep = g_last_error;
         delete sc;
@@ -1018,6 +1043,141 @@ int rtb_scene_create(const rtb_scene_desc* desc, int device, rtb_scene** out) {
     }
     if (rc == RTB_OK) rc = finish_host_scene(sc->hs, err);
     return finish_scene(sc, rc, err, out);
+}
+
+// ---- scene + BVH as one blob: what a multi-GPU job broadcasts once (BASELINE.json north_star) --------------------
+// Layout: ExportHeader | per object: ExportObject, vertices (3 f64 each), indices (u32), cumulative areas (f64) | LBVH tables
+// (fp32 nodes, quantised nodes, 4-wide nodes, triangles, normals) exactly as they sit in device memory.  A rank that imports
+// the blob neither parses TOML / OBJ nor builds a BVH; it gets bit-identical tables, hence bit-identical traversal.
+namespace {
+struct ExportHeader {
+    char magic[8];
+    uint64_t total_bytes;
+    double cam_pos[3], cam_dir[3];
+    int32_t n_objects, light;
+    int32_t n_tris, n_nodes, n_leaves, root, depth, n_nodes4, root4, pad;
+    float qmin[3], qstep[3], bmin[3], bmax[3];
+    double build_ms;
+};
+struct ExportObject {
+    double emitted[3], k[3], color_d[3], color_s[3], pos[3], n[3], bb_min[3], bb_max[3];
+    double phong_kd, phong_ks, r, surface_area;
+    int32_t brdf, phong_power, geom, pad;
+    uint64_t n_vertices, n_indices, n_cum;
+};
+constexpr char EXPORT_MAGIC[8] = {'R', 'T', 'B', 'S', 'C', 'N', '2', 0};
+void put3(double* d, const D3& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+D3 get3(const double* d) { return D3{d[0], d[1], d[2]}; }
+size_t lbvh_bytes(const LbvhResult& B, int n_tris) {
+    if (n_tris == 0) return 0;
+    return (size_t)B.n_nodes * 4 * sizeof(float4) + (size_t)B.n_nodes * 2 * sizeof(uint4) + (size_t)std::max(B.n_nodes4, 1) * 4 * sizeof(uint4) +
+           (size_t)n_tris * TRI_STRIDE * sizeof(float4) + (size_t)n_tris * sizeof(float4);
+}
+}  // namespace
+
+int64_t rtb_scene_export(rtb_scene* scene, void* buf, int64_t cap) {
+    if (!scene) return fail(RTB_EINVAL, "NULL scene");
+    // a host-only handle (device = -1) exports the objects alone (n_tris = -1 in the header): the importer builds the LBVH itself
+    const bool tables = scene->device >= 0;
+    const int n_tris = tables ? scene->view.n_tris : 0;
+    size_t total = sizeof(ExportHeader);
+    for (const HostObject& o : scene->hs.objects)
+        total += sizeof(ExportObject) + o.vertices.size() * 3 * sizeof(double) + o.indices.size() * sizeof(uint32_t) + o.cumulative_area.size() * sizeof(double);
+    total = align_up(total, 16);
+    const size_t lbvh_off = total;
+    total += lbvh_bytes(scene->bvh, n_tris);
+    if (!buf || cap < (int64_t)total) return (int64_t)total;   // size query
+    unsigned char* p = static_cast<unsigned char*>(buf);
+    ExportHeader H{};
+    std::memcpy(H.magic, EXPORT_MAGIC, 8);
+    H.total_bytes = total;
+    put3(H.cam_pos, scene->hs.cam_pos);
+    put3(H.cam_dir, scene->hs.cam_dir);
+    H.n_objects = (int32_t)scene->hs.objects.size();
+    H.light = scene->hs.light;
+    const LbvhResult& B = scene->bvh;
+    H.n_tris = tables ? n_tris : -1; H.n_nodes = B.n_nodes; H.n_leaves = B.n_leaves; H.root = B.root; H.depth = B.depth; H.n_nodes4 = B.n_nodes4; H.root4 = B.root4;
+    for (int k = 0; k < 3; ++k) { H.qmin[k] = B.qmin[k]; H.qstep[k] = B.qstep[k]; H.bmin[k] = B.bmin[k]; H.bmax[k] = B.bmax[k]; }
+    H.build_ms = scene->info.build_ms;
+    std::memcpy(p, &H, sizeof(H));
+    size_t off = sizeof(H);
+    for (const HostObject& o : scene->hs.objects) {
+        ExportObject E{};
+        put3(E.emitted, o.emitted); put3(E.k, o.k); put3(E.color_d, o.color_d); put3(E.color_s, o.color_s); put3(E.pos, o.pos); put3(E.n, o.n);
+        put3(E.bb_min, o.bb_min); put3(E.bb_max, o.bb_max);
+        E.phong_kd = o.phong_kd; E.phong_ks = o.phong_ks; E.r = o.r; E.surface_area = o.surface_area;
+        E.brdf = o.brdf; E.phong_power = o.phong_power; E.geom = o.geom;
+        E.n_vertices = o.vertices.size(); E.n_indices = o.indices.size(); E.n_cum = o.cumulative_area.size();
+        std::memcpy(p + off, &E, sizeof(E)); off += sizeof(E);
+        for (const D3& v : o.vertices) { const double t[3] = {v.x, v.y, v.z}; std::memcpy(p + off, t, sizeof(t)); off += sizeof(t); }
+        if (!o.indices.empty()) { std::memcpy(p + off, o.indices.data(), o.indices.size() * sizeof(uint32_t)); off += o.indices.size() * sizeof(uint32_t); }
+        if (!o.cumulative_area.empty()) { std::memcpy(p + off, o.cumulative_area.data(), o.cumulative_area.size() * sizeof(double)); off += o.cumulative_area.size() * sizeof(double); }
+    }
+    if (n_tris) {
+        CU_TRY(cudaSetDevice(scene->device));
+        off = lbvh_off;
+        auto down = [&](const void* src, size_t bytes) { cudaError_t e = cudaMemcpy(p + off, src, bytes, cudaMemcpyDeviceToHost); off += bytes; return e; };
+        CU_TRY(down(B.d_nodes, (size_t)B.n_nodes * 4 * sizeof(float4)));
+        CU_TRY(down(B.d_qnodes, (size_t)B.n_nodes * 2 * sizeof(uint4)));
+        CU_TRY(down(B.d_qnodes4, (size_t)std::max(B.n_nodes4, 1) * 4 * sizeof(uint4)));
+        CU_TRY(down(B.d_tris, (size_t)n_tris * TRI_STRIDE * sizeof(float4)));
+        CU_TRY(down(B.d_tri_nrm, (size_t)n_tris * sizeof(float4)));
+    }
+    return (int64_t)total;
+}
+
+int rtb_scene_import(const void* buf, int64_t bytes, int device, rtb_scene** out) {
+    if (!buf || !out) return fail(RTB_EINVAL, "NULL argument");
+    *out = nullptr;
+    const unsigned char* p = static_cast<const unsigned char*>(buf);
+    ExportHeader H;
+    if (bytes < (int64_t)sizeof(H)) return fail(RTB_EPARSE, "exported scene: truncated header");
+    std::memcpy(&H, p, sizeof(H));
+    if (std::memcmp(H.magic, EXPORT_MAGIC, 8) != 0 || H.total_bytes != (uint64_t)bytes || H.n_objects < 0 || H.n_objects > MAX_OBJECTS)
+        return fail(RTB_EPARSE, "exported scene: bad magic, size or object count");
+    rtb_scene* sc = new rtb_scene();
+    sc->device = device;
+    sc->hs.cam_pos = get3(H.cam_pos);
+    sc->hs.cam_dir = get3(H.cam_dir);
+    sc->hs.light = H.light;
+    size_t off = sizeof(H);
+    auto need = [&](size_t n) { return off + n <= (size_t)bytes; };
+    for (int i = 0; i < H.n_objects; ++i) {
+        ExportObject E;
+        if (!need(sizeof(E))) { delete sc; return fail(RTB_EPARSE, "exported scene: truncated object table"); }
+        std::memcpy(&E, p + off, sizeof(E)); off += sizeof(E);
+        if (E.n_vertices > (1ull << 31) || E.n_indices > (1ull << 32) || E.n_cum > (1ull << 31) ||
+            !need(E.n_vertices * 24 + E.n_indices * 4 + E.n_cum * 8)) { delete sc; return fail(RTB_EPARSE, "exported scene: truncated mesh data"); }
+        HostObject o;
+        o.emitted = get3(E.emitted); o.k = get3(E.k); o.color_d = get3(E.color_d); o.color_s = get3(E.color_s); o.pos = get3(E.pos); o.n = get3(E.n);
+        o.bb_min = get3(E.bb_min); o.bb_max = get3(E.bb_max);
+        o.phong_kd = E.phong_kd; o.phong_ks = E.phong_ks; o.r = E.r; o.surface_area = E.surface_area;
+        o.brdf = E.brdf; o.phong_power = E.phong_power; o.geom = E.geom;
+        o.vertices.resize((size_t)E.n_vertices);
+        for (D3& v : o.vertices) { double t[3]; std::memcpy(t, p + off, sizeof(t)); off += sizeof(t); v = D3{t[0], t[1], t[2]}; }
+        o.indices.resize((size_t)E.n_indices);
+        if (E.n_indices) { std::memcpy(o.indices.data(), p + off, (size_t)E.n_indices * 4); off += (size_t)E.n_indices * 4; }
+        o.cumulative_area.resize((size_t)E.n_cum);
+        if (E.n_cum) { std::memcpy(o.cumulative_area.data(), p + off, (size_t)E.n_cum * 8); off += (size_t)E.n_cum * 8; }
+        sc->hs.objects.push_back(std::move(o));
+    }
+    off = align_up(off, 16);
+    LbvhImport imp{};
+    imp.n_tris = H.n_tris;
+    LbvhResult& M = imp.meta;
+    M.n_nodes = H.n_nodes; M.n_leaves = H.n_leaves; M.root = H.root; M.depth = H.depth; M.n_nodes4 = H.n_nodes4; M.root4 = H.root4;
+    for (int k = 0; k < 3; ++k) { M.qmin[k] = H.qmin[k]; M.qstep[k] = H.qstep[k]; M.bmin[k] = H.bmin[k]; M.bmax[k] = H.bmax[k]; }
+    if (H.n_tris > 0) {
+        if (H.n_nodes < 0 || H.n_nodes4 < 0 || !need(lbvh_bytes(M, H.n_tris))) { delete sc; return fail(RTB_EPARSE, "exported scene: truncated LBVH tables"); }
+        imp.nodes = reinterpret_cast<const float4*>(p + off); off += (size_t)M.n_nodes * 4 * sizeof(float4);
+        imp.qnodes = reinterpret_cast<const uint4*>(p + off); off += (size_t)M.n_nodes * 2 * sizeof(uint4);
+        imp.qnodes4 = reinterpret_cast<const uint4*>(p + off); off += (size_t)std::max(M.n_nodes4, 1) * 4 * sizeof(uint4);
+        imp.tris = reinterpret_cast<const float4*>(p + off); off += (size_t)H.n_tris * TRI_STRIDE * sizeof(float4);
+        imp.tri_nrm = reinterpret_cast<const float4*>(p + off);
+    }
+    int rc = finish_scene(sc, RTB_OK, std::string(), out, H.n_tris >= 0 ? &imp : nullptr);   // no tables in the blob: build here
+    if (rc == RTB_OK && H.n_tris >= 0) (*out)->info.build_ms = H.build_ms;   // the build happened on the exporting rank
+    return rc;
 }
 
 void rtb_scene_destroy(rtb_scene* scene) { delete scene; }

@@ -130,6 +130,23 @@ class Scene:
         _check(_abi.lib().rtb_scene_create(C.byref(desc), device, C.byref(h)), load=True)
         return cls(h.value, name)
 
+    # ---- scene + BVH as one blob (multi-GPU broadcast) ---------------------------------------------
+    def export(self) -> np.ndarray:
+        """rtb_scene_export: the loaded objects and the device-built LBVH tables as one uint8 array."""
+        n = _abi.lib().rtb_scene_export(self._h, None, 0)
+        _check(int(n))
+        buf = np.empty(int(n), dtype=np.uint8)
+        _check(int(_abi.lib().rtb_scene_export(self._h, buf.ctypes.data_as(C.c_void_p), buf.size)))
+        return buf
+
+    @classmethod
+    def from_export(cls, blob, device: int = 0, name: str = "") -> "Scene":
+        """rtb_scene_import: a scene handle on `device` from another handle's export — no parsing, no BVH build."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        h = C.c_void_p()
+        _check(_abi.lib().rtb_scene_import(blob.ctypes.data_as(C.c_void_p), blob.size, device, C.byref(h)), load=True)
+        return cls(h.value, name)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             _abi.lib().rtb_scene_destroy(self._h)

@@ -8,6 +8,7 @@ kernel (``rtb_untile_device``) — or numpy on the CPU — puts them into scan-l
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -57,6 +58,30 @@ def gather_frame_cpu(local_shard: np.ndarray, width: int, height: int, group=Non
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
     return untile_numpy(torch.stack(parts).numpy(), width, height, world)
+
+
+def broadcast_scene(path: str | None, assets_dir: str | None = None, *, device: int, src: int = 0, group=None) -> Scene:
+    """The one-time scene + BVH broadcast of a multi-GPU job: rank `src` loads the TOML / OBJ files and builds the LBVH on its
+    GPU, exports both (rtb_scene_export) and broadcasts the blob (NCCL on CUDA tensors; gloo works on CPU tensors for handles
+    with device = -1); every other rank imports it (rtb_scene_import) — no parsing, no BVH build, bit-identical tables."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    cuda = device >= 0 and dist.get_backend(group) == "nccl"
+    tdev = torch.device("cuda", device) if cuda else torch.device("cpu")
+    scene = None
+    size = torch.zeros(1, dtype=torch.int64, device=tdev)
+    if rank == src:
+        scene = Scene.from_toml(path, assets_dir, device)
+        blob = torch.from_numpy(scene.export())      # (a host-only handle exports the objects alone: importers build their own LBVH)
+        size[0] = blob.numel()
+    dist.broadcast(size, src, group=group)
+    payload = blob.to(tdev) if rank == src else torch.empty(int(size.item()), dtype=torch.uint8, device=tdev)
+    dist.broadcast(payload, src, group=group)
+    if rank != src:
+        scene = Scene.from_export(payload.cpu().numpy(), device, name=os.path.splitext(os.path.basename(path))[0] if path else "")
+    return scene
 
 
 def render_sharded(scene: Scene, width: int, height: int, spp: int, *, seed: int = 0, use_mis: bool = False,

@@ -444,3 +444,26 @@ def test_every_mode_with_tiny_pools(monkeypatch):
         monkeypatch.delenv(k, raising=False)
     monkeypatch.setenv("RTB_KEEP", "1")       # (monkeypatch restores os.environ after the script's own changes)
     runpy.run_path(os.path.join(ROOT, "tools", "gpu_sanitize.py"), run_name="__main__")
+
+
+def test_imported_scene_is_bit_identical(rtb, gpu_scene):
+    # the scene + BVH broadcast of a multi-GPU job (sharding.broadcast_scene): a handle imported from another handle's export
+    # holds the same LBVH tables byte for byte, so traversal results are IDENTICAL (not merely close) and no build runs
+    a = gpu_scene("flying_unicorn")
+    blob = a.export()
+    b = rtb.Scene.from_export(blob, device=0)
+    assert (b.info.bvh_nodes, b.info.bvh_leaves, b.info.bvh_depth, b.info.n_triangles) == (a.info.bvh_nodes, a.info.bvh_leaves, a.info.bvh_depth, 37380)
+    assert np.array_equal(b.export(), blob)                          # export(import(x)) == x
+    rng = np.random.default_rng(2)
+    n = 100_000
+    lo, hi = np.array(a.info.bvh_min), np.array(a.info.bvh_max)
+    org = (lo + (hi - lo) * (rng.random((n, 3)) * 1.4 - 0.2)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    ra, rb = a.trace_rays(org, d), b.trace_rays(org, d)
+    assert all(np.array_equal(ra[k], rb[k]) for k in ("obj", "tri", "t")) and (ra["tri"] >= 0).mean() > 0.05
+    assert np.abs(a.render(160, 120, 16, seed=3).astype(int) - b.render(160, 120, 16, seed=3).astype(int)).max() <= 1
+    oa, ob = (s.render(96, 72, 8, seed=3, accel=rtb.ACCEL_OCTREE_REFERENCE).astype(int) for s in (a, b))
+    assert np.abs(oa - ob).max() <= 1                                  # the octrees are rebuilt from the shipped f64 vertices
+    c = rtb.Scene.from_export(rtb.Scene.from_toml(scene_path("cubes"), device=-1).export(), device=0)   # objects only: the importer builds
+    assert c.info.bvh_nodes > 0 and np.abs(c.render(64, 48, 8, seed=1).astype(int) - gpu_scene("cubes").render(64, 48, 8, seed=1).astype(int)).max() <= 1

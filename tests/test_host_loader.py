@@ -232,3 +232,25 @@ def test_reference_octree_build_matches_oracle(rtb, oracle_scene, name):
     assert seen == (2 if name == "cubes" else 1)
     if name == "flying_unicorn":
         assert mine == {"nodes": 47183, "parents": 9540, "leaves": 37643, "tri_refs": 187766}
+
+
+def test_scene_export_import_round_trip(rtb):
+    # rtb_scene_export / rtb_scene_import (the multi-GPU scene broadcast), host part: every object field, every triangle and
+    # the reference-octree census survive the blob; damaged blobs are refused with RTB_EPARSE
+    a = rtb.Scene.from_toml(scene_path("flying_unicorn"), device=-1)
+    blob = a.export()
+    b = rtb.Scene.from_export(blob, device=-1)
+    assert b.info.n_objects == a.info.n_objects == 9 and b.info.n_triangles == a.info.n_triangles == 37380
+    assert b.light_source == a.light_source and list(b.info.camera_dir) == list(a.info.camera_dir)
+    for i in range(a.info.n_objects):
+        assert a.object(i) == b.object(i)
+    assert np.array_equal(a.triangles(), b.triangles())
+    assert a.octree_stats(6) == b.octree_stats(6)
+    for bad in (blob[:100], blob[:-8], np.concatenate([blob, np.zeros(4, np.uint8)])):
+        with pytest.raises(rtb.LoadTomlError) as e:
+            rtb.Scene.from_export(bad, device=-1)
+        assert e.value.kind == "Parse"
+    broken = blob.copy()
+    broken[0] ^= 0xFF
+    with pytest.raises(rtb.LoadTomlError):
+        rtb.Scene.from_export(broken, device=-1)

@@ -68,3 +68,38 @@ def test_gather_frame_gloo(world, w, h):
         p.join(120)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world))
+
+
+def _bcast_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import raytracer_server_b200  # noqa: F401
+    from raytracer_server_b200 import sharding as S
+
+    # only rank 0 touches the files; host-only handles (device = -1) ship the objects, a GPU rank would ship its LBVH too
+    path = os.path.join(root, "tests", "golden", "scenes", "cubes.toml")
+    sc = S.broadcast_scene(path if rank == 0 else None, device=-1, src=0)
+    ret[rank] = (sc.info.n_objects, sc.info.n_triangles, sc.light_source, sc.object(6)["bb_min"], sc.octree_stats(6)["tri_refs"],
+                 float(sc.triangles().sum()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_broadcast_scene_gloo():
+    # the scene (+ BVH) broadcast of a multi-GPU job, host side: rank 0 loads, everyone else imports the blob
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret[0] == ret[1] and ret[0][:3] == (9, 24, 8) and ret[0][4] == 44
