@@ -637,7 +637,10 @@ void launch_binning(RenderContext* c, const RenderArgs& a, int cur) {
 
 void fill_args(const rtb_scene* sc, const rtb_params* p, RenderContext* c, RenderArgs& a) {
     std::memset(&a, 0, sizeof(a));
-    a.S = sc->view;   // (callers asking for RTB_ACCEL_OCTREE_REFERENCE have run ensure_octrees first: need_accel)
+    {   // (callers asking for RTB_ACCEL_OCTREE_REFERENCE have run ensure_octrees first: need_accel; another thread may be inside it now)
+        std::lock_guard<std::mutex> lk(const_cast<rtb_scene*>(sc)->mu);
+        a.S = sc->view;
+    }
     a.cam = make_camera(sc->fs.cam_pos, sc->fs.cam_dir, p->width, p->height);
     a.width = p->width;
     a.height = p->height;
