@@ -1116,6 +1116,7 @@ int64_t rtb_scene_export(rtb_scene* scene, void* buf, int64_t cap) {
         if (!o.indices.empty()) { std::memcpy(p + off, o.indices.data(), o.indices.size() * sizeof(uint32_t)); off += o.indices.size() * sizeof(uint32_t); }
         if (!o.cumulative_area.empty()) { std::memcpy(p + off, o.cumulative_area.data(), o.cumulative_area.size() * sizeof(double)); off += o.cumulative_area.size() * sizeof(double); }
     }
+    if (off < lbvh_off) std::memset(p + off, 0, lbvh_off - off);   // alignment gap: the blob is a pure function of the scene
     if (n_tris) {
         CU_TRY(cudaSetDevice(scene->device));
         off = lbvh_off;
