@@ -78,7 +78,7 @@ struct RenderContext {
     size_t probe_cap = 0;
     volatile unsigned long long* h_state = nullptr;   // mapped pinned {iteration, live paths} (graph mode)
     unsigned long long* d_state = nullptr;
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one iteration (4 kernels) for cur = 0 / 1 ...
+    cudaGraphExec_t graph_exec[4] = {nullptr, nullptr, nullptr, nullptr};   // one iteration (4 kernels) for cur = 0 / 1; [2], [3]: the same with the inline-tail k_shade ...
     std::vector<unsigned char> graph_args;                 // ... captured for exactly these kernel arguments
     int grid_shade_nomesh = 0;   // grid of the mesh-less k_shade instantiation (160-thread CTAs)
     int trav_minb = 4;   // CTAs per SM the launched k_traverse instantiation was compiled for (RTB_TRAV_MINB = 4 | 5 | 6)
@@ -484,6 +484,10 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         CU_TRY(cudaFuncSetAttribute(k_shade<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CU_TRY(cudaFuncSetAttribute(k_shade<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CU_TRY(cudaFuncSetAttribute(k_generate<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        const int smem_tail = (int)shared_scene_bytes(MAX_OBJECTS, MAX_OBJECTS, SHADE_THREADS);
+        CU_TRY(cudaFuncSetAttribute(k_shade<0, 0, 0, true, SHADE_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tail));
+        CU_TRY(cudaFuncSetAttribute(k_shade<1, 0, 0, true, SHADE_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tail));
+        CU_TRY(cudaFuncSetAttribute(k_shade<2, 0, 0, true, SHADE_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tail));
         int b = 0;
         if (const char* e = getenv("RTB_TRAV_MINB")) c->trav_minb = atoi(e) == 5 ? 5 : (atoi(e) == 6 ? 6 : 4);
         if (c->trav_minb == 5) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 5>, WF_THREADS, smem_stack));
@@ -721,8 +725,21 @@ static bool shade_is_nomesh(int mode, const RenderArgs& a) {
     return a.S.n_tris == 0 && mode != 0 && a.S.n_planes == 5 && a.S.n_prims - a.S.n_planes == 3 && !getenv("RTB_NO_SMALL_TABLE") &&
            !getenv("RTB_GENERIC_TABLE");
 }
-static void launch_shade(int mode, int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur) {
+// paths left below which a run switches to the inline-tail k_shade (0 = never); RTB_INLINE_TAIL overrides
+uint32_t inline_tail_below() {   // read per run: tests and A/B tools flip it inside one process
+    const char* e = getenv("RTB_INLINE_TAIL");
+    return e ? (uint32_t)std::max(0, atoi(e)) : (2u << 20);   // measured: gains saturate between 1 Mi and 4 Mi paths
+}
+
+static void launch_shade(int mode, int n_planes, int n_spheres, int grid, size_t smem, cudaStream_t st, const RenderArgs& a, int cur, bool inline_tail = false) {
 #define RTB_SHADE(M, P, S) k_shade<M, P, S><<<grid, SHADE_THREADS, smem, st>>>(a, cur)
+    if (inline_tail) {   // the tail of a run: k_shade traverses the LBVH itself (generic analytic table; + the traversal stack in shared memory)
+        const size_t smem_t = shared_scene_bytes(a.S.n_prims, a.S.n_objects, SHADE_THREADS);
+        if (mode == 1) k_shade<1, 0, 0, true, SHADE_THREADS, true><<<grid, SHADE_THREADS, smem_t, st>>>(a, cur);
+        else if (mode == 2) k_shade<2, 0, 0, true, SHADE_THREADS, true><<<grid, SHADE_THREADS, smem_t, st>>>(a, cur);
+        else k_shade<0, 0, 0, true, SHADE_THREADS, true><<<grid, SHADE_THREADS, smem_t, st>>>(a, cur);
+        return;
+    }
     if (shade_is_nomesh(mode, a)) {
         // cornell_box: analytic primitives only
         if (mode == 1) k_shade<1, 5, 3, false, SHADE_THREADS_NOMESH><<<grid, SHADE_THREADS_NOMESH, smem, st>>>(a, cur);
@@ -778,6 +795,10 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     const bool nomesh = shade_is_nomesh(shade_mode, a);
     const int grid_shade = nomesh ? c->grid_shade_nomesh : c->grid_shade;
     a.shade_warps = (uint32_t)grid_shade * (uint32_t)((nomesh ? SHADE_THREADS_NOMESH : SHADE_THREADS) / 32);
+    // the inline tail: once at most `tail_below` paths are left, k_shade traverses the LBVH itself and the run ends in one launch
+    // (the LBVH only: the reference's octree search and the counting build keep the queued form)
+    const uint32_t tail_below = (a.S.n_tris > 0 && !nomesh && !count_work && a.accel == RTB_ACCEL_LBVH) ? inline_tail_below() : 0u;
+    bool tail_mode = false;
     const bool use_graph = !count_work && a.P <= (1u << 21) && !getenv("RTB_NO_GRAPH");
     if (use_graph && !done) {
         RenderArgs ag = a;
@@ -786,20 +807,21 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         c->h_state[0] = 0;
         c->h_state[1] = 1;
         cudaError_t ge = cudaSuccess;
-        const bool cached = c->graph_exec[0] && c->graph_args.size() == sizeof(RenderArgs) &&
+        const bool cached = c->graph_exec[0] && (!tail_below || c->graph_exec[2]) && c->graph_args.size() == sizeof(RenderArgs) &&
                             std::memcmp(c->graph_args.data(), &ag, sizeof(RenderArgs)) == 0;
         if (!cached) {   // progressive passes re-use the graphs: the sample range lives in the control block, not in the arguments
             for (auto& e : c->graph_exec) if (e) { cudaGraphExecDestroy(e); e = nullptr; }
-            for (int k = 0; k < 2 && ge == cudaSuccess; ++k) {
+            for (int k = 0; k < (tail_below ? 4 : 2) && ge == cudaSuccess; ++k) {   // [0], [1]: the queued form; [2], [3]: the inline tail
                 cudaGraph_t g = nullptr;
                 ge = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
                 if (ge != cudaSuccess) break;
-                k_prepare<<<1, 1, 0, c->stream>>>(ag, k);
-                const RenderArgs agk = with_cur(ag, k);   // queue pointers of this parity, resolved here
-                launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, agk, k);
-                launch_binning(c, agk, k);
-                launch_traverse(c, agk, k, false, smem_stack);
-                launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, agk, k);
+                const int par = k & 1;
+                k_prepare<<<1, 1, 0, c->stream>>>(ag, par);
+                const RenderArgs agk = with_cur(ag, par);   // queue pointers of this parity, resolved here
+                launch_generate(a.S.n_planes, a.S.n_prims - a.S.n_planes, c->grid_gen, smem_tab, c->stream, agk, par);
+                launch_binning(c, agk, par);
+                launch_traverse(c, agk, par, false, smem_stack);
+                launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, agk, par, k >= 2);
                 ge = cudaStreamEndCapture(c->stream, &g);
                 if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->graph_exec[k], g, 0);
                 if (g) cudaGraphDestroy(g);
@@ -818,13 +840,14 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         const uint64_t run_ahead = 6;
         while (!done) {
             if (cancel && *cancel) { cancelled = true; break; }
-            ge = cudaGraphLaunch(exec[cur], c->stream);
+            ge = cudaGraphLaunch(exec[cur + (tail_mode ? 2 : 0)], c->stream);
             if (ge != cudaSuccess) break;
             launches += a.bin_bits > 0 ? 7 : 4;
             ++it;
             cur ^= 1;
             for (;;) {   // {iteration, live paths} as published by the newest k_prepare that has run
                 const unsigned long long seen = c->h_state[0];
+                if (tail_below && seen >= 1 && c->h_state[1] <= tail_below && c->h_state[0] == seen) tail_mode = true;
                 if (seen >= 1 && c->h_state[1] == 0 && c->h_state[0] == seen) { done = true; break; }
                 if (it - seen < run_ahead) break;
                 if (cudaStreamQuery(c->stream) == cudaSuccess && c->h_state[0] == seen && it - seen >= run_ahead) {
@@ -835,8 +858,10 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
             }
         }
         cudaError_t se = cudaStreamSynchronize(c->stream);
-        if (ge != cudaSuccess || se != cudaSuccess)
+        if (ge != cudaSuccess || se != cudaSuccess) {
+            cudaGetLastError();   // do not leave the error for the next call to trip over
             return fail(RTB_ECUDA, std::string("graph launch: ") + cudaGetErrorString(ge != cudaSuccess ? ge : se));
+        }
         done = true;
     }
     int outstanding = 0;
@@ -857,7 +882,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         CU_TRY(cudaEventRecord(ev[0], c->stream));
         launch_traverse(c, ac, cur, count_work, smem_stack);
         CU_TRY(cudaEventRecord(ev[1], c->stream));
-        launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, ac, cur);
+        launch_shade(shade_mode, a.S.n_planes, a.S.n_prims - a.S.n_planes, grid_shade, smem_tab, c->stream, ac, cur, tail_mode);
         CU_TRY(cudaEventRecord(ev[2], c->stream));
         ++ext_iters;
         launches += a.bin_bits > 0 ? 7 : 4;
@@ -875,6 +900,7 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
             if (q == cudaErrorNotReady) break;
             if (q != cudaSuccess) return fail(RTB_ECUDA, std::string("wavefront loop: ") + cudaGetErrorString(q));
             if (c->h_active[s] == 0) done = true;
+            else if (tail_below && c->h_active[s] <= tail_below) tail_mode = true;
             ++oldest;
             --outstanding;
         }

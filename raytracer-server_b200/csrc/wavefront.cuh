@@ -654,7 +654,11 @@ __device__ __forceinline__ uint32_t seg_slot(uint32_t base, uint32_t k) { return
 // light, no probe items; 1 = live NEE estimator, 2 = the dead "MIS" branch.  MODE 0, the general instantiation, keeps
 // every branch at run time (both estimators, Phong, mesh lights, rtb_sample_radiance probes).
 constexpr int SHADE_THREADS_NOMESH = 160;   // the mesh-less instantiation needs 96 registers: 4 CTAs of 160 threads = 20 warps per SM
-template <int MODE, int NP = 0, int NS = 0, bool MESH = true, int THREADS = SHADE_THREADS>
+// INLINE = true (the TAIL of a run, launched by the host once few paths are left): a ray that needs the LBVH is traversed right
+// here (bvh_traverse, intersect.cuh) instead of being queued for k_traverse, so every remaining path runs to its end inside ONE
+// launch — the ~100 iterations in which the last long paths used to die out a few hundred at a time (each four launches that
+// hardly fill an SM) collapse into one.  SIMD utilisation of the inline traversal is poor, but the tail holds < 0.1 % of the work.
+template <int MODE, int NP = 0, int NS = 0, bool MESH = true, int THREADS = SHADE_THREADS, bool INLINE = false>
 __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_MINB : 640 / THREADS) k_shade(const __grid_constant__ RenderArgs a, int c) {
     constexpr bool FAST = MODE != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -663,7 +667,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
     const uint32_t head = C->ext_head(c), tail = C->ext_tail(c);
     const uint32_t count = head + (a.Pcap - tail);
     if (blockIdx.x * (THREADS / 32) * SHADE_CHUNK >= count) return;   // CTA beyond the static region of a small launch
-    const SharedScene sh = stage_scene(a.S, smem_raw, false);
+    const SharedScene sh = stage_scene(a.S, smem_raw, INLINE);   // INLINE: + the traversal stack
     const unsigned lane = threadIdx.x & 31;
     const unsigned below = (1u << lane) - 1u;
     const PathQueue &Q = a.qin, &N = a.qout;
@@ -683,6 +687,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
     uint32_t* const ctr_back = &C->ext_tail(1 - c);
     uint32_t* const ctr_sh = &C->sh_head(1 - c);
     uint32_t n_ext = 0, n_ext_bvh = 0, n_sh = 0, n_sh_bvh = 0, n_queued = 0;
+    uint32_t n_sh_inline = 0;   // INLINE: shadow / probe rays traversed here (counted as BVH shadow rays, never pending)
     auto slot_of = [&](uint32_t i) { return i < head ? i : tail + (i - head); };
 
     // ---- work fetch (warp-uniform): static first chunk, then chunks from the cursor, reserved one ahead
@@ -701,6 +706,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
     bool cur_valid = false, cont = false, sp_valid = false, sp_nrm = false;
     float2 h2 = make_float2(0.f, __uint_as_float(PC_NONE));
     float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, b4 = o4, tri_n = o4;   // cont: tri_n carries the stale `o` instead
+    float4 ev_keep = o4;   // INLINE: a kept path may sit on a triangle, so the stale `o` / MIS pdf needs its own register
     uint32_t cur_slot = 0, sp_slot = 0;
     // output segments (warp-uniform): front / back class of the other path queue, shadow queue
     uint32_t f_base = 0, f_used = SHADE_SEG, b_base = 0, b_used = SHADE_SEG, s_base = 0, s_used = SHADE_SEG;
@@ -779,7 +785,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                 const uint32_t sample = sdw >> 12, depth = sdw & 0xfffu;
                 const HitGeom hg = hit_geometry(sh, o, d, t, id, tri_n);
                 const DevMaterial& mat = sh.mats[hg.obj];
-                const float3 ovec = (origin & PC_STALE_O) ? (cont ? f3(tri_n) : f3(Q.ov[cur_slot])) : -d;
+                const float3 ovec = (origin & PC_STALE_O) ? (cont ? f3(INLINE ? ev_keep : tri_n) : f3(Q.ov[cur_slot])) : -d;
                 const float3 emitted = f3(mat.emitted);
                 const bool emits = emitted.x != 0.f || emitted.y != 0.f || emitted.z != 0.f;
                 // emission: received_radiance adds emitted(obj0) (src/scene.rs:155); a specular vertex adds
@@ -790,7 +796,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                     // the BRDF sample of the previous (diffuse) vertex reached the sampled light: its emission counts with the
                     // balance weight pdf_brdf / (pdf_brdf + pdf_light), both per solid angle at the previous vertex
                     if (emits && hg.obj == light_obj) {
-                        const float pdf_b = cont ? tri_n.w : Q.ov[cur_slot].w;
+                        const float pdf_b = cont ? (INLINE ? ev_keep.w : tri_n.w) : Q.ov[cur_slot].w;
                         const float pdf_l = a.light_pdf * (t * t) / fmaxf(dot(hg.n, -d), 1e-20f);
                         accum_add(a.accum, acc, beta * emitted * (pdf_b / (pdf_b + pdf_l)));
                     }
@@ -886,7 +892,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                                     if (!light_is_mesh) {
                                         // the light is analytic: it must be the nearest analytic hit and no triangle may lie in front of it
                                         if (ida != PC_NONE && sh.prims[ida].obj == light_obj) {
-                                            if (needs_bvh) {
+                                            if (needs_bvh && INLINE) {
+                                                ++n_sh_inline;
+                                                uint32_t idt = PC_NONE;
+                                                float tt = ta;
+                                                if (!bvh_traverse<true, false>(a.S, sh, hg.pos, i2, hg.pcode, tt, idt, ta + SHADOW_MARGIN, nullptr)) accum_add(a.accum, acc, c2);
+                                            } else if (needs_bvh) {
                                                 pr_push = true;
                                                 pd = make_float4(i2.x, i2.y, i2.z, ta);
                                                 pc = make_float4(c2.x, c2.y, c2.z, __uint_as_float(acc));
@@ -894,6 +905,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                                                 accum_add(a.accum, acc, c2);
                                             }
                                         }
+                                    } else if (needs_bvh && INLINE) {   // mesh light, traversed here: see below
+                                        ++n_sh_inline;
+                                        uint32_t idt = PC_NONE;
+                                        float tt = ta;
+                                        bvh_traverse<false, false>(a.S, sh, hg.pos, i2, hg.pcode, tt, idt, 0.f, nullptr);
+                                        if (idt != PC_NONE && __float_as_int(__ldg(a.S.tris + (size_t)(idt - TRI_BASE) * TRI_STRIDE + 2).w) == light_obj) accum_add(a.accum, acc, c2);
                                     } else if (needs_bvh) {  // mesh light: nearest triangle below the analytic hit must belong to it
                                         pr_push = true;
                                         pd = make_float4(i2.x, i2.y, i2.z, ta);
@@ -938,7 +955,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                         if (MESH) ray_pair_hits_bvh_box(a.S, hg.pos, next_dir, ta, sh_dir, sh_tlim, ext_box, sh_box);
                         else ext_box = sh_box = false;   // no triangles in the scene: no ray ever leaves this kernel for k_traverse
                         if (want_sh && !occ) {
-                            if (sh_box) {
+                            if (sh_box && INLINE) {   // mutually_visible's mesh half, right here
+                                ++n_sh_inline;
+                                uint32_t idt = PC_NONE;
+                                float tt = sh_tlim;
+                                if (!bvh_traverse<true, false>(a.S, sh, hg.pos, sh_dir, hg.pcode, tt, idt, sh_tlim + SHADOW_MARGIN, nullptr)) accum_add(a.accum, acc, sh_contrib);
+                            } else if (sh_box) {
                                 sh_push = true;
                                 ++n_sh_bvh;
                                 so = make_float4(hg.pos.x, hg.pos.y, hg.pos.z, __uint_as_float(hg.pcode));
@@ -950,10 +972,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
                         }
                         if (ext_push) {
                             ext_front = ext_box;
+                            n_ext_bvh += ext_front ? 1u : 0u;
+                            if (INLINE && ext_front) {   // Mesh::intersect for the extension ray, right here: the hit is final afterwards
+                                bvh_traverse<false, false>(a.S, sh, hg.pos, next_dir, hg.pcode, ta, ida, 0.f, nullptr);
+                                ext_front = false;
+                            }
                             ed = make_float4(next_dir.x, next_dir.y, next_dir.z, __uint_as_float(acc));
                             eh = make_float2(ta, __uint_as_float(ida));
                             ++n_ext;
-                            n_ext_bvh += ext_front ? 1u : 0u;
                         }
                     }
                 }
@@ -999,7 +1025,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
         cur_valid = keep;
         if (keep) {
             o4 = eo; d4 = ed; b4 = eb; h2 = eh;
-            tri_n = ev;      // stale `o` of a specular vertex (PC_STALE_O in eo.w); analytic hits need no triangle normal
+            if (INLINE) {    // the next hit may be a triangle (traversed above): its normal, and the stale `o` in its own register
+                ev_keep = ev;
+                const uint32_t idk = __float_as_uint(eh.y);
+                if (idk != PC_NONE && idk >= TRI_BASE) tri_n = __ldg(a.S.tri_nrm + (idk - TRI_BASE));
+            } else {
+                tri_n = ev;  // stale `o` of a specular vertex (PC_STALE_O in eo.w); analytic hits need no triangle normal
+            }
             cont = true;
         }
         // ---- the prefetched entry's hit id has arrived by now -> start the dependent triangle-normal fetch
@@ -1034,6 +1066,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
         n_ext_bvh += __shfl_down_sync(0xffffffffu, n_ext_bvh, off);
         n_sh += __shfl_down_sync(0xffffffffu, n_sh, off);
         n_sh_bvh += __shfl_down_sync(0xffffffffu, n_sh_bvh, off);
+        if (INLINE) n_sh_inline += __shfl_down_sync(0xffffffffu, n_sh_inline, off);
         n_queued += __shfl_down_sync(0xffffffffu, n_queued, off);
     }
     if (lane == 0) {
@@ -1042,7 +1075,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
         if (n_ext) atomicAdd(&C->rays_extension, (unsigned long long)n_ext);
         if (n_ext_bvh) atomicAdd(&C->rays_bvh, (unsigned long long)n_ext_bvh);
         if (n_sh) atomicAdd(&C->rays_shadow, (unsigned long long)n_sh);
-        if (n_sh_bvh) atomicAdd(&C->shadow_bvh, (unsigned long long)n_sh_bvh);
+        if (n_sh_bvh + n_sh_inline) atomicAdd(&C->shadow_bvh, (unsigned long long)(n_sh_bvh + n_sh_inline));
     }
 }
 

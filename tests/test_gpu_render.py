@@ -361,7 +361,7 @@ def test_binning_knob_changes_nothing_but_the_order(gpu_scene):
         st = g.stats()
         assert np.abs(f - ref).max() <= 1
         assert all(st[k] == base[k] for k in ("samples", "rays_primary", "rays_extension", "rays_shadow", "rays_bvh", "shadow_bvh"))
-        assert st["kernel_launches"] == base["kernel_launches"] + 3 * st["iterations"]      # k_bin_keys, _scan, _scatter per iteration
+        assert st["kernel_launches"] >= 7 * st["iterations"]      # k_bin_keys, _scan, _scatter on top of the four per iteration
 
 
 def test_streaming_job_in_reference_octree_mode(gpu_scene, rtb, monkeypatch):
@@ -467,3 +467,22 @@ def test_imported_scene_is_bit_identical(rtb, gpu_scene):
     assert np.abs(oa - ob).max() <= 1                                  # the octrees are rebuilt from the shipped f64 vertices
     c = rtb.Scene.from_export(rtb.Scene.from_toml(scene_path("cubes"), device=-1).export(), device=0)   # objects only: the importer builds
     assert c.info.bvh_nodes > 0 and np.abs(c.render(64, 48, 8, seed=1).astype(int) - gpu_scene("cubes").render(64, 48, 8, seed=1).astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("name,use_mis", [("flying_unicorn", False), ("flying_unicorn", True), ("cubes", False)])
+def test_inline_tail_changes_nothing_but_the_iterations(gpu_scene, monkeypatch, name, use_mis):
+    # Once few paths are left (RTB_INLINE_TAIL, default 2 Mi) k_shade traverses the LBVH itself and the run ends in one
+    # launch instead of ~100 nearly empty iterations.  Same rays, same frame; far fewer iterations.
+    g = gpu_scene(name)
+    W, H, spp = 320, 240, 64
+    monkeypatch.setenv("RTB_INLINE_TAIL", "0")
+    ref = g.render(W, H, spp, seed=17, use_mis=use_mis).astype(int)
+    base = g.stats()
+    for tail in ("1000", "2097152"):
+        monkeypatch.setenv("RTB_INLINE_TAIL", tail)
+        f = g.render(W, H, spp, seed=17, use_mis=use_mis).astype(int)
+        st = g.stats()
+        assert np.abs(f - ref).max() <= 1
+        assert all(st[k] == base[k] for k in ("samples", "rays_primary", "rays_extension", "rays_shadow", "rays_bvh", "shadow_bvh"))
+        assert st["iterations"] < base["iterations"]
+    assert st["iterations"] <= 0.5 * base["iterations"]
