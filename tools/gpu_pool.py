@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd())
 import raytracer_server_b200 as R
 g = R.Scene.from_toml("tests/golden/scenes/flying_unicorn.toml")
 w,h,spp=1920,1080,256
-for P in (1<<23, 1<<24, 1<<25):
+for P in (1<<24, 1<<25, 3<<24, 1<<26, 1<<25):
     g.render(w,h,16,pool_paths=P)
     g.render(w,h,spp,seed=1,pool_paths=P)
     st=g.stats()
