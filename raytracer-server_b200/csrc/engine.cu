@@ -525,7 +525,10 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         c->Pcap = cap;
     }
     {
-        const uint32_t cap = SP + seg_room;
+        // 2 x SP: a path that queued a shadow ray may stay in registers (k_shade, `sh_tight`) while the shadow queue holds fewer than SP
+        // entries; from then on it is parked as before, which adds at most one entry (two under the dead-MIS estimator: SP is 2 P
+        // there) per path and iteration
+        const uint32_t cap = 2u * SP + seg_room;
         if (c->SPalloc < cap) {
             cudaFree(c->sbuf);
             c->sbuf = nullptr;

@@ -712,6 +712,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
     uint32_t f_base = 0, f_used = SHADE_SEG, b_base = 0, b_used = SHADE_SEG, s_base = 0, s_used = SHADE_SEG;
     bool f_next = false, b_next = false, s_next = false;
     uint32_t nb = 0;           // lane = class: base of the segment reserved ahead
+    // A path that queued a shadow ray (or a dead-MIS probe) stays in registers like any other as long as the shadow queue has
+    // room: its NEE candidate is resolved by k_traverse on its own (the entry carries contribution and accumulator index).  Once
+    // this warp's shadow segments lie beyond SP entries the old rule applies — such a path is parked — which bounds the queue by
+    // 2 SP (+ the segment slack): before, about one path in three written to the path queue was there only because of its shadow ray.
+    bool sh_tight = false;
 
     for (;;) {
         // (a) lanes without a path take their prefetched entry
@@ -986,7 +991,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
             }
         }
         // ---- where does the path go?  In registers if its next hit is final and it queued no shadow ray.
-        bool keep = ext_push && !ext_front && !sh_push && !pr_push && !park;
+        bool keep = ext_push && !ext_front && !park && (!(sh_push || pr_push) || !sh_tight);
         if (ext_push && !ext_front && __float_as_uint(eh.y) == PC_NONE) {   // left the scene: nothing to shade
             keep = false;
             ext_push = false;
@@ -1021,6 +1026,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == SHADE_THREADS ? RTB_SHADE_
             if (pr_push && slot >= a.SPcap) { atomicAdd(&C->overflow, 1u); pr_push = false; }
             if (pr_push) { SQ.o[slot] = so; SQ.d[slot] = pd; SQ.c[slot] = pc; }
         }
+        if (ms | mp) sh_tight = s_base + SHADE_SEG > a.SP;   // warp-uniform: where this warp's current shadow segment ends
         // ---- next vertex of the same path, straight from registers
         cur_valid = keep;
         if (keep) {

@@ -69,7 +69,8 @@ def test_frame_independent_of_the_path_pool(gpu_scene, use_mis):
         assert st["iterations"] >= st_ref["iterations"]
 
 
-def test_paths_stay_in_registers(gpu_scene):
+def test_paths_stay_in_registers(gpu_scene, monkeypatch):
+    monkeypatch.setenv("RTB_INLINE_TAIL", "0")          # the queued form throughout (the inline tail would traverse in place)
     # cornell_box has no mesh: no ray ever needs k_traverse, so k_shade follows every path from the camera ray to its
     # end without queueing it again (one queue entry per sample, written by k_generate)
     g = gpu_scene("cornell_box")
@@ -80,7 +81,8 @@ def test_paths_stay_in_registers(gpu_scene):
     g2 = gpu_scene("flying_unicorn")
     g2.render(320, 240, 16, seed=4)
     st2 = g2.stats()
-    # a path is queued when its next ray can reach the mesh box (or its shadow ray could): far fewer than one entry per vertex
+    # a path is queued when its next ray can reach the mesh box (a queued shadow ray alone no longer parks it while the shadow
+    # queue has room): far fewer than one entry per vertex
     assert st2["rays_bvh"] - st2["rays_primary"] <= st2["paths_queued"] < 0.35 * st2["rays_extension"]
 
 
