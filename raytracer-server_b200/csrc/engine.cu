@@ -597,12 +597,13 @@ int local_tiles(const rtb_params* p) {
 
 // Path slots in flight.  More slots = fewer, fuller wavefront iterations (measured on flying_unicorn 1080p 256 spp:
 // 8 Mi 497, 16 Mi 528, 32 Mi 542 Msamples/s), but 240 B of queue memory each; default: one eighth of the frame's
-// samples, between 1 Mi and 32 Mi (7.7 GB).
+// samples, between 1 Mi and 32 Mi (7.7 GB); tools/gpu_pool_small.py has the small-frame sweep.
 uint32_t pool_for(uint64_t samples, int pool_paths) {
     uint64_t P;
     if (pool_paths > 0) P = (uint64_t)pool_paths;
     else {
-        uint64_t want = samples / 8;
+        // one eighth of the work keeps the regeneration tail short; a frame of at most 2 Mi samples goes through in ONE wave
+        uint64_t want = std::max<uint64_t>(samples / 8, std::min<uint64_t>(samples, 2ull << 20));
         P = 1ull << 20;
         while (P < want && P < (1ull << 25)) P <<= 1;
     }
@@ -800,9 +801,13 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
     a.shade_warps = (uint32_t)grid_shade * (uint32_t)((nomesh ? SHADE_THREADS_NOMESH : SHADE_THREADS) / 32);
     // the inline tail: once at most `tail_below` paths are left, k_shade traverses the LBVH itself and the run ends in one launch
     // (the LBVH only: the reference's octree search and the counting build keep the queued form)
-    const uint32_t tail_below = (a.S.n_tris > 0 && !nomesh && !count_work && a.accel == RTB_ACCEL_LBVH) ? inline_tail_below() : 0u;
+    // — and never more than a quarter of the pool: a run whose pool is that small would otherwise spend its WHOLE life in the
+    // inline form, which costs 3-4 x per path (measured: 600x450x64 with a 1 Mi pool, 97 vs 26 ms)
+    const uint32_t tail_below = (a.S.n_tris > 0 && !nomesh && !count_work && a.accel == RTB_ACCEL_LBVH) ? std::min(inline_tail_below(), a.P / 4u) : 0u;
     bool tail_mode = false;
-    const bool use_graph = !count_work && a.P <= (1u << 21) && !getenv("RTB_NO_GRAPH");
+    uint32_t graph_max_pool = 1u << 24;
+    if (const char* e = getenv("RTB_GRAPH_MAX_POOL")) graph_max_pool = (uint32_t)std::max(0, atoi(e));   // experiment knob
+    const bool use_graph = !count_work && a.P <= graph_max_pool && !getenv("RTB_NO_GRAPH");
     if (use_graph && !done) {
         RenderArgs ag = a;
         ag.host_state = c->d_state;
