@@ -6,16 +6,18 @@
 //
 // Pipeline (all on the GPU, one stream):
 //   1. triangle bounds + centroid bounds (atomic min/max on order-preserving int keys)
-//   2. 63-bit Morton codes of the centroids (21 bits per axis)
-//   3. radix sort of (code, triangle) pairs                         [cub::DeviceRadixSort]
-//   4. hierarchy over the sorted triangles, one of
-//        PLOC   (default) parallel locally-ordered clustering, Meister & Bittner 2018: mutual nearest
-//               neighbours (by merged box area, +-16 positions in Morton order) merge round by round;
+//   2. hierarchy, one of
+//        binned SAH (default, round 2)  top-down, level-synchronous, 16 bins per axis, leaves of <= 2 triangles: see the
+//               k_sah_* kernels.  Emits nodes and leaf order directly (steps 3-5 below are for the two bottom-up builders).
+//        PLOC   (RTB_BVH=ploc; the default of round 1) parallel locally-ordered clustering, Meister & Bittner 2018: mutual
+//               nearest neighbours (by merged box area, +-16 positions in Morton order) merge round by round;
 //               depth-first leaf positions by walking parent links
-//        Karras (RTB_BVH=lbvh) Karras 2012: one thread per internal node finds its range and split, bottom-up
-//               refit with one atomic arrival counter per node
-//      Measured on flying_unicorn (per 8 Mi-slot iteration of k_traverse): Karras 238 us, PLOC 227 us, host
-//      binned SAH (RTB_BVH=sah, diagnostic only) 203 us.
+//        Karras (RTB_BVH=lbvh; the fallback when a tree comes out deeper than the traversal stack) Karras 2012: one thread per
+//               internal node finds its range and split, bottom-up refit with one atomic arrival counter per node
+//      Measured on flying_unicorn 1920x1080x64 (k_traverse per frame, tools/gpu_bvh_quality.py): Karras 60.6 ms, PLOC 59.4 ms,
+//      binned SAH 54.8 ms (the host prototype with a full sweep instead of bins: 54.3 ms).  Build: 6 ms more than PLOC.
+//   3. 63-bit Morton codes of the centroids (21 bits per axis), radix sort of (code, triangle) pairs   [cub::DeviceRadixSort]
+//   4. PLOC / Karras hierarchy over the sorted triangles
 //   5. collapse subtrees of <= LEAF_MAX triangles into leaves (subtrees are contiguous in leaf order),
 //      compact the surviving nodes                                   [cub::DeviceScan]
 //   6. emit 64-byte nodes {child0 box, child1 box, child refs} and triangles in leaf order
@@ -352,12 +354,205 @@ struct DevBuf {
     T* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
+    void release() { if (p) cudaFree(p); p = nullptr; }
 };
+
+
+// ---------------------------------------------------------------- binned SAH, top-down, level-synchronous (the default hierarchy)
+// Wald 2007 ("On fast construction of SAH-based bounding volume hierarchies"), run breadth-first on the device: every open
+// subtree of a level is an ITEM; per level
+//   k_sah_bin       every triangle adds its box to one of SAH_BINS bins per axis of its item (integer atomics on ordered floats)
+//   k_sah_split     one thread per item: box -> the parent's node, sweep the 3 x 16 bins, leaf or split
+//   (exclusive scan of the split flags: inner-node numbers and next level's item slots, deterministic)
+//   k_sah_children  split items name their inner node and open two items in the next level
+//   k_sah_assign    every triangle moves to its child item (and adds itself to that item's bounds) or records its leaf
+// One read-back per level (the number of splits).  Triangles are never moved: a leaf's first slot in leaf order is known from
+// the counts on the way down (left subtree first), and ONE stable radix sort by that slot at the end gives the leaf order.
+// Every atomic is an integer min / max / add, so the tree is identical from run to run.
+// Traversal time of flying_unicorn against PLOC: -8 % (tools/gpu_bvh_quality.py); a full-sweep SAH on the host gains 1 % more.
+constexpr int SAH_BINS = 16;
+constexpr float SAH_NODE_COST = 1.0f;    // one node visit in units of one triangle test (flat between 0.7 and 2)
+
+struct SahItem {
+    int lo[3], hi[3], clo[3], chi[3];   // triangle / centroid bounds, ordered ints (same layout as Bounds6)
+    int count;
+    int imin, imax;                     // triangle index range: splits a subtree whose centroids all coincide
+    int parent2;                        // inner node that owns this item * 2 + side; -1: the root
+    int first_base;                     // first leaf-order slot of the PARENT's range
+};
+struct SahBin { int lo[3], hi[3], count; };
+struct SahDecision { int kind, axis, split, first; };   // kind 0 leaf, 1 split after bin `split` of `axis`, 2 split at triangle index `split`
+
+__device__ __forceinline__ int sah_bin_of(float c, float clo, float ext) {
+    return min(SAH_BINS - 1, max(0, (int)((c - clo) * ((float)SAH_BINS / ext))));
+}
+__device__ __forceinline__ float sah_area(const int* lo, const int* hi) {
+    float dx = ordered_to_float(hi[0]) - ordered_to_float(lo[0]), dy = ordered_to_float(hi[1]) - ordered_to_float(lo[1]),
+          dz = ordered_to_float(hi[2]) - ordered_to_float(lo[2]);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_sah_root(const Bounds6* gb, int n, SahItem* items, int* item_of) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) item_of[i] = 0;
+    if (i == 0) {
+        SahItem it;
+        for (int k = 0; k < 3; ++k) { it.lo[k] = gb->lo[k]; it.hi[k] = gb->hi[k]; it.clo[k] = gb->clo[k]; it.chi[k] = gb->chi[k]; }
+        it.count = n; it.imin = 0; it.imax = n - 1; it.parent2 = -1; it.first_base = 0;
+        items[0] = it;
+    }
+}
+
+__global__ void k_sah_clear_bins(int nbins, SahBin* bins) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbins) return;
+    SahBin b;
+    for (int k = 0; k < 3; ++k) { b.lo[k] = float_to_ordered(FLT_MAX); b.hi[k] = float_to_ordered(-FLT_MAX); }
+    b.count = 0;
+    bins[i] = b;
+}
+
+__global__ void k_sah_bin(int n, const int* __restrict__ item_of, const SahItem* __restrict__ items, const float4* __restrict__ tlo,
+                          const float4* __restrict__ thi, SahBin* bins) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = item_of[i];
+    if (j < 0) return;
+    const SahItem& it = items[j];
+    if (it.count < 2) return;
+    const float4 lo = tlo[i], hi = thi[i];
+    const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    const int olo[3] = {float_to_ordered(lo.x), float_to_ordered(lo.y), float_to_ordered(lo.z)};
+    const int ohi[3] = {float_to_ordered(hi.x), float_to_ordered(hi.y), float_to_ordered(hi.z)};
+    for (int ax = 0; ax < 3; ++ax) {
+        const float clo = ordered_to_float(it.clo[ax]), ext = ordered_to_float(it.chi[ax]) - clo;
+        if (!(ext > 0.f)) continue;
+        SahBin* b = bins + ((size_t)j * 3 + ax) * SAH_BINS + sah_bin_of(c[ax], clo, ext);
+        for (int k = 0; k < 3; ++k) { atomicMin(&b->lo[k], olo[k]); atomicMax(&b->hi[k], ohi[k]); }
+        atomicAdd(&b->count, 1);
+    }
+}
+
+__global__ void k_sah_split(int m, const SahItem* __restrict__ items, const SahBin* __restrict__ bins, int leaf_max, float node_cost,
+                            float4* __restrict__ nodes, int* root_ref, SahDecision* __restrict__ dec, int* __restrict__ flag) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const SahItem& it = items[j];
+    const int side = it.parent2 & 1, parent = it.parent2 >> 1;
+    const int first = it.first_base + ((it.parent2 >= 0 && side) ? items[j - 1].count : 0);
+    if (it.parent2 >= 0) {   // this subtree's box, into its slot of the parent's node
+        float* o = reinterpret_cast<float*>(nodes + (size_t)parent * 4);
+        o[side * 4 + 0] = ordered_to_float(it.lo[0]); o[side * 4 + 1] = ordered_to_float(it.hi[0]);
+        o[side * 4 + 2] = ordered_to_float(it.lo[1]); o[side * 4 + 3] = ordered_to_float(it.hi[1]);
+        o[8 + side * 2 + 0] = ordered_to_float(it.lo[2]); o[8 + side * 2 + 1] = ordered_to_float(it.hi[2]);
+    }
+    float best = FLT_MAX;
+    int bax = -1, bsplit = -1;
+    if (it.count >= 2) {
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!(ordered_to_float(it.chi[ax]) - ordered_to_float(it.clo[ax]) > 0.f)) continue;
+            const SahBin* b = bins + ((size_t)j * 3 + ax) * SAH_BINS;
+            float ra[SAH_BINS];
+            int alo[3], ahi[3];
+            for (int k = 0; k < 3; ++k) { alo[k] = float_to_ordered(FLT_MAX); ahi[k] = float_to_ordered(-FLT_MAX); }
+            for (int q = SAH_BINS - 1; q > 0; --q) {
+                if (b[q].count) for (int k = 0; k < 3; ++k) { alo[k] = min(alo[k], b[q].lo[k]); ahi[k] = max(ahi[k], b[q].hi[k]); }
+                ra[q] = sah_area(alo, ahi);
+            }
+            for (int k = 0; k < 3; ++k) { alo[k] = float_to_ordered(FLT_MAX); ahi[k] = float_to_ordered(-FLT_MAX); }
+            int lc = 0;
+            for (int q = 0; q < SAH_BINS - 1; ++q) {
+                if (b[q].count) for (int k = 0; k < 3; ++k) { alo[k] = min(alo[k], b[q].lo[k]); ahi[k] = max(ahi[k], b[q].hi[k]); }
+                lc += b[q].count;
+                const int rc = it.count - lc;
+                if (lc == 0 || rc == 0) continue;
+                const float cost = sah_area(alo, ahi) * (float)lc + ra[q + 1] * (float)rc;
+                if (cost < best) { best = cost; bax = ax; bsplit = q; }
+            }
+        }
+    }
+    const float A = sah_area(it.lo, it.hi);
+    SahDecision d;
+    d.first = first;
+    d.axis = bax;
+    d.split = bsplit;
+    if (it.count < 2 || (it.count <= leaf_max && (bax < 0 || node_cost * A + best >= A * (float)it.count)) || (bax < 0 && it.count <= 8)) d.kind = 0;
+    else if (bax < 0) { d.kind = 2; d.split = it.imin + (it.imax - it.imin) / 2; }   // coinciding centroids: halve the index range
+    else d.kind = 1;
+    dec[j] = d;
+    flag[j] = d.kind != 0;
+    if (d.kind == 0) {
+        const int ref = encode_leaf(first, it.count);
+        if (it.parent2 >= 0) reinterpret_cast<int*>(nodes + (size_t)parent * 4 + 3)[side] = ref;
+        else *root_ref = ref;
+    }
+}
+
+__global__ void k_sah_children(int m, const SahItem* __restrict__ items, const SahDecision* __restrict__ dec, const int* __restrict__ flag,
+                               const int* __restrict__ pos, int inner_base, float4* __restrict__ nodes, int* root_ref, SahItem* __restrict__ next) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m || !flag[j]) return;
+    const SahItem& it = items[j];
+    const int inner = inner_base + pos[j];
+    if (it.parent2 >= 0) reinterpret_cast<int*>(nodes + (size_t)(it.parent2 >> 1) * 4 + 3)[it.parent2 & 1] = inner;
+    else *root_ref = inner;
+    reinterpret_cast<int*>(nodes + (size_t)inner * 4 + 3)[2] = 0;
+    reinterpret_cast<int*>(nodes + (size_t)inner * 4 + 3)[3] = 0;
+    for (int s = 0; s < 2; ++s) {
+        SahItem c;
+        for (int k = 0; k < 3; ++k) {
+            c.lo[k] = c.clo[k] = float_to_ordered(FLT_MAX);
+            c.hi[k] = c.chi[k] = float_to_ordered(-FLT_MAX);
+        }
+        c.count = 0; c.imin = 0x7fffffff; c.imax = -1;
+        c.parent2 = inner * 2 + s;
+        c.first_base = dec[j].first;
+        next[2 * pos[j] + s] = c;
+    }
+}
+
+__global__ void k_sah_assign(int n, int* __restrict__ item_of, const SahItem* __restrict__ items, const SahDecision* __restrict__ dec,
+                             const int* __restrict__ pos, const float4* __restrict__ tlo, const float4* __restrict__ thi, SahItem* next,
+                             uint32_t* __restrict__ leaf_slot) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = item_of[i];
+    if (j < 0) return;
+    const SahDecision d = dec[j];
+    if (d.kind == 0) {
+        leaf_slot[i] = (uint32_t)d.first;
+        item_of[i] = -1;
+        return;
+    }
+    const float4 lo = tlo[i], hi = thi[i];
+    const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    int side;
+    if (d.kind == 1) {
+        const float clo = ordered_to_float(items[j].clo[d.axis]), ext = ordered_to_float(items[j].chi[d.axis]) - clo;
+        side = sah_bin_of(c[d.axis], clo, ext) > d.split;
+    } else side = i > d.split;
+    const int nj = 2 * pos[j] + side;
+    SahItem* t = next + nj;
+    atomicMin(&t->lo[0], float_to_ordered(lo.x)); atomicMin(&t->lo[1], float_to_ordered(lo.y)); atomicMin(&t->lo[2], float_to_ordered(lo.z));
+    atomicMax(&t->hi[0], float_to_ordered(hi.x)); atomicMax(&t->hi[1], float_to_ordered(hi.y)); atomicMax(&t->hi[2], float_to_ordered(hi.z));
+    for (int k = 0; k < 3; ++k) { atomicMin(&t->clo[k], float_to_ordered(c[k])); atomicMax(&t->chi[k], float_to_ordered(c[k])); }
+    atomicAdd(&t->count, 1);
+    atomicMin(&t->imin, i);
+    atomicMax(&t->imax, i);
+    item_of[i] = nj;
+}
+
+__global__ void k_iota(int n, uint32_t* v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
 
 }  // namespace
 
-// ---- EXPERIMENT (RTB_BVH=sah): host-side binned-SAH build into the same node format, to measure how much
-// traversal time the LBVH's tree quality costs.  Not the product path.
+// ---- DIAGNOSTIC (RTB_BVH=sah_host): host-side SAH build into the same node format — the prototype the device builder above was
+// checked against (same policy by default: 16 bins, leaves of <= 2 triangles, node cost 1 -> the same node count), with knobs the
+// device builder does not have (RTB_SAH_BINS, RTB_SAH_SWEEP = full sweep below that many triangles, RTB_SAH_LEAF, RTB_SAH_CT).
+// Not the product path.
 namespace {
 struct HB { float lo[3], hi[3]; };
 struct SahBuilder {
@@ -368,41 +563,54 @@ struct SahBuilder {
     static float area(const HB& b) { float dx=b.hi[0]-b.lo[0], dy=b.hi[1]-b.lo[1], dz=b.hi[2]-b.lo[2]; return 2.f*(dx*dy+dy*dz+dz*dx); }
     static void grow(HB& a, const HB& b) { for (int k=0;k<3;++k){ a.lo[k]=fminf(a.lo[k],b.lo[k]); a.hi[k]=fmaxf(a.hi[k],b.hi[k]); } }
     static HB empty() { HB b; for (int k=0;k<3;++k){ b.lo[k]=FLT_MAX; b.hi[k]=-FLT_MAX; } return b; }
+    int nbins = 16, sweep_max = 0, leaf_max = 2;
+    float ct = 1.f;                                  // cost of one node visit in units of one triangle test (= SAH_NODE_COST)
+    std::vector<float> ra_s;                         // sweep scratch
     // returns encoded ref (>=0 node, <0 leaf) and the box
     int build(int first, int count, HB& box) {
         box = empty();
         HB cb = empty();
         for (int i=first;i<first+count;++i){ int t=order[i]; grow(box,tb[t]); for(int k=0;k<3;++k){ cb.lo[k]=fminf(cb.lo[k],cen[3*t+k]); cb.hi[k]=fmaxf(cb.hi[k],cen[3*t+k]); } }
-        if (count <= 4) {
-            bool make_leaf = count <= 2;
-            if (!make_leaf) {  // SAH decides below; fall through to try a split
+        if (count == 1) return ~((first << 3) | 0);
+        float best = FLT_MAX; int bax=-1, bsplit=-1; bool swept = false;
+        if (count <= sweep_max) {                    // full sweep: every split position of every axis
+            swept = true;
+            ra_s.resize(count);
+            for (int ax=0; ax<3; ++ax) {
+                std::sort(order.begin()+first, order.begin()+first+count, [&](int a, int b){ float ca=cen[3*a+ax], cb2=cen[3*b+ax]; return ca<cb2 || (ca==cb2 && a<b); });
+                HB acc=empty();
+                for (int i=count-1;i>0;--i){ grow(acc,tb[order[first+i]]); ra_s[i]=area(acc); }
+                acc=empty();
+                for (int i=0;i<count-1;++i){ grow(acc,tb[order[first+i]]); float cost=area(acc)*(i+1)+ra_s[i+1]*(count-i-1); if(cost<best){best=cost;bax=ax;bsplit=i+1;} }
             }
-            if (make_leaf) return ~((first << 3) | (count - 1));
+            if (bax >= 0 && bax != 2) std::sort(order.begin()+first, order.begin()+first+count, [&](int a, int b){ float ca=cen[3*a+bax], cb2=cen[3*b+bax]; return ca<cb2 || (ca==cb2 && a<b); });
+        } else {
+            const int NB = nbins;
+            for (int ax=0; ax<3; ++ax) {
+                float ext = cb.hi[ax]-cb.lo[ax];
+                if (!(ext > 0.f)) continue;
+                HB bb[64]; int bc[64];
+                for (int b=0;b<NB;++b){ bb[b]=empty(); bc[b]=0; }
+                for (int i=first;i<first+count;++i){ int t=order[i]; int b=(int)((cen[3*t+ax]-cb.lo[ax])/ext*NB); if(b>=NB)b=NB-1; if(b<0)b=0; grow(bb[b],tb[t]); bc[b]++; }
+                float ra[64]; HB acc=empty();
+                for (int b=NB-1;b>0;--b){ grow(acc,bb[b]); ra[b]=area(acc); }
+                acc=empty(); int lc=0; int rc=count;
+                for (int b=0;b<NB-1;++b){ grow(acc,bb[b]); lc+=bc[b]; rc=count-lc; if(lc==0||rc==0) continue; float cost=area(acc)*lc+ra[b+1]*rc; if(cost<best){best=cost;bax=ax;bsplit=b;} }
+            }
         }
-        const int NB = 16;
-        float best = FLT_MAX; int bax=-1, bsplit=-1;
-        for (int ax=0; ax<3; ++ax) {
-            float ext = cb.hi[ax]-cb.lo[ax];
-            if (!(ext > 0.f)) continue;
-            HB bb[NB]; int bc[NB];
-            for (int b=0;b<NB;++b){ bb[b]=empty(); bc[b]=0; }
-            for (int i=first;i<first+count;++i){ int t=order[i]; int b=(int)((cen[3*t+ax]-cb.lo[ax])/ext*NB); if(b>=NB)b=NB-1; if(b<0)b=0; grow(bb[b],tb[t]); bc[b]++; }
-            float ra[NB]; HB acc=empty();
-            for (int b=NB-1;b>0;--b){ grow(acc,bb[b]); ra[b]=area(acc); }
-            acc=empty(); int lc=0; int rc=count;
-            for (int b=0;b<NB-1;++b){ grow(acc,bb[b]); lc+=bc[b]; rc=count-lc; if(lc==0||rc==0) continue; float cost=area(acc)*lc+ra[b+1]*rc; if(cost<best){best=cost;bax=ax;bsplit=b;} }
-        }
-        float leaf_cost = area(box) * count;
-        if (bax < 0 || (count <= 4 && best >= leaf_cost)) {
+        const float leaf_cost = area(box) * count;
+        if (count <= leaf_max && (bax < 0 || ct * area(box) + best >= leaf_cost)) return ~((first << 3) | (count - 1));
+        int mid;
+        if (bax < 0) {
             if (count <= 8) return ~((first << 3) | (count - 1));
-            // degenerate: median split on order
-            int mid = first + count/2; HB lb, rb; int idx=(int)nodes.size()/4; nodes.resize(nodes.size()+4);
-            int l = build(first, mid-first, lb), r = build(mid, first+count-mid, rb);
-            emit(idx, l, r, lb, rb); return idx;
+            mid = first + count/2;                   // degenerate: median split on order
+        } else if (swept) mid = first + bsplit;
+        else {
+            const int NB = nbins;
+            float ext = cb.hi[bax]-cb.lo[bax];
+            mid = (int)(std::partition(order.begin()+first, order.begin()+first+count, [&](int t){ int b=(int)((cen[3*t+bax]-cb.lo[bax])/ext*NB); if(b>=NB)b=NB-1; if(b<0)b=0; return b<=bsplit; }) - order.begin());
+            if (mid==first || mid==first+count) mid = first+count/2;
         }
-        float ext = cb.hi[bax]-cb.lo[bax];
-        int mid = (int)(std::partition(order.begin()+first, order.begin()+first+count, [&](int t){ int b=(int)((cen[3*t+bax]-cb.lo[bax])/ext*NB); if(b>=NB)b=NB-1; if(b<0)b=0; return b<=bsplit; }) - order.begin());
-        if (mid==first || mid==first+count) mid = first+count/2;
         int idx=(int)nodes.size()/4; nodes.resize(nodes.size()+4);
         HB lb, rb;
         int l = build(first, mid-first, lb), r = build(mid, first+count-mid, rb);
@@ -427,6 +635,10 @@ static bool build_sah_host(const float* d_verts, const int32_t* d_tri_obj, int n
     SahBuilder B; B.v=hv.data(); B.n=n; B.tb.resize(n); B.cen.resize((size_t)3*n); B.order.resize(n);
     HB all=SahBuilder::empty();
     for (int i=0;i<n;++i){ HB b=SahBuilder::empty(); for(int k=0;k<3;++k){ for(int q=0;q<3;++q){ float x=hv[(size_t)i*9+3*q+k]; b.lo[k]=fminf(b.lo[k],x); b.hi[k]=fmaxf(b.hi[k],x);} float pad=fmaxf(fabsf(b.lo[k]),fabsf(b.hi[k]))*1e-6f+1e-30f; b.lo[k]-=pad; b.hi[k]+=pad; B.cen[3*i+k]=0.5f*(b.lo[k]+b.hi[k]); } B.tb[i]=b; SahBuilder::grow(all,b); B.order[i]=i; }
+    if (const char* e = getenv("RTB_SAH_BINS")) B.nbins = std::min(64, std::max(2, atoi(e)));
+    if (const char* e = getenv("RTB_SAH_SWEEP")) B.sweep_max = std::max(0, atoi(e));
+    if (const char* e = getenv("RTB_SAH_LEAF")) B.leaf_max = std::min(8, std::max(1, atoi(e)));
+    if (const char* e = getenv("RTB_SAH_CT")) B.ct = (float)atof(e);
     HB rootbox; int root = B.build(0, n, rootbox);
     std::vector<uint32_t> ord(B.order.begin(), B.order.end());
     uint32_t* d_ord=nullptr;
@@ -613,7 +825,8 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
                            bool force_karras) {
     out = LbvhResult();
     if (n <= 0) return true;
-    if (const char* e = getenv("RTB_BVH")) if (!force_karras && std::string(e) == "sah") return build_sah_host(d_verts, d_tri_obj, n, stream, out, err);
+    const std::string mode = getenv("RTB_BVH") ? getenv("RTB_BVH") : "";
+    if (!force_karras && mode == "sah_host") return build_sah_host(d_verts, d_tri_obj, n, stream, out, err);
     const int T = 256;
     const int nb = (n + T - 1) / T;
     const int ni = n - 1;
@@ -645,8 +858,8 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
     LBVH_CHECK(cudaMalloc((void**)&d_tris, (size_t)n * rtb::TRI_STRIDE * sizeof(float4)));
     out.d_tris = d_tris;
     LBVH_CHECK(cudaMalloc((void**)&out.d_tri_nrm, (size_t)n * sizeof(float4)));
-    const char* mode_env = getenv("RTB_BVH");
-    const bool karras = force_karras || (mode_env && std::string(mode_env) == "lbvh");   // default: PLOC on the same Morton order
+    const bool karras = force_karras || mode == "lbvh";
+    const bool sah = !karras && mode != "ploc";   // default: binned SAH, top-down; "ploc" / "lbvh": bottom-up over the Morton order
 
     Bounds6 hb;
     int leaf_max = LEAF_MAX;
@@ -675,6 +888,59 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
                                       nhi.p, out.d_nodes, nullptr);
         out.root = 0;  // Karras: internal node 0 is the root; it is always used here (n > LEAF_MAX) and keeps index 0
         out.n_leaves = out.n_nodes + 1;
+    } else if (sah) {
+        DevBuf<SahItem> items[2];
+        DevBuf<SahBin> bins;
+        DevBuf<SahDecision> dec;
+        DevBuf<int> flag, pos, item_of, root_ref;
+        DevBuf<uint32_t> slot, slot2, ids, order;
+        DevBuf<unsigned char> tmp2;
+        LBVH_CHECK(items[0].alloc(n)); LBVH_CHECK(items[1].alloc(n)); LBVH_CHECK(dec.alloc(n)); LBVH_CHECK(flag.alloc(n)); LBVH_CHECK(pos.alloc(n + 1));
+        LBVH_CHECK(item_of.alloc(n)); LBVH_CHECK(root_ref.alloc(1)); LBVH_CHECK(slot.alloc(n)); LBVH_CHECK(slot2.alloc(n)); LBVH_CHECK(ids.alloc(n));
+        LBVH_CHECK(order.alloc(n));
+        LBVH_CHECK(cudaMalloc((void**)&out.d_nodes, (size_t)n * 4 * sizeof(float4)));   // at most n - 1 inner nodes
+        size_t bins_cap = 0;
+        k_sah_root<<<nb, T, 0, stream>>>(gb.p, n, items[0].p, item_of.p);
+        int m = 1, inner = 0, cur = 0, levels = 0;
+        while (m > 0) {
+            if (++levels > 4096) { err = "SAH build made no progress"; return false; }
+            const size_t nbins = (size_t)m * 3 * SAH_BINS;
+            if (nbins > bins_cap) {
+                LBVH_CHECK(cudaStreamSynchronize(stream));
+                bins.release();
+                bins_cap = std::max(nbins, 2 * bins_cap);
+                LBVH_CHECK(bins.alloc(bins_cap));
+            }
+            const int mb = (m + T - 1) / T;
+            k_sah_clear_bins<<<(int)((nbins + T - 1) / T), T, 0, stream>>>((int)nbins, bins.p);
+            k_sah_bin<<<nb, T, 0, stream>>>(n, item_of.p, items[cur].p, tlo.p, thi.p, bins.p);
+            k_sah_split<<<mb, T, 0, stream>>>(m, items[cur].p, bins.p, leaf_max, SAH_NODE_COST, out.d_nodes, root_ref.p, dec.p, flag.p);
+            LBVH_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, flag.p, pos.p, m, stream));
+            k_sah_children<<<mb, T, 0, stream>>>(m, items[cur].p, dec.p, flag.p, pos.p, inner, out.d_nodes, root_ref.p, items[cur ^ 1].p);
+            k_sah_assign<<<nb, T, 0, stream>>>(n, item_of.p, items[cur].p, dec.p, pos.p, tlo.p, thi.p, items[cur ^ 1].p, slot.p);
+            int tail[2];  // flag[m-1], pos[m-1]
+            LBVH_CHECK(cudaMemcpyAsync(&tail[0], flag.p + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+            LBVH_CHECK(cudaMemcpyAsync(&tail[1], pos.p + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+            LBVH_CHECK(cudaStreamSynchronize(stream));
+            const int splits = tail[0] + tail[1];
+            inner += splits;
+            m = 2 * splits;
+            cur ^= 1;
+        }
+        if (inner > n - 1) { err = "SAH node count mismatch"; return false; }
+        // leaf order = triangles by the first slot of their leaf (stable: index order inside a leaf)
+        size_t sort_bytes = 0;
+        k_iota<<<nb, T, 0, stream>>>(n, ids.p);
+        LBVH_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, slot.p, slot2.p, ids.p, order.p, n, 0, 32, stream));
+        LBVH_CHECK(tmp2.alloc(sort_bytes));
+        LBVH_CHECK(cub::DeviceRadixSort::SortPairs(tmp2.p, sort_bytes, slot.p, slot2.p, ids.p, order.p, n, 0, 32, stream));
+        k_pack_tris<<<nb, T, 0, stream>>>(n, order.p, d_verts, d_tri_obj, d_tris, out.d_tri_nrm);
+        int root = 0;
+        LBVH_CHECK(cudaMemcpyAsync(&root, root_ref.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        LBVH_CHECK(cudaStreamSynchronize(stream));
+        out.root = root;
+        out.n_nodes = inner;
+        out.n_leaves = inner + 1;
     } else {
         // ---- PLOC: cluster arrays ping-pong between (cn0, cl0, ch0, cs0) and (cn1, ...)
         DevBuf<int> cn[2], cs[2], nnb, valid, merge, pv, pm, nsize, leafpos;

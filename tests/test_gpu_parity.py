@@ -472,6 +472,69 @@ def test_wide_table_gives_the_same_hits(rtb, gpu_scene, monkeypatch):
     assert np.abs(f2 - f4).max() <= 1
 
 
+@pytest.mark.gpu
+def test_every_hierarchy_builder_gives_the_same_hits(rtb, gpu_scene, monkeypatch):
+    # RTB_BVH picks the hierarchy over the same triangles: binned SAH (default, top-down on the device), PLOC, Karras, and the
+    # host-side SAH the device builder was checked against.  Nearest hits do not depend on the tree; the SAH tree is the shallowest.
+    g0 = gpu_scene("flying_unicorn")
+    rng = np.random.default_rng(9)
+    n = 100_000
+    lo, hi = np.array(g0.info.bvh_min), np.array(g0.info.bvh_max)
+    org = (lo + (hi - lo) * rng.random((n, 3)) * 1.6 - 0.3 * (hi - lo)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    a = g0.trace_rays(org, d)
+    assert (a["tri"] >= 0).mean() > 0.05
+    f0 = g0.render(160, 120, 16, seed=2).astype(int)
+    info = {"sah": (g0.info.bvh_nodes, g0.info.bvh_depth)}
+    for mode in ("ploc", "lbvh", "sah_host"):
+        monkeypatch.setenv("RTB_BVH", mode)
+        g = rtb.Scene.from_toml(scene_path("flying_unicorn"), device=0)
+        monkeypatch.delenv("RTB_BVH")
+        b = g.trace_rays(org, d)
+        assert np.array_equal(a["obj"], b["obj"]) and np.array_equal(a["t"], b["t"]), mode
+        assert (a["tri"] != b["tri"]).mean() < 1e-4, mode      # exact distance ties on shared edges only
+        assert np.abs(f0 - g.render(160, 120, 16, seed=2).astype(int)).max() <= 1, mode
+        info[mode] = (g.info.bvh_nodes, g.info.bvh_depth)
+    assert info["sah"][1] <= min(info["ploc"][1], info["lbvh"][1])
+    assert abs(info["sah"][0] - info["sah_host"][0]) <= 0.02 * info["sah"][0]    # same policy, same tree up to float rounding of the bins
+    # the build is deterministic: integer atomics and scans only
+    g1 = rtb.Scene.from_toml(scene_path("flying_unicorn"), device=0)
+    e0, e1 = g0.export(), g1.export()
+    e0[152:160] = e1[152:160] = 0            # ExportHeader.build_ms, the one field that is a measurement
+    assert np.array_equal(e0, e1)
+
+
+@pytest.mark.gpu
+def test_sah_builder_splits_coinciding_centroids(rtb):
+    # 40 copies of one triangle (no centroid extent: no bin can separate them -> halved by triangle index until 8 fit a leaf)
+    # next to 200 distinct ones; every builder must still find the same nearest hit
+    rng = np.random.default_rng(4)
+    base = np.array([[0, 0, 0], [4, 0, 0], [0, 4, 0]], dtype=np.float64)
+    tris = [base.copy() for _ in range(40)]
+    for _ in range(200):
+        c = rng.uniform(-20, 20, 3)
+        tris.append(c + rng.normal(size=(3, 3)) * 2.0)
+    tris = np.array(tris)
+    objs = [{"brdf": ("diffuse", (0.7, 0.7, 0.7)), "geometry": ("mesh", tris)},
+            {"emitted": (20, 20, 20), "brdf": ("diffuse", (0, 0, 0)), "geometry": ("sphere", (0, 60, 0), 2.0)}]
+    g = rtb.Scene.from_objects((0, 0, 60), (0, 0, -1), objs)
+    os.environ["RTB_BVH"] = "lbvh"
+    try:
+        k = rtb.Scene.from_objects((0, 0, 60), (0, 0, -1), objs)
+    finally:
+        del os.environ["RTB_BVH"]
+    m = 50_000
+    org = rng.uniform(-30, 30, size=(m, 3)).astype(np.float32)
+    d = rng.normal(size=(m, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    a, b = g.trace_rays(org, d), k.trace_rays(org, d)
+    assert np.array_equal(a["obj"], b["obj"]) and np.array_equal(a["t"], b["t"])
+    # straight down onto the stack of copies: the hit is one of them (the lowest index wins ties inside a leaf, any of the 40 across leaves)
+    hit = g.trace_rays(np.array([[1, 1, 10]], np.float32), np.array([[0, 0, -1]], np.float32))
+    assert hit["obj"][0] == 0 and 0 <= hit["tri"][0] < 40 and abs(hit["t"][0] - 10) < 1e-4
+
+
 # ---------------------------------------------------------------- ACCEL_OCTREE_REFERENCE: the reference's real mesh path
 @pytest.mark.parametrize("name", ["cubes", "flying_unicorn"])
 def test_octree_mode_returns_the_reference_hits(rtb, gpu_scene, oracle_scene, oracle_mod, parity_log, name):
