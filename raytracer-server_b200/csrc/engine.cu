@@ -904,7 +904,9 @@ int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_be
         cur ^= 1;
         while (outstanding > 0) {
             int s = (int)(oldest % RenderContext::RING);
-            cudaError_t q = outstanding >= RenderContext::RING ? cudaEventSynchronize(c->ring_ev[s]) : cudaEventQuery(c->ring_ev[s]);
+            // at most 6 iterations ahead of the newest count the host has seen (like the graph path): the switch to the inline tail and
+            // the end of the run are noticed that much sooner (bench frame: 82 -> 6x iterations)
+            cudaError_t q = outstanding >= 6 ? cudaEventSynchronize(c->ring_ev[s]) : cudaEventQuery(c->ring_ev[s]);
             if (q == cudaErrorNotReady) break;
             if (q != cudaSuccess) return fail(RTB_ECUDA, std::string("wavefront loop: ") + cudaGetErrorString(q));
             if (c->h_active[s] == 0) done = true;
