@@ -47,6 +47,12 @@ namespace {
 
 constexpr int LEAF_MAX = 2;
 
+int depth_limit() {   // levels the traversal stack holds; RTB_BVH_MAX_DEPTH lowers it (test hook)
+    int d = BVH_MAX_DEPTH;
+    if (const char* e = getenv("RTB_BVH_MAX_DEPTH")) d = std::min(BVH_MAX_DEPTH, std::max(1, atoi(e)));
+    return d;
+}
+
 __device__ __forceinline__ int float_to_ordered(float f) {
     int i = __float_as_int(f);
     return i >= 0 ? i : i ^ 0x7fffffff;
@@ -806,8 +812,7 @@ static bool build_lbvh_tables(const float* d_verts, const int32_t* d_tri_obj, in
 // that came out too deep is rebuilt with the Karras hierarchy, and a mesh whose tree still does not fit is refused
 // ("unsupported: ..." -> RTB_EUNSUPPORTED) instead of being traversed with an overflowing stack.
 bool build_lbvh(const float* d_verts, const int32_t* d_tri_obj, int n, cudaStream_t stream, LbvhResult& out, std::string& err) {
-    int max_depth = BVH_MAX_DEPTH;
-    if (const char* e = getenv("RTB_BVH_MAX_DEPTH")) max_depth = std::min(BVH_MAX_DEPTH, std::max(1, atoi(e)));   // test hook
+    const int max_depth = depth_limit();
     if (!build_lbvh_tables(d_verts, d_tri_obj, n, stream, out, err, false)) return false;
     if (out.depth > max_depth) {
         free_lbvh(out);
@@ -845,6 +850,8 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
 
     k_init_bounds<<<1, 1, 0, stream>>>(gb.p);
     k_tri_bounds<<<nb, T, 0, stream>>>(d_verts, n, tlo.p, thi.p, gb.p);
+    const bool karras = force_karras || mode == "lbvh";
+    const bool sah = !karras && mode != "ploc" && n > LEAF_MAX;   // default: binned SAH, top-down; "ploc" / "lbvh": bottom-up over the Morton order
     k_morton<<<nb, T, 0, stream>>>(tlo.p, thi.p, n, gb.p, keys.p, vals.p);
 
     size_t tmp_bytes = 0, scan_bytes = 0;
@@ -852,14 +859,12 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
     LBVH_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, used.p, newidx.p, n, stream));
     DevBuf<unsigned char> tmp;
     LBVH_CHECK(tmp.alloc(tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes));
-    LBVH_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, stream));
+    if (!sah) LBVH_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, stream));   // the SAH builder has no use for the Morton order
 
     float4* d_tris = nullptr;
     LBVH_CHECK(cudaMalloc((void**)&d_tris, (size_t)n * rtb::TRI_STRIDE * sizeof(float4)));
     out.d_tris = d_tris;
     LBVH_CHECK(cudaMalloc((void**)&out.d_tri_nrm, (size_t)n * sizeof(float4)));
-    const bool karras = force_karras || mode == "lbvh";
-    const bool sah = !karras && mode != "ploc";   // default: binned SAH, top-down; "ploc" / "lbvh": bottom-up over the Morton order
 
     Bounds6 hb;
     int leaf_max = LEAF_MAX;
@@ -903,7 +908,10 @@ static bool build_lbvh_f32(const float* d_verts, const int32_t* d_tri_obj, int n
         k_sah_root<<<nb, T, 0, stream>>>(gb.p, n, items[0].p, item_of.p);
         int m = 1, inner = 0, cur = 0, levels = 0;
         while (m > 0) {
-            if (++levels > 4096) { err = "SAH build made no progress"; return false; }
+            if (++levels > depth_limit() + 1) {   // already deeper than the traversal stack holds (16 bins peel at least one exponent
+                free_lbvh(out);                   // step of centroid range per level, so this takes an adversarial mesh): Karras' turn
+                return build_lbvh_f32(d_verts, d_tri_obj, n, stream, out, err, true);
+            }
             const size_t nbins = (size_t)m * 3 * SAH_BINS;
             if (nbins > bins_cap) {
                 LBVH_CHECK(cudaStreamSynchronize(stream));
