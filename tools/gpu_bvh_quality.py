@@ -23,5 +23,5 @@ for mode in sys.argv[1:] or ("", "lbvh", "sah"):
         st = g.stats(); st["wall"] = dt
         if best is None or dt < best["wall"]: best = st
     i = g.info
-    print(f"RTB_BVH={mode or 'ploc (default)'}: load {load*1e3:.0f} ms nodes {i.bvh_nodes} depth {i.bvh_depth} | frame {best['wall']*1e3:.1f} ms traverse {best['extend_ms']:.1f} shade {best['shade_ms']:.1f} -> {best['samples']/best['wall']/1e6:.1f} Msamples/s", flush=True)
+    print(f"RTB_BVH={mode or 'sah (default)'}: load {load*1e3:.0f} ms nodes {i.bvh_nodes} depth {i.bvh_depth} | frame {best['wall']*1e3:.1f} ms traverse {best['extend_ms']:.1f} shade {best['shade_ms']:.1f} -> {best['samples']/best['wall']/1e6:.1f} Msamples/s", flush=True)
     del g
