@@ -173,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -255,6 +255,28 @@ def measure_configs(R, device, full_c4=True):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _stdout_for_json_only():
+    """The contract is ONE JSON line on stdout; libraries do not know that (NCCL prints its version line to fd 1 when the box sets
+    NCCL_DEBUG=VERSION).  Everything written to fd 1 from here on goes to stderr, the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -265,6 +287,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the configs / scaling_reference / weak / c4_full blocks")
     ap.add_argument("--spp", type=int, default=0, help="override spp (debug only; invalidates the bench line)")
     args = ap.parse_args()
+    _stdout_for_json_only()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -547,7 +570,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        _emit(out)
     return 0
 
 
