@@ -74,7 +74,7 @@ struct DevScene {          // passed to kernels by value
     const float* light_cdf;
     const float4* tri_orig; // 3 x float4 per triangle in GLOBAL order: a, b, c (mesh-light sampling)
     // RTB_ACCEL_OCTREE_REFERENCE (octree.cuh): the reference's per-mesh octrees, built lazily on first use (nullptr before)
-    const float4* oct_nodes;   // 4 x float4 per node
+    const float4* oct_nodes;   // 2 x float4 per node (octree.cuh)
     const int32_t* oct_tris;   // leaf triangle references = slots of `tris`
     const int32_t* oct_roots;  // root node per mesh, in object order (-1: empty mesh)
     int32_t n_oct_meshes;

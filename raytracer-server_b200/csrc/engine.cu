@@ -377,16 +377,24 @@ int ensure_octrees(rtb_scene* sc) {
         HostOctree ot;
         build_reference_octree(ob, ot);
         if (ot.nodes.empty()) { roots.push_back(-1); continue; }
-        const int node_base = (int)(nodes.size() / 4), ref_base = (int)refs.size();
+        const int node_base = (int)(nodes.size() / 2), ref_base = (int)refs.size();
         const int first_tri = sc->fs.materials[(size_t)i].first_tri;
         roots.push_back(node_base);
-        for (const HostOctreeNode& n : ot.nodes) {
-            nodes.push_back(make_float4((float)n.mn[0], (float)n.mn[1], (float)n.mn[2], as_f(n.count >= 0 ? ref_base + n.first : 0)));
-            nodes.push_back(make_float4((float)n.mx[0], (float)n.mx[1], (float)n.mx[2], as_f(n.count)));
-            int c[8];
-            for (int k = 0; k < 8; ++k) c[k] = n.child[k] >= 0 ? node_base + n.child[k] : -1;
-            nodes.push_back(make_float4(as_f(c[0]), as_f(c[1]), as_f(c[2]), as_f(c[3])));
-            nodes.push_back(make_float4(as_f(c[4]), as_f(c[5]), as_f(c[6]), as_f(c[7])));
+        // breadth-first renumbering: the children of a parent become neighbours, in octant order (octree.cuh: node record)
+        std::vector<int> bfs{0}, first_child(ot.nodes.size(), 0);
+        for (size_t q = 0; q < bfs.size(); ++q) {
+            const HostOctreeNode& n = ot.nodes[(size_t)bfs[q]];
+            if (n.count >= 0) continue;
+            first_child[(size_t)bfs[q]] = (int)bfs.size();
+            for (int k = 0; k < 8; ++k) if (n.child[k] >= 0) bfs.push_back(n.child[k]);
+        }
+        for (int old_index : bfs) {
+            const HostOctreeNode& n = ot.nodes[(size_t)old_index];
+            int mask = 0;
+            for (int k = 0; k < 8; ++k) if (n.child[k] >= 0) mask |= 1 << k;
+            const bool leaf = n.count >= 0;
+            nodes.push_back(make_float4((float)n.mn[0], (float)n.mn[1], (float)n.mn[2], as_f(leaf ? ref_base + n.first : node_base + first_child[(size_t)old_index])));
+            nodes.push_back(make_float4((float)n.mx[0], (float)n.mx[1], (float)n.mx[2], as_f(leaf ? n.count : -1 - mask)));
         }
         for (int32_t t : ot.tri_refs) refs.push_back(slot_of[(size_t)(first_tri + t)]);
     }
@@ -406,7 +414,7 @@ int ensure_octrees(rtb_scene* sc) {
     sc->view.oct_tris = sc->d_oct_tris;
     sc->view.oct_roots = sc->d_oct_roots;
     sc->view.n_oct_meshes = (int)roots.size();
-    sc->oct_nodes = (int)(nodes.size() / 4);
+    sc->oct_nodes = (int)(nodes.size() / 2);
     sc->oct_refs = (int)refs.size();
     sc->oct_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     sc->info.octree_nodes = sc->oct_nodes;
@@ -445,11 +453,12 @@ void release_context(rtb_scene* sc, RenderContext* c) {
 }
 
 int default_bin_bits();
-// the octree kernel runs one ray per thread through a deeply branching search: there, unlike in k_traverse, neighbouring
-// lanes that walk neighbouring octants in the same order do pay (bench frame at 64 spp: traversal 800 -> 638 ms with 4 cell
-// bits per axis, 601 with 5, for 73 / 125 ms of binning: frame 892 -> 803 ms)
+// the FIRST octree kernel ran one ray per thread through a deeply branching search (5.8 of 32 lanes active): there neighbouring
+// lanes that walk neighbouring octants in the same order did pay (bench frame at 64 spp: traversal 800 -> 638 ms with 4 cell
+// bits per axis, 601 with 5, for 73 / 125 ms of binning: frame 892 -> 803 ms).  The persistent, stepwise kernel that replaced it
+// does not need the help: 496 ms unbinned, 554 ms with 4 bits.  Off by default; rtb_params.tuning[3] still selects it.
 #ifndef RTB_OCTREE_BIN_BITS
-#define RTB_OCTREE_BIN_BITS 4
+#define RTB_OCTREE_BIN_BITS 0
 #endif
 constexpr int OCTREE_BIN_BITS = RTB_OCTREE_BIN_BITS;
 // cell bits per axis of the coherence binning this request asks for (0 = off):
@@ -626,8 +635,10 @@ int default_bin_bits() {
 // every mesh query of one iteration: the LBVH kernel (the product's fast path) or the reference's octrees
 void launch_traverse(RenderContext* c, const RenderArgs& a, int cur, bool count_work, size_t smem_stack) {
     if (a.accel == RTB_ACCEL_OCTREE_REFERENCE) {
-        if (count_work) k_traverse_octree<true><<<c->grid_bin, WF_THREADS, 0, c->stream>>>(a, cur);
-        else k_traverse_octree<false><<<c->grid_bin, WF_THREADS, 0, c->stream>>>(a, cur);
+        // persistent like k_traverse (same grid, same work cursor); shared memory = the per-thread stack of parent nodes
+        const size_t smem_oct = (size_t)OCT_MAX_DEPTH * WF_THREADS * sizeof(int2);
+        if (count_work) k_traverse_octree<true><<<c->grid_ext_count, WF_THREADS, smem_oct, c->stream>>>(a, cur);
+        else k_traverse_octree<false><<<c->grid_ext, WF_THREADS, smem_oct, c->stream>>>(a, cur);
     } else if (count_work && a.S.wide) k_traverse<true, 4, true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
     else if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
     else if (a.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);

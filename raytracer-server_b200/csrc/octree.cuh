@@ -11,9 +11,13 @@
 // so the triangle found can be farther away than another one in a later octant (~30 % of the mesh-origin
 // secondary rays on flying_unicorn), and Scene::trace_ray (src/scene.rs:272-289) then compares THAT hit with the other
 // objects.  This file reproduces exactly that in fp32, over the octree octree_host.cpp built in f64.
-// Node record (64 B, 4 x float4): min.xyz | first   max.xyz | count (-1: parent)   children[0..3]   children[4..7]
-// (int bits; child = node index or -1).  Leaf triangles are references into the LBVH's triangle table (leaf order), so
-// hit ids, self-intersection handling and shading are shared with the LBVH path.
+// Node record (32 B, 2 x float4; int bits in .w):   min.xyz | leaf: first reference, parent: index of its first child
+//                                                   max.xyz | leaf: count >= 0,       parent: -1 - mask
+// The children of a parent lie next to each other in octant order (engine.cu renumbers the host tree breadth-first), and bit i
+// of `mask` says whether octant i has one: child i = first child + popcount(mask below bit i).  A search therefore carries
+// (first child, mask) of the parent it is in and loads ONE record per child test — the first layout (64 B, eight explicit
+// child indices) cost a second, dependent load per test.  Leaf triangles are references into the LBVH's triangle table (leaf
+// order), so hit ids, self-intersection handling and shading are shared with the LBVH path.
 #pragma once
 
 #include "intersect.cuh"
@@ -77,17 +81,9 @@ __device__ __forceinline__ bool oct_leaf(const DevScene& S, int first, int count
     return best_id != PC_NONE;
 }
 
-// Octree::intersect for ONE mesh (root node index `root`): true + (t, id) of the hit the reference would return
-__device__ __forceinline__ bool oct_intersect(const DevScene& S, int root, float3 o, float3 d, float3 inv, uint32_t origin, float& t_out, uint32_t& id_out,
-                                              uint32_t* work) {
-    const float4* N = S.oct_nodes;
-    const float4 rmn = __ldg(N + (size_t)root * 4), rmx = __ldg(N + (size_t)root * 4 + 1);
-    if (__float_as_int(rmx.w) >= 0) {   // the root is a leaf (a mesh of at most SMALL_NODE triangles)
-        if (work) work[1] += (uint32_t)__float_as_int(rmx.w);
-        return oct_leaf(S, __float_as_int(rmn.w), __float_as_int(rmx.w), o, d, origin, t_out, id_out);
-    }
-    // octant_search_order (:1245-1260): insertion sort of 0..7 by the distance from ray.pos to the centre of the ROOT's
-    // octant, ascending, stable — a rank computation gives the same order (ties: lower index first)
+// octant_search_order (src/geometry.rs:1245-1260): insertion sort of 0..7 by the distance from ray.pos to the centre of the ROOT's
+// octant, ascending, stable — a rank computation gives the same order (ties: lower index first).  3 bits per position.
+__device__ __forceinline__ uint32_t oct_search_order(const float4 rmn, const float4 rmx, float3 o) {
     const float cx = 0.5f * (rmn.x + rmx.x), cy = 0.5f * (rmn.y + rmx.y), cz = 0.5f * (rmn.z + rmx.z);
     float dist[8];
 #pragma unroll
@@ -97,7 +93,7 @@ __device__ __forceinline__ bool oct_intersect(const DevScene& S, int root, float
         const float oz = 0.5f * ((i & 1) ? cz + rmx.z : rmn.z + cz) - o.z;
         dist[i] = sqrtf(ox * ox + oy * oy + oz * oz);   // Vec3::mag: the comparison is made on the rounded root
     }
-    uint32_t order = 0;   // 3 bits per position
+    uint32_t order = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         int rank = 0;
@@ -105,25 +101,38 @@ __device__ __forceinline__ bool oct_intersect(const DevScene& S, int root, float
         for (int j = 0; j < 8; ++j) rank += (dist[j] < dist[i] || (dist[j] == dist[i] && j < i)) ? 1 : 0;
         order |= (uint32_t)i << (3 * rank);
     }
-    int node[OCT_MAX_DEPTH];
+    return order;
+}
+
+// Octree::intersect for ONE mesh (root node index `root`): true + (t, id) of the hit the reference would return
+__device__ __forceinline__ bool oct_intersect(const DevScene& S, int root, float3 o, float3 d, float3 inv, uint32_t origin, float& t_out, uint32_t& id_out,
+                                              uint32_t* work) {
+    const float4* N = S.oct_nodes;
+    const float4 rmn = __ldg(N + (size_t)root * 2), rmx = __ldg(N + (size_t)root * 2 + 1);
+    if (__float_as_int(rmx.w) >= 0) {   // the root is a leaf (a mesh of at most SMALL_NODE triangles)
+        if (work) work[1] += (uint32_t)__float_as_int(rmx.w);
+        return oct_leaf(S, __float_as_int(rmn.w), __float_as_int(rmx.w), o, d, origin, t_out, id_out);
+    }
+    const uint32_t order = oct_search_order(rmn, rmx, o);
+    int sbase[OCT_MAX_DEPTH], smask[OCT_MAX_DEPTH];   // (first child, mask) of the parents above the current one
+    int cur_base = __float_as_int(rmn.w), cur_mask = -1 - __float_as_int(rmx.w);
     unsigned long long pos = 0;   // 4 bits per level: next position in `order` to try
     int level = 0;
-    node[0] = root;
     for (;;) {
         const unsigned p = (unsigned)(pos >> (4 * level)) & 15u;
         if (p == 8u) {   // this parent is exhausted without a hit
             if (level == 0) return false;
             pos &= ~(15ull << (4 * level));
             --level;
+            cur_base = sbase[level];
+            cur_mask = smask[level];
             continue;
         }
         pos += 1ull << (4 * level);
         const int i = (int)(order >> (3 * p)) & 7;
-        const float4* np = N + (size_t)node[level] * 4;
-        const float4 cq = __ldg(np + 2 + (i >> 2));
-        const int c = __float_as_int((i & 3) == 0 ? cq.x : (i & 3) == 1 ? cq.y : (i & 3) == 2 ? cq.z : cq.w);
-        if (c < 0) continue;   // children[i] == None
-        const float4 cmn = __ldg(N + (size_t)c * 4), cmx = __ldg(N + (size_t)c * 4 + 1);
+        if (!((cur_mask >> i) & 1)) continue;   // children[i] == None
+        const int c = cur_base + __popc((unsigned)cur_mask & ((1u << i) - 1u));
+        const float4 cmn = __ldg(N + (size_t)c * 2), cmx = __ldg(N + (size_t)c * 2 + 1);
         if (work) work[0]++;
         if (!oct_box_hit(cmn, cmx, o, d, inv)) continue;
         const int cnt = __float_as_int(cmx.w);
@@ -131,8 +140,11 @@ __device__ __forceinline__ bool oct_intersect(const DevScene& S, int root, float
             if (work) work[1] += (uint32_t)cnt;
             if (oct_leaf(S, __float_as_int(cmn.w), cnt, o, d, origin, t_out, id_out)) return true;
         } else if (level + 1 < OCT_MAX_DEPTH) {
+            sbase[level] = cur_base;
+            smask[level] = cur_mask;
             ++level;
-            node[level] = c;
+            cur_base = __float_as_int(cmn.w);
+            cur_mask = -1 - cnt;
         }
     }
 }

@@ -554,37 +554,178 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_cons
 // each ray walks the reference's octrees (octree.cuh) instead of the LBVH.  One ray per thread, grid-stride; the octree
 // search is not a nearest-hit query, so a shadow ray cannot stop at the first triangle below its limit either: it takes
 // the hit the reference's trace_ray would see and compares (mutually_visible, src/scene.rs:258-270).
+// Persistent, like k_traverse: a lane that has finished its ray takes the next one while its neighbours are still searching,
+// and the search itself is cut into uniform steps — ONE child-box test per lane and step (oct_step), leaves tested in a phase
+// of their own — so that lanes at different depths of different octrees still execute the same instruction.  (The first
+// version ran oct_trace_meshes once per thread: ncu counted 5.8 of 32 lanes active per instruction.)
+enum : int { OCT_IDLE = 0, OCT_NEXT_MESH, OCT_DESCEND, OCT_LEAF, OCT_DONE };
+constexpr int OCT_STEPS = 16;   // child-box tests per lane and round (swept 2 .. 32 with refill thresholds 16 .. 31: tools/gpu_octree.py)
+
 template <bool COUNT>
-__global__ void __launch_bounds__(WF_THREADS) k_traverse_octree(const __grid_constant__ RenderArgs a, int c) {
+__global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_constant__ RenderArgs a, int c) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int2* const nstack = reinterpret_cast<int2*>(smem_raw) + threadIdx.x;   // (first child, mask) of the parent at level l: nstack[l * blockDim.x]
+    const unsigned nstride = blockDim.x;
     DevCtrl* C = a.ctrl;
     const uint32_t n_ext = min(C->ext_head(c), a.Pcap);
     const uint32_t count = n_ext + min(C->sh_head(c), a.SPcap);
+    const unsigned lane = threadIdx.x & 31;
     const int light_obj = a.S.hdr->light_obj;
     const uint32_t* const perm = a.bin_bits > 0 ? a.bin_perm : nullptr;   // bin order: neighbouring lanes walk neighbouring octants
+    const int refill_below = a.tune_refill > 0 ? a.tune_refill : REFILL_BELOW;
+    const int steps = a.tune_steps > 0 ? a.tune_steps : OCT_STEPS;
+    const float4* const N = a.S.oct_nodes;
     uint32_t work[2] = {0, 0};
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < count; pos += gridDim.x * blockDim.x) {
-        const uint32_t i = perm ? perm[pos] : pos;
-        if (i < n_ext) {
-            const float2 h2 = a.qin.hit[i];
-            if (__float_as_uint(h2.y) == HIT_HOLE) continue;
-            const float4 o4 = a.qin.o[i], d4 = a.qin.d[i];
-            float t = h2.x;
-            uint32_t id = PC_NONE;
-            oct_trace_meshes(a.S, f3(o4), f3(d4), __float_as_uint(o4.w), t, id, COUNT ? work : nullptr);
-            if (id != PC_NONE) a.qin.hit[i] = make_float2(t, __uint_as_float(id));
-        } else {
-            const uint32_t j = i - n_ext;
-            const float4 d4 = a.sqin.d[j];
-            if (__float_as_uint(d4.w) == TLIM_HOLE) continue;
-            const float4 o4 = a.sqin.o[j], c4 = a.sqin.c[j];
-            float t = d4.w;   // NEE candidate: |y - x| - margin; dead-MIS probe: the analytic hit distance
-            uint32_t id = PC_NONE;
-            oct_trace_meshes(a.S, f3(o4), f3(d4), __float_as_uint(o4.w), t, id, COUNT ? work : nullptr);
-            bool add;
-            if (__float_as_uint(c4.w) & SHADOW_PROBE)
-                add = id != PC_NONE && __float_as_int(__ldg(a.S.tris + (size_t)(id - TRI_BASE) * TRI_STRIDE + 2).w) == light_obj;
-            else add = id == PC_NONE;   // no mesh hit below the limit: visible
-            if (add) accum_add(a.accum, __float_as_uint(c4.w) & ~SHADOW_PROBE, f3(c4));
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t wnext = min(gwarp * FETCH_CHUNK, count), wend = min(gwarp * FETCH_CHUNK + FETCH_CHUNK, count);
+    bool exhausted = false;
+    if (blockIdx.x * (WF_THREADS / 32) * FETCH_CHUNK >= count) return;
+    // lane state: the ray, the best hit so far over the analytic primitives and the meshes already searched, the search position
+    float3 o = f3(0.f, 0.f, 0.f), d = o, inv = o;
+    uint32_t origin = 0, best_id = PC_NONE, slot = 0, order = 0;
+    float best_t = 0.f;
+    unsigned long long pos = 0;        // 4 bits per level: next position in `order` to try (Octree::_intersect_recurse's loop index)
+    int level = 0, mesh = -1, leaf_first = 0, leaf_cnt = 0;
+    int cur_base = 0, cur_mask = 0;    // the parent being searched: its first child and which octants have one
+    int phase = OCT_IDLE, kind = -1;   // kind: 0 extension, 1 NEE shadow ray, 2 dead-MIS probe
+
+    for (;;) {
+        // ---- retire finished rays
+        if (phase == OCT_DONE) {
+            if (kind == 0) {
+                if (best_id != PC_NONE) a.qin.hit[slot] = make_float2(best_t, __uint_as_float(best_id));
+            } else {
+                const float4 c4 = a.sqin.c[slot];
+                bool add;
+                if (kind == 2) add = best_id != PC_NONE && __float_as_int(__ldg(a.S.tris + (size_t)(best_id - TRI_BASE) * TRI_STRIDE + 2).w) == light_obj;
+                else add = best_id == PC_NONE;   // no mesh hit below the limit: visible
+                if (add) accum_add(a.accum, __float_as_uint(c4.w) & ~SHADOW_PROBE, f3(c4));
+            }
+            phase = OCT_IDLE;
+            kind = -1;
+        }
+        // ---- refill idle lanes
+        const unsigned idle_mask = __ballot_sync(0xffffffffu, phase == OCT_IDLE);
+        if (idle_mask && !exhausted) {
+            if (!warp_reserve(&C->cursor_trav, count, wnext, wend)) exhausted = true;
+            else {
+                const uint32_t q = wnext + __popc(idle_mask & ((1u << lane) - 1u));
+                if (phase == OCT_IDLE && q < wend) {
+                    const uint32_t my = perm ? perm[q] : q;
+                    float4 o4, d4;
+                    bool take = false;
+                    if (my < n_ext) {
+                        const float2 h2 = a.qin.hit[my];
+                        if (__float_as_uint(h2.y) != HIT_HOLE) {
+                            take = true;
+                            slot = my;
+                            kind = 0;
+                            o4 = a.qin.o[my];
+                            d4 = a.qin.d[my];
+                            best_t = h2.x;
+                        }
+                    } else {
+                        d4 = a.sqin.d[my - n_ext];
+                        if (__float_as_uint(d4.w) != TLIM_HOLE) {
+                            take = true;
+                            slot = my - n_ext;
+                            o4 = a.sqin.o[slot];
+                            kind = (__float_as_uint(a.sqin.c[slot].w) & SHADOW_PROBE) ? 2 : 1;
+                            best_t = d4.w;   // NEE candidate: |y - x| - margin; dead-MIS probe: the analytic hit distance
+                        }
+                    }
+                    if (take) {
+                        o = f3(o4);
+                        d = f3(d4);
+                        inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        origin = __float_as_uint(o4.w);
+                        best_id = PC_NONE;
+                        mesh = -1;
+                        phase = OCT_NEXT_MESH;
+                    }
+                }
+                wnext = min(wnext + (uint32_t)__popc(idle_mask), wend);
+            }
+        }
+        if (__ballot_sync(0xffffffffu, phase != OCT_IDLE) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        for (;;) {
+            // ---- (1) Scene::trace_ray's loop over the objects (src/scene.rs:277-284): the next mesh, its root, its search order
+            if (phase == OCT_NEXT_MESH) {
+                int root = -1;
+                // a NEE shadow ray is decided by the first mesh hit below its limit (visible iff none): the other meshes cannot change that
+                if (!(kind == 1 && best_id != PC_NONE))
+                    while (++mesh < a.S.n_oct_meshes && (root = __ldg(a.S.oct_roots + mesh)) < 0) {}
+                if (root < 0) phase = OCT_DONE;
+                else {
+                    const float4 rmn = __ldg(N + (size_t)root * 2), rmx = __ldg(N + (size_t)root * 2 + 1);
+                    if (__float_as_int(rmx.w) >= 0) {   // the root is a leaf (a mesh of at most SMALL_NODE triangles)
+                        leaf_first = __float_as_int(rmn.w);
+                        leaf_cnt = __float_as_int(rmx.w);
+                        level = -1;
+                        phase = OCT_LEAF;
+                    } else {
+                        order = oct_search_order(rmn, rmx, o);
+                        pos = 0;
+                        level = 0;
+                        cur_base = __float_as_int(rmn.w);
+                        cur_mask = -1 - __float_as_int(rmx.w);
+                        phase = OCT_DESCEND;
+                    }
+                }
+            }
+            // ---- (2) child-box tests, at most `steps` per lane and round
+            for (int k = 0; k < steps; ++k) {
+                if (!__any_sync(0xffffffffu, phase == OCT_DESCEND)) break;
+                if (phase != OCT_DESCEND) continue;
+                const unsigned p = (unsigned)(pos >> (4 * level)) & 15u;
+                if (p == 8u) {   // this parent is exhausted without a hit
+                    if (level == 0) phase = OCT_NEXT_MESH;
+                    else {
+                        pos &= ~(15ull << (4 * level));
+                        --level;
+                        const int2 up = nstack[level * nstride];
+                        cur_base = up.x;
+                        cur_mask = up.y;
+                    }
+                    continue;
+                }
+                pos += 1ull << (4 * level);
+                const int i = (int)(order >> (3 * p)) & 7;
+                if (!((cur_mask >> i) & 1)) continue;   // children[i] == None
+                const int ch = cur_base + __popc((unsigned)cur_mask & ((1u << i) - 1u));
+                const float4 cmn = __ldg(N + (size_t)ch * 2), cmx = __ldg(N + (size_t)ch * 2 + 1);
+                if (COUNT) work[0]++;
+                if (!oct_box_hit(cmn, cmx, o, d, inv)) continue;
+                const int cnt = __float_as_int(cmx.w);
+                if (cnt >= 0) {   // leaf: tested in phase (3)
+                    leaf_first = __float_as_int(cmn.w);
+                    leaf_cnt = cnt;
+                    phase = OCT_LEAF;
+                } else if (level + 1 < OCT_MAX_DEPTH) {
+                    nstack[level * nstride] = make_int2(cur_base, cur_mask);
+                    ++level;
+                    cur_base = __float_as_int(cmn.w);
+                    cur_mask = -1 - cnt;
+                }
+            }
+            // ---- (3) leaves: the nearest of the leaf's triangles ends the search of this mesh, wherever the hit lies
+            if (phase == OCT_LEAF) {
+                if (COUNT) work[1] += (uint32_t)leaf_cnt;
+                float t;
+                uint32_t id;
+                if (oct_leaf(a.S, leaf_first, leaf_cnt, o, d, origin, t, id)) {
+                    if (t < best_t) {   // strict '<' against the best so far (src/scene.rs:280)
+                        best_t = t;
+                        best_id = id;
+                    }
+                    phase = OCT_NEXT_MESH;
+                } else phase = level < 0 ? OCT_NEXT_MESH : OCT_DESCEND;
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, phase != OCT_DONE && phase != OCT_IDLE);
+            if (act == 0 || (!exhausted && __popc(act) < refill_below)) break;
         }
     }
     if (COUNT) {
@@ -592,7 +733,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_traverse_octree(const __grid_con
             work[0] += __shfl_down_sync(0xffffffffu, work[0], off);
             work[1] += __shfl_down_sync(0xffffffffu, work[1], off);
         }
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             atomicAdd(&C->node_visits, (unsigned long long)work[0]);
             atomicAdd(&C->tri_tests, (unsigned long long)work[1]);
         }
