@@ -75,7 +75,7 @@ struct DevScene {          // passed to kernels by value
     const float4* tri_orig; // 3 x float4 per triangle in GLOBAL order: a, b, c (mesh-light sampling)
     // RTB_ACCEL_OCTREE_REFERENCE (octree.cuh): the reference's per-mesh octrees, built lazily on first use (nullptr before)
     const float4* oct_nodes;   // 2 x float4 per node (octree.cuh)
-    const int32_t* oct_tris;   // leaf triangle references = slots of `tris`
+    const float4* oct_tris;    // leaf triangles in reference order: a COPY of the `tris` record per reference (TRI_STRIDE x float4), its slot in `tris` in [1].w
     const int32_t* oct_roots;  // root node per mesh, in object order (-1: empty mesh)
     int32_t n_oct_meshes;
     int32_t n_prims, n_objects, n_tris, root;

@@ -125,7 +125,7 @@ struct rtb_scene {
     // RTB_ACCEL_OCTREE_REFERENCE: the reference's octrees, built on first use
     bool octrees_built = false;
     float4* d_oct_nodes = nullptr;
-    int32_t* d_oct_tris = nullptr;
+    float4* d_oct_tris = nullptr;
     int32_t* d_oct_roots = nullptr;
     int oct_nodes = 0, oct_refs = 0;
     double oct_build_ms = 0;
@@ -358,8 +358,9 @@ int ensure_octrees(rtb_scene* sc) {
     const auto t0 = std::chrono::steady_clock::now();
     const int n_tris = sc->view.n_tris;
     std::vector<int32_t> slot_of((size_t)n_tris, -1);   // global triangle index -> slot in the LBVH triangle table
+    std::vector<float4> tris_host((size_t)n_tris * TRI_STRIDE);
     if (n_tris) {
-        std::vector<float4> tris((size_t)n_tris * TRI_STRIDE);
+        std::vector<float4>& tris = tris_host;
         CU_TRY(cudaMemcpy(tris.data(), sc->bvh.d_tris, tris.size() * sizeof(float4), cudaMemcpyDeviceToHost));
         for (int s = 0; s < n_tris; ++s) {
             int g;
@@ -402,9 +403,14 @@ int ensure_octrees(rtb_scene* sc) {
         CU_TRY(cudaMalloc((void**)&sc->d_oct_nodes, nodes.size() * sizeof(float4)));
         CU_TRY(cudaMemcpy(sc->d_oct_nodes, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
-    if (!refs.empty()) {
-        CU_TRY(cudaMalloc((void**)&sc->d_oct_tris, refs.size() * sizeof(int32_t)));
-        CU_TRY(cudaMemcpy(sc->d_oct_tris, refs.data(), refs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!refs.empty()) {   // every reference gets its own copy of the triangle record; [1].w (the global triangle id there) names the slot in the LBVH table
+        std::vector<float4> rt(refs.size() * TRI_STRIDE);
+        for (size_t k = 0; k < refs.size(); ++k) {
+            for (int q = 0; q < TRI_STRIDE; ++q) rt[k * TRI_STRIDE + q] = tris_host[(size_t)refs[k] * TRI_STRIDE + q];
+            rt[k * TRI_STRIDE + 1].w = as_f(refs[k]);
+        }
+        CU_TRY(cudaMalloc((void**)&sc->d_oct_tris, rt.size() * sizeof(float4)));
+        CU_TRY(cudaMemcpy(sc->d_oct_tris, rt.data(), rt.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
     if (!roots.empty()) {
         CU_TRY(cudaMalloc((void**)&sc->d_oct_roots, roots.size() * sizeof(int32_t)));

@@ -47,17 +47,19 @@ __device__ __forceinline__ bool oct_box_hit(const float4 mn, const float4 mx, fl
 }
 
 // Node::Leaf: the nearest of the leaf's triangles, Triangle::intersect each (src/geometry.rs:637-670, :1276-1293).
-// Same arithmetic as trav_leaf (intersect.cuh), but over triangle REFERENCES and without an upper bound on t.
+// Same arithmetic as trav_leaf (intersect.cuh), but over the leaf's own triangle list and without an upper bound on t.
 __device__ __forceinline__ bool oct_leaf(const DevScene& S, int first, int count, float3 o, float3 d, uint32_t origin, float& t_out, uint32_t& id_out) {
     const uint32_t origin_id = origin & PC_ID_MASK;
     float best = INFINITY;
     uint32_t best_id = PC_NONE;
     for (int k = first; k < first + count; ++k) {
-        const uint32_t s = (uint32_t)__ldg(S.oct_tris + k);
-        const float4* tp = S.tris + (size_t)s * TRI_STRIDE;
+        // the leaf's triangles lie next to each other in the octree's own table (a copy of the LBVH's record per reference, which
+        // names its slot there): one fetch per triangle instead of reference -> record
+        const float4* tp = S.oct_tris + (size_t)k * TRI_STRIDE;
         float4 t0, t1;
         ldg256(tp, t0, t1);
         const float4 t2 = __ldg(tp + 2);
+        const uint32_t s = __float_as_uint(t1.w);
         const float3 e1 = f3(t1), e2 = f3(t2);
         const float3 pvec = cross(d, e2);
         const float det = dot(e1, pvec);
