@@ -106,6 +106,21 @@ __device__ __forceinline__ uint32_t oct_search_order(const float4 rmn, const flo
     return order;
 }
 
+// inverse of `order`: 3 bits per OCTANT = its position in the search order
+__device__ __forceinline__ uint32_t oct_rank_of_order(uint32_t order) {
+    uint32_t rank = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) rank |= (uint32_t)p << (3 * ((order >> (3 * p)) & 7u));
+    return rank;
+}
+// the children a parent has (bit i of mask = octant i), as bits in search order
+__device__ __forceinline__ uint32_t oct_present_in_order(int mask, uint32_t rank) {
+    uint32_t rem = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rem |= (((uint32_t)mask >> i) & 1u) << ((rank >> (3 * i)) & 7u);
+    return rem;
+}
+
 // Octree::intersect for ONE mesh (root node index `root`): true + (t, id) of the hit the reference would return
 __device__ __forceinline__ bool oct_intersect(const DevScene& S, int root, float3 o, float3 d, float3 inv, uint32_t origin, float& t_out, uint32_t& id_out,
                                               uint32_t* work) {

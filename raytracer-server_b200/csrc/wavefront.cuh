@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(WF_THREADS, MINB) k_traverse(const __grid_cons
 // of their own — so that lanes at different depths of different octrees still execute the same instruction.  (The first
 // version ran oct_trace_meshes once per thread: ncu counted 5.8 of 32 lanes active per instruction.)
 enum : int { OCT_IDLE = 0, OCT_NEXT_MESH, OCT_DESCEND, OCT_LEAF, OCT_DONE };
-constexpr int OCT_STEPS = 16;   // child-box tests per lane and round (swept 2 .. 32 with refill thresholds 16 .. 31: tools/gpu_octree.py)
+constexpr int OCT_STEPS = 12;   // child-box tests per lane and round (swept 6 .. 24 with refill thresholds 24 / 28: flat between 8 and 12)
 
 template <bool COUNT>
 __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_constant__ RenderArgs a, int c) {
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_
     float3 o = f3(0.f, 0.f, 0.f), d = o, inv = o;
     uint32_t origin = 0, best_id = PC_NONE, slot = 0, order = 0;
     float best_t = 0.f;
-    unsigned long long pos = 0;        // 4 bits per level: next position in `order` to try (Octree::_intersect_recurse's loop index)
+    uint32_t rank = 0, rem = 0;        // rank: position of octant i in `order` (3 bits each); rem: see phase (2)
     int level = 0, mesh = -1, leaf_first = 0, leaf_cnt = 0;
     int cur_base = 0, cur_mask = 0;    // the parent being searched: its first child and which octants have one
     int phase = OCT_IDLE, kind = -1;   // kind: 0 extension, 1 NEE shadow ray, 2 dead-MIS probe
@@ -668,33 +668,35 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_
                         phase = OCT_LEAF;
                     } else {
                         order = oct_search_order(rmn, rmx, o);
-                        pos = 0;
+                        rank = oct_rank_of_order(order);
                         level = 0;
                         cur_base = __float_as_int(rmn.w);
                         cur_mask = -1 - __float_as_int(rmx.w);
+                        rem = oct_present_in_order(cur_mask, rank);
                         phase = OCT_DESCEND;
                     }
                 }
             }
-            // ---- (2) child-box tests, at most `steps` per lane and round
+            // ---- (2) child-box tests, at most `steps` per lane and round.  `rem` = the children of the current parent that are still
+            // to be tried, as bits in SEARCH order (bit p = the p-th octant of `order` has a child): a step takes the lowest one, so
+            // octants without a child (a third of all slots) never cost a step
             for (int k = 0; k < steps; ++k) {
                 if (!__any_sync(0xffffffffu, phase == OCT_DESCEND)) break;
                 if (phase != OCT_DESCEND) continue;
-                const unsigned p = (unsigned)(pos >> (4 * level)) & 15u;
-                if (p == 8u) {   // this parent is exhausted without a hit
+                if (rem == 0u) {   // this parent is exhausted without a hit
                     if (level == 0) phase = OCT_NEXT_MESH;
                     else {
-                        pos &= ~(15ull << (4 * level));
                         --level;
                         const int2 up = nstack[level * nstride];
                         cur_base = up.x;
-                        cur_mask = up.y;
+                        cur_mask = up.y & 255;
+                        rem = (unsigned)up.y >> 8;
                     }
                     continue;
                 }
-                pos += 1ull << (4 * level);
+                const unsigned p = (unsigned)__ffs((int)rem) - 1u;
+                rem &= rem - 1u;
                 const int i = (int)(order >> (3 * p)) & 7;
-                if (!((cur_mask >> i) & 1)) continue;   // children[i] == None
                 const int ch = cur_base + __popc((unsigned)cur_mask & ((1u << i) - 1u));
                 const float4 cmn = __ldg(N + (size_t)ch * 2), cmx = __ldg(N + (size_t)ch * 2 + 1);
                 if (COUNT) work[0]++;
@@ -705,10 +707,11 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_
                     leaf_cnt = cnt;
                     phase = OCT_LEAF;
                 } else if (level + 1 < OCT_MAX_DEPTH) {
-                    nstack[level * nstride] = make_int2(cur_base, cur_mask);
+                    nstack[level * nstride] = make_int2(cur_base, cur_mask | (int)(rem << 8));
                     ++level;
                     cur_base = __float_as_int(cmn.w);
                     cur_mask = -1 - cnt;
+                    rem = oct_present_in_order(cur_mask, rank);
                 }
             }
             // ---- (3) leaves: the nearest of the leaf's triangles ends the search of this mesh, wherever the hit lies
