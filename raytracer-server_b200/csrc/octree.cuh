@@ -106,19 +106,26 @@ __device__ __forceinline__ uint32_t oct_search_order(const float4 rmn, const flo
     return order;
 }
 
-// inverse of `order`: 3 bits per OCTANT = its position in the search order
-__device__ __forceinline__ uint32_t oct_rank_of_order(uint32_t order) {
-    uint32_t rank = 0;
+// one byte per OCTANT: 1 << (its position in the search order); .x = octants 0..3, .y = octants 4..7
+__device__ __forceinline__ uint2 oct_order_bytes(uint32_t order) {
+    uint2 B = make_uint2(0u, 0u);
 #pragma unroll
-    for (int p = 0; p < 8; ++p) rank |= (uint32_t)p << (3 * ((order >> (3 * p)) & 7u));
-    return rank;
+    for (int p = 0; p < 8; ++p) {
+        const uint32_t i = (order >> (3 * p)) & 7u;
+        const uint32_t v = (1u << p) << (8u * (i & 3u));
+        if (i & 4u) B.y |= v; else B.x |= v;
+    }
+    return B;
 }
-// the children a parent has (bit i of mask = octant i), as bits in search order
-__device__ __forceinline__ uint32_t oct_present_in_order(int mask, uint32_t rank) {
-    uint32_t rem = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) rem |= (((uint32_t)mask >> i) & 1u) << ((rank >> (3 * i)) & 7u);
-    return rem;
+// the children a parent has (bit i of mask = octant i), as bits in search order: every mask bit is spread to a byte
+// (nibble * 0x00204081 puts bit k at 8k without carries), selects its octant's byte of B, and the bytes are OR-ed together
+__device__ __forceinline__ uint32_t oct_present_in_order(int mask, uint2 B) {
+    const uint32_t mlo = ((((uint32_t)mask & 15u) * 0x00204081u) & 0x01010101u) * 0xffu;
+    const uint32_t mhi = (((((uint32_t)mask >> 4) & 15u) * 0x00204081u) & 0x01010101u) * 0xffu;
+    uint32_t x = (B.x & mlo) | (B.y & mhi);
+    x |= x >> 16;
+    x |= x >> 8;
+    return x & 0xffu;
 }
 
 // Octree::intersect for ONE mesh (root node index `root`): true + (t, id) of the hit the reference would return

@@ -584,7 +584,8 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_
     float3 o = f3(0.f, 0.f, 0.f), d = o, inv = o;
     uint32_t origin = 0, best_id = PC_NONE, slot = 0, order = 0;
     float best_t = 0.f;
-    uint32_t rank = 0, rem = 0;        // rank: position of octant i in `order` (3 bits each); rem: see phase (2)
+    uint2 obytes = make_uint2(0u, 0u);   // per octant one byte: 1 << its position in `order` (oct_order_bytes)
+    uint32_t rem = 0;                  // see phase (2)
     int level = 0, mesh = -1, leaf_first = 0, leaf_cnt = 0;
     int cur_base = 0, cur_mask = 0;    // the parent being searched: its first child and which octants have one
     int phase = OCT_IDLE, kind = -1;   // kind: 0 extension, 1 NEE shadow ray, 2 dead-MIS probe
@@ -668,11 +669,11 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_
                         phase = OCT_LEAF;
                     } else {
                         order = oct_search_order(rmn, rmx, o);
-                        rank = oct_rank_of_order(order);
+                        obytes = oct_order_bytes(order);
                         level = 0;
                         cur_base = __float_as_int(rmn.w);
                         cur_mask = -1 - __float_as_int(rmx.w);
-                        rem = oct_present_in_order(cur_mask, rank);
+                        rem = oct_present_in_order(cur_mask, obytes);
                         phase = OCT_DESCEND;
                     }
                 }
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_
                     ++level;
                     cur_base = __float_as_int(cmn.w);
                     cur_mask = -1 - cnt;
-                    rem = oct_present_in_order(cur_mask, rank);
+                    rem = oct_present_in_order(cur_mask, obytes);
                 }
             }
             // ---- (3) leaves: the nearest of the leaf's triangles ends the search of this mesh, wherever the hit lies
