@@ -46,37 +46,44 @@ __device__ __forceinline__ bool oct_box_hit(const float4 mn, const float4 mx, fl
     return t_in <= t_out && t_out >= EPS;
 }
 
-// Node::Leaf: the nearest of the leaf's triangles, Triangle::intersect each (src/geometry.rs:637-670, :1276-1293).
-// Same arithmetic as trav_leaf (intersect.cuh), but over the leaf's own triangle list and without an upper bound on t.
+// Triangle::intersect (src/geometry.rs:637-670) on entry k of the octree's own triangle table (a copy of the LBVH's record per
+// leaf reference, naming its slot there: one fetch per triangle instead of reference -> record).  Same arithmetic as trav_leaf
+// (intersect.cuh); no upper bound on t.
+__device__ __forceinline__ bool oct_tri_test(const DevScene& S, int k, float3 o, float3 d, uint32_t origin, float& t_out, uint32_t& id_out) {
+    const float4* tp = S.oct_tris + (size_t)k * TRI_STRIDE;
+    float4 t0, t1;
+    ldg256(tp, t0, t1);
+    const float4 t2 = __ldg(tp + 2);
+    const uint32_t s = __float_as_uint(t1.w);
+    const float3 e1 = f3(t1), e2 = f3(t2);
+    const float3 pvec = cross(d, e2);
+    const float det = dot(e1, pvec);
+    const float nd = det * t0.w;
+    if (fabsf(nd) < DN_EPS) return false;
+    const float inv = __fdividef(1.0f, det);
+    const float3 tvec = o - f3(t0);
+    const float u = dot(tvec, pvec) * inv;
+    const float3 qvec = cross(tvec, e1);
+    const float vv = dot(d, qvec) * inv;
+    float t = dot(e2, qvec) * inv;
+    if (TRI_BASE + s == (origin & PC_ID_MASK)) {   // the triangle the ray starts on: as the reference's f64 arithmetic sees it (intersect.cuh header)
+        const float dnf = (origin & PC_FLIPPED) ? -nd : nd;
+        t = -SURF_OFFSET / dnf;
+    }
+    if (u < 0.0f || vv < 0.0f || u + vv > 1.0f || !(t > T_EPS)) return false;
+    t_out = t;
+    id_out = TRI_BASE + s;
+    return true;
+}
+
+// Node::Leaf: the nearest of the leaf's triangles (src/geometry.rs:1276-1293)
 __device__ __forceinline__ bool oct_leaf(const DevScene& S, int first, int count, float3 o, float3 d, uint32_t origin, float& t_out, uint32_t& id_out) {
-    const uint32_t origin_id = origin & PC_ID_MASK;
     float best = INFINITY;
     uint32_t best_id = PC_NONE;
     for (int k = first; k < first + count; ++k) {
-        // the leaf's triangles lie next to each other in the octree's own table (a copy of the LBVH's record per reference, which
-        // names its slot there): one fetch per triangle instead of reference -> record
-        const float4* tp = S.oct_tris + (size_t)k * TRI_STRIDE;
-        float4 t0, t1;
-        ldg256(tp, t0, t1);
-        const float4 t2 = __ldg(tp + 2);
-        const uint32_t s = __float_as_uint(t1.w);
-        const float3 e1 = f3(t1), e2 = f3(t2);
-        const float3 pvec = cross(d, e2);
-        const float det = dot(e1, pvec);
-        const float nd = det * t0.w;
-        if (fabsf(nd) < DN_EPS) continue;
-        const float inv = __fdividef(1.0f, det);
-        const float3 tvec = o - f3(t0);
-        const float u = dot(tvec, pvec) * inv;
-        const float3 qvec = cross(tvec, e1);
-        const float vv = dot(d, qvec) * inv;
-        float t = dot(e2, qvec) * inv;
-        if (TRI_BASE + s == origin_id) {   // the triangle the ray starts on: as the reference's f64 arithmetic sees it (intersect.cuh header)
-            const float dnf = (origin & PC_FLIPPED) ? -nd : nd;
-            t = -SURF_OFFSET / dnf;
-        }
-        if (u < 0.0f || vv < 0.0f || u + vv > 1.0f || !(t > T_EPS)) continue;
-        if (t < best) { best = t; best_id = TRI_BASE + s; }   // strict '<': the first of equal hits stays (:1281)
+        float t;
+        uint32_t id;
+        if (oct_tri_test(S, k, o, d, origin, t, id) && t < best) { best = t; best_id = id; }   // strict '<': the first of equal hits stays (:1281)
     }
     t_out = best;
     id_out = best_id;

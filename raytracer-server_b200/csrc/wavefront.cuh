@@ -715,18 +715,68 @@ __global__ void __launch_bounds__(WF_THREADS, 4) k_traverse_octree(const __grid_
                     rem = oct_present_in_order(cur_mask, obytes);
                 }
             }
-            // ---- (3) leaves: the nearest of the leaf's triangles ends the search of this mesh, wherever the hit lies
-            if (phase == OCT_LEAF) {
-                if (COUNT) work[1] += (uint32_t)leaf_cnt;
-                float t;
-                uint32_t id;
-                if (oct_leaf(a.S, leaf_first, leaf_cnt, o, d, origin, t, id)) {
-                    if (t < best_t) {   // strict '<' against the best so far (src/scene.rs:280)
-                        best_t = t;
-                        best_id = id;
+            // ---- (3) leaves: the nearest of the leaf's triangles ends the search of this mesh, wherever the hit lies.  The pending
+            // leaves of the warp are tested COOPERATIVELY: their (ray, triangle) pairs are dealt out over all 32 lanes — a lane
+            // fetches the owner's ray by shuffle, tests one triangle, and a segmented min hands the nearest hit (lowest triangle
+            // on ties, like the reference's strict '<') back to the owner.  (A loop per owner ran with 6 of 32 lanes.)
+            if (__any_sync(0xffffffffu, phase == OCT_LEAF)) {
+                const bool owner_lane = phase == OCT_LEAF;
+                const int my_cnt = owner_lane ? leaf_cnt : 0;
+                if (COUNT) work[1] += (uint32_t)my_cnt;
+                int incl = my_cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                    if ((int)lane >= off) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - my_cnt;   // first pair of this lane's leaf
+                float bt = INFINITY;
+                uint32_t bid = PC_NONE;
+                for (int base = 0; base < total; base += 32) {
+                    const int pair = base + (int)lane;
+                    int own = 0;   // the last lane whose first pair is <= pair: the owner (lanes without a leaf share the NEXT owner's value)
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const int cand = own + step;
+                        const int e = __shfl_sync(0xffffffffu, excl, cand & 31);
+                        if (e <= pair) own = cand;
                     }
-                    phase = OCT_NEXT_MESH;
-                } else phase = level < 0 ? OCT_NEXT_MESH : OCT_DESCEND;
+                    const int k_in = pair - __shfl_sync(0xffffffffu, excl, own);
+                    const float3 ro = f3(__shfl_sync(0xffffffffu, o.x, own), __shfl_sync(0xffffffffu, o.y, own), __shfl_sync(0xffffffffu, o.z, own));
+                    const float3 rd = f3(__shfl_sync(0xffffffffu, d.x, own), __shfl_sync(0xffffffffu, d.y, own), __shfl_sync(0xffffffffu, d.z, own));
+                    const uint32_t rorigin = __shfl_sync(0xffffffffu, origin, own);
+                    const int rfirst = __shfl_sync(0xffffffffu, leaf_first, own);
+                    float t = INFINITY;
+                    uint32_t id = PC_NONE;
+                    if (pair < total) {
+                        float tt;
+                        uint32_t ii;
+                        if (oct_tri_test(a.S, rfirst + k_in, ro, rd, rorigin, tt, ii)) { t = tt; id = ii; }
+                    }
+                    // segmented min towards the first lane of each owner's run (pairs of one owner are neighbours, in triangle order)
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const float t2 = __shfl_down_sync(0xffffffffu, t, off);
+                        const uint32_t i2 = __shfl_down_sync(0xffffffffu, id, off);
+                        const int o2 = __shfl_down_sync(0xffffffffu, own, off);
+                        if ((int)lane + off < 32 && o2 == own && t2 < t) { t = t2; id = i2; }
+                    }
+                    // the owner reads its run's first lane of this pass (its run may have started in an earlier pass)
+                    const int src = max(excl - base, 0);
+                    const float ts = __shfl_sync(0xffffffffu, t, src & 31);
+                    const uint32_t is = __shfl_sync(0xffffffffu, id, src & 31);
+                    if (owner_lane && excl < base + 32 && excl + my_cnt > base && ts < bt) { bt = ts; bid = is; }
+                }
+                if (owner_lane) {
+                    if (bid != PC_NONE) {
+                        if (bt < best_t) {   // strict '<' against the best so far (src/scene.rs:280)
+                            best_t = bt;
+                            best_id = bid;
+                        }
+                        phase = OCT_NEXT_MESH;
+                    } else phase = level < 0 ? OCT_NEXT_MESH : OCT_DESCEND;
+                }
             }
             const unsigned act = __ballot_sync(0xffffffffu, phase != OCT_DONE && phase != OCT_IDLE);
             if (act == 0 || (!exhausted && __popc(act) < refill_below)) break;
