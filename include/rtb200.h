@@ -52,7 +52,7 @@ typedef struct rtb_job rtb_job;
                                  RTB_EST_NEE, less variance near the light; sphere lights only; never used for parity */
 
 /* mesh acceleration (Mesh::intersect, src/geometry.rs:883-905) */
-#define RTB_ACCEL_LBVH 0             /* true nearest hit = the reference's brute-force branch (:887-903), through the device-built LBVH */
+#define RTB_ACCEL_LBVH 0             /* true nearest hit = the reference's brute-force branch (:887-903), through the device-built BVH (binned SAH, linear node table) */
 #define RTB_ACCEL_OCTREE_REFERENCE 1 /* the branch the reference actually runs: its per-mesh octree with the early exit on the first child
                                         that reports any hit (:1237-1295; Octree::build :1149-1216 restated on the host).  NOT a nearest-hit
                                         structure — it is what makes the Rust binary's flying_unicorn differ from the exact image by 30 dB.
