@@ -1674,8 +1674,8 @@ namespace {
 
 constexpr int PIXELS_PER_MSG = 60;  // RenderJob::PIXELS_PER_MSG, src/server.rs:145
 // Band schedule of a single-pass job: the first bands are small, so the first records leave early; later bands grow,
-// because every band pays for its own tail of under-filled wavefront iterations (sizes in samples: 8 Mi, 8 Mi, 16 Mi,
-// 32 Mi, then 64 Mi each; a frame below 16 Mi samples is one band)
+// because every band pays for its own tail of under-filled wavefront iterations (sizes in samples for a large frame: 8 Mi,
+// 8 Mi, 16 Mi, 32 Mi, then 64 Mi each; smaller frames start at a sixteenth of their samples, rtb_job_begin)
 constexpr uint64_t BAND_MIN_SAMPLES = 8ull << 20;
 constexpr int BAND_GROWTH_CAP = 8;   // largest band = BAND_GROWTH_CAP x the first
 
@@ -1911,7 +1911,12 @@ int rtb_job_begin(rtb_scene* scene, const rtb_params* params, int32_t passes, rt
     // bands of whole tile rows (see BAND_MIN_SAMPLES)
     const int tiles_x = (params->width + TILE - 1) / TILE, tiles_y = (params->height + TILE - 1) / TILE;
     const uint64_t row_samples = (uint64_t)tiles_x * 1024ull * 4ull * (uint64_t)std::max(1, params->spp / 4);
-    int rows = (int)std::max<uint64_t>(1, (BAND_MIN_SAMPLES + row_samples - 1) / row_samples);
+    // first band: a sixteenth of the frame's samples, between 1 Mi and BAND_MIN_SAMPLES (8 Mi) — small frames used to wait for a
+    // quarter to a half of the whole job before the first record (600x450x256: 22.5 -> 12.5 ms, 600x450x64: 13.3 -> 5.4 ms; job +3 %)
+    const uint64_t total_samples = row_samples * (uint64_t)tiles_y;
+    uint64_t band_min = std::min<uint64_t>(BAND_MIN_SAMPLES, std::max<uint64_t>(1ull << 20, total_samples / 16));
+    if (const char* e = getenv("RTB_BAND_MIN_SAMPLES")) band_min = (uint64_t)std::max(1ll, atoll(e));   // experiment knob
+    int rows = (int)std::max<uint64_t>(1, (band_min + row_samples - 1) / row_samples);
     int growth_cap = BAND_GROWTH_CAP;
     if (const char* e = getenv("RTB_BAND_TILE_ROWS")) { rows = std::max(1, atoi(e)); growth_cap = 1; }   // test / experiment knobs
     if (const char* e = getenv("RTB_BAND_GROWTH_CAP")) growth_cap = std::max(1, atoi(e));
