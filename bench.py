@@ -152,6 +152,8 @@ def run_reference(args):
     wl = workload(args.gpus)
     steps = max(1, args.steps)
     per_step = max(3.0, min(20.0, 90.0 / (steps + args.warmup)))
+    if os.environ.get("RTB_BENCH_CPU_SECONDS"):   # test hook (tests/test_bench_contract.py): a shorter CPU sample
+        per_step = float(os.environ["RTB_BENCH_CPU_SECONDS"])
     vals = []
     for _ in range(args.warmup):
         cpu_reference_run(wl["width"], wl["height"], wl["spp"], seconds_target=min(per_step, 3.0))
