@@ -406,6 +406,10 @@ def main():
                 "steps": steps}
 
     # ---------------------------------------------------------------- value: K timed steps of the headline frame
+    # The headline frames (path pools of 32 Mi slots) are launched kernel by kernel, with CUDA events around k_traverse / k_shade: that
+    # is what the library does for pools above 16 Mi anyway; RTB_NO_GRAPH pins it, so that the per-kernel times the roofline needs are
+    # there even under the --spp debug override.  The `configs` block below runs with the library's defaults (graph replay).
+    os.environ["RTB_NO_GRAPH"] = "1"
     fr = Frame(W, H)
     clocks = ClockSampler(local_rank)
     for i in range(args.warmup):
@@ -530,6 +534,7 @@ def main():
             c = cpu_reference_run(W, H, SPP, seconds_target=15.0)
             cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
                    "mrays_per_s": c["mrays"], "build": CPU_BUILD, "scheduling": CPU_SCHED}
+        os.environ.pop("RTB_NO_GRAPH", None)
         if world == 1 and not args.no_configs and not args.spp:
             extra["configs"] = measure_configs(R, local_rank)
 
@@ -542,7 +547,7 @@ def main():
                 "samples_per_step": W * H * (SPP // 4) * 4,
                 "parallelism": f"tiles32x32 interleaved x{world}, one all_gather per frame" if world > 1 else "single GPU",
                 "scaling_note": "N > 1 renders ONE fixed frame (3840x2160, 256 spp) at every N; the N = 1 line is configs[2] and carries the fixed frame as scaling_reference",
-                "l2": "no flush needed: every step re-traces the whole frame, streaming ~270 GB through HBM (path / shadow queue entries of the paths that leave registers + the accumulator buffer, cleared per step), far more than the 126 MB L2; only the 4 MB scene + LBVH is meant to stay cache-resident",
+                "launch_mode": "kernel-by-kernel launches with CUDA events around k_traverse / k_shade (the library's own mode for pools above 16 Mi slots, pinned with RTB_NO_GRAPH=1); the configs block uses the library defaults (CUDA-graph replay for its small frames)", "l2": "no flush needed: every step re-traces the whole frame, streaming ~270 GB through HBM (path / shadow queue entries of the paths that leave registers + the accumulator buffer, cleared per step), far more than the 126 MB L2; only the 4 MB scene + LBVH is meant to stay cache-resident",
                 "timing": "host clock between barrier + torch.cuda.synchronize brackets (rtb_render_device returns synchronised), max over ranks; device_ms_per_step = CUDA events on the render stream"},
             "mrays_per_s": rays / elapsed / 1e6,
             "rays_per_sample": rays / max(1.0, job["samples"]),

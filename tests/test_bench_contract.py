@@ -27,3 +27,25 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_rtb200_arm_line_has_the_contract_keys():
+    # a reduced-spp run (debug flag, invalid as a bench number) is enough to check the SHAPE of the line the driver parses
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--spp", "8", "--no-configs", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 3 and d["value"] > 0 and d["gpu_launches"] > 0
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "issue" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert set(d["config"]) >= {"workload", "width", "height", "spp"}
