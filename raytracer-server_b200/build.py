@@ -27,6 +27,13 @@ def _deps(src: str) -> list[str]:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    # the objects depend on the flags too: a change of RTB_NVCC_EXTRA alone must rebuild (an experiment that silently measured
+    # the previous binary is worse than a slow build)
+    stamp, flags = os.path.join(OBJ, "flags.txt"), " ".join([*ARCH, *COMMON, *EXTRA])
+    if not os.path.exists(stamp) or open(stamp).read() != flags:
+        force = True
+        with open(stamp, "w") as f:
+            f.write(flags)
     objs = []
     for src in SOURCES:
         obj = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
