@@ -81,7 +81,9 @@ struct RenderContext {
     cudaGraphExec_t graph_exec[4] = {nullptr, nullptr, nullptr, nullptr};   // one iteration (4 kernels) for cur = 0 / 1; [2], [3]: the same with the inline-tail k_shade ...
     std::vector<unsigned char> graph_args;                 // ... captured for exactly these kernel arguments
     int grid_shade_nomesh = 0;   // grid of the mesh-less k_shade instantiation (160-thread CTAs)
-    int trav_minb = 4;   // CTAs per SM the launched k_traverse instantiation was compiled for (RTB_TRAV_MINB = 4 | 5 | 6)
+    int trav_minb = 5;   // CTAs per SM the launched k_traverse instantiation was compiled for (RTB_TRAV_MINB = 4 | 5 | 6).  5 since the
+                         // SAH tree (51 registers, a few spills, 40 warps per SM): bench frame 540.4 -> 537.0 ms; on the PLOC tree 4 was ahead
+    int grid_oct = 0;    // k_traverse_octree's own persistent grid
     int grid_ext = 0, grid_ext_count = 0, grid_sh = 0, grid_sh_count = 0, grid_gen = 0, grid_shade = 0, grid_bin = 0;
 
     ~RenderContext() {
@@ -504,6 +506,7 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         CU_TRY(cudaFuncSetAttribute(k_shade<1, 0, 0, true, SHADE_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tail));
         CU_TRY(cudaFuncSetAttribute(k_shade<2, 0, 0, true, SHADE_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tail));
         int b = 0;
+        if (sc->view.wide) c->trav_minb = 4;   // the 4-wide experiment table has one instantiation only
         if (const char* e = getenv("RTB_TRAV_MINB")) c->trav_minb = atoi(e) == 5 ? 5 : (atoi(e) == 6 ? 6 : 4);
         if (c->trav_minb == 5) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 5>, WF_THREADS, smem_stack));
         else if (c->trav_minb == 6) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<false, 6>, WF_THREADS, smem_stack));
@@ -513,6 +516,8 @@ int ensure_context(rtb_scene* sc, RenderContext* c, uint32_t P, uint32_t SP, siz
         if (sc->view.wide) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true, 4, true>, WF_THREADS, smem_stack));
         else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse<true>, WF_THREADS, smem_stack));
         c->grid_ext_count = std::max(1, b) * prop.multiProcessorCount;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_traverse_octree<false>, WF_THREADS, (size_t)OCT_MAX_DEPTH * WF_THREADS * sizeof(int2)));
+        c->grid_oct = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<0>, SHADE_THREADS, smem_tab));
         c->grid_shade = std::max(1, b) * prop.multiProcessorCount;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<1, 5, 3, false, SHADE_THREADS_NOMESH>, SHADE_THREADS_NOMESH, smem_tab));
@@ -641,10 +646,10 @@ int default_bin_bits() {
 // every mesh query of one iteration: the LBVH kernel (the product's fast path) or the reference's octrees
 void launch_traverse(RenderContext* c, const RenderArgs& a, int cur, bool count_work, size_t smem_stack) {
     if (a.accel == RTB_ACCEL_OCTREE_REFERENCE) {
-        // persistent like k_traverse (same grid, same work cursor); shared memory = the per-thread stack of parent nodes
+        // persistent like k_traverse (its own grid, the same work cursor); shared memory = the per-thread stack of parent nodes
         const size_t smem_oct = (size_t)OCT_MAX_DEPTH * WF_THREADS * sizeof(int2);
-        if (count_work) k_traverse_octree<true><<<c->grid_ext_count, WF_THREADS, smem_oct, c->stream>>>(a, cur);
-        else k_traverse_octree<false><<<c->grid_ext, WF_THREADS, smem_oct, c->stream>>>(a, cur);
+        if (count_work) k_traverse_octree<true><<<c->grid_oct, WF_THREADS, smem_oct, c->stream>>>(a, cur);
+        else k_traverse_octree<false><<<c->grid_oct, WF_THREADS, smem_oct, c->stream>>>(a, cur);
     } else if (count_work && a.S.wide) k_traverse<true, 4, true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
     else if (count_work) k_traverse<true><<<c->grid_ext_count, WF_THREADS, smem_stack, c->stream>>>(a, cur);
     else if (a.S.wide && c->trav_minb == 4) k_traverse<false, 4, true><<<c->grid_ext, WF_THREADS, smem_stack, c->stream>>>(a, cur);
@@ -783,7 +788,7 @@ static void launch_shade(int mode, int n_planes, int n_spheres, int grid, size_t
 int run_wavefront(rtb_scene* sc, RenderContext* c, RenderArgs& a, uint32_t ks_begin, uint32_t ks_end, bool count_work,
                   volatile int* cancel, rtb_stats& st, bool& cancelled) {
     cancelled = false;
-    a.trav_warps = (uint32_t)(count_work ? c->grid_ext_count : c->grid_ext) * (WF_THREADS / 32);   // must match the launched grid
+    a.trav_warps = (uint32_t)(a.accel == RTB_ACCEL_OCTREE_REFERENCE ? c->grid_oct : (count_work ? c->grid_ext_count : c->grid_ext)) * (WF_THREADS / 32);   // must match the launched grid
     a.shade_warps = (uint32_t)c->grid_shade * (SHADE_THREADS / 32);
     DevCtrl h{};
     h.ext_head(0) = h.ext_head(1) = 0;
