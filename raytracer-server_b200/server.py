@@ -37,7 +37,7 @@ DEFAULT_PORT = "8080"                                      # src/main.rs:16
 
 def default_job_factory(scenes: dict, width: int, height: int, accel: int = 0):
     """accel: 0 = LBVH (true nearest hit, the fast path), 1 = the reference's own octrees (ACCEL_OCTREE_REFERENCE: the image the
-    Rust binary sends, non-nearest triangles included; 5 x slower on flying_unicorn).  `main` reads it from $RTB_ACCEL."""
+    Rust binary sends, non-nearest triangles included; 2.4 x slower on flying_unicorn).  `main` reads it from $RTB_ACCEL."""
     from .host import RenderJob
 
     def make(scene_name: str, spp: int, passes: int = 1):
